@@ -1,0 +1,226 @@
+// C-ABI glue (include/dfvo_b200.h).  No torch types, no exceptions across the boundary.
+#include "../../include/dfvo_b200.h"
+
+#include <string.h>
+
+#include <new>
+
+#include "liteflownet.h"
+#include "net_common.h"
+
+namespace dfvo { const char* last_error(); }
+
+using namespace dfvo;
+
+struct dfvo_ctx {
+  int device = 0;
+  WeightStore weights[2];
+  LiteFlowNetBase* lfn = nullptr;
+};
+
+#define API_BEGIN try {
+#define API_END                                                     \
+  } catch (const std::bad_alloc&) {                                 \
+    dfvo::set_error("host allocation failed");                      \
+    return DFVO_ENOMEM;                                             \
+  } catch (...) {                                                   \
+    dfvo::set_error("unexpected C++ exception");                    \
+    return DFVO_EINVAL;                                             \
+  }
+
+template <typename T>
+static int stage_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int stride,
+                             int leaky, cudaStream_t s) {
+  Arena a;
+  const int Cp = (C + 15) / 16 * 16;
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  float* f32a = a.alloc_t<float>((size_t)B * H * W * Cp);
+  float* f32b = a.alloc_t<float>((size_t)B * H * W * Cp);
+  T* ta = a.alloc_t<T>((size_t)B * H * W * Cp);
+  T* tb = a.alloc_t<T>((size_t)B * H * W * Cp);
+  T* to = a.alloc_t<T>((size_t)B * Ho * Wo * 64);
+  if (!f32a || !f32b || !ta || !tb || !to) return DFVO_ENOMEM;
+  Ten<float> A = make_ten<float>(f32a, B, H, W, Cp, Cp), Bn = make_ten<float>(f32b, B, H, W, Cp, Cp);
+  int rc;
+  if ((rc = nchw_to_nhwc_f32(first, B, C, H, W, A, s))) return rc;
+  if ((rc = nchw_to_nhwc_f32(second, B, C, H, W, Bn, s))) return rc;
+  Ten<T> TA = make_ten<T>(ta, B, H, W, C, Cp), TB = make_ten<T>(tb, B, H, W, C, Cp);
+  Ten<float> Ac = A, Bc = Bn; Ac.C = C; Bc.C = C;
+  if ((rc = convert_copy<float, T>(cten(Ac), TA, s))) return rc;
+  if ((rc = convert_copy<float, T>(cten(Bc), TB, s))) return rc;
+  Ten<T> TO = make_ten<T>(to, B, Ho, Wo, 64, 64);
+  if ((rc = correlation49<T>(cten(TA), cten(TB), 0, stride, leaky, TO, s))) return rc;
+  Ten<T> TO49 = TO; TO49.C = 49;
+  if ((rc = nhwc_to_nchw<T>(cten(TO49), out, s))) return rc;
+  DFVO_CUDA(cudaStreamSynchronize(s));
+  return DFVO_OK;
+}
+
+template <typename T>
+static int stage_warp(const float* input, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  Arena a;
+  float* f32 = a.alloc_t<float>((size_t)B * H * W * C);
+  float* fl = a.alloc_t<float>((size_t)B * H * W * 2);
+  T* ti = a.alloc_t<T>((size_t)B * H * W * C);
+  T* to = a.alloc_t<T>((size_t)B * H * W * C);
+  if (!f32 || !fl || !ti || !to) return DFVO_ENOMEM;
+  int rc;
+  Ten<float> I = make_ten<float>(f32, B, H, W, C, C), Fl = make_ten<float>(fl, B, H, W, 2, 2);
+  if ((rc = nchw_to_nhwc_f32(input, B, C, H, W, I, s))) return rc;
+  if ((rc = nchw_to_nhwc_f32(flow, B, 2, H, W, Fl, s))) return rc;
+  Ten<T> TI = make_ten<T>(ti, B, H, W, C, C), TO = make_ten<T>(to, B, H, W, C, C);
+  if ((rc = convert_copy<float, T>(cten(I), TI, s))) return rc;
+  if ((rc = warp_bilinear<T>(cten(TI), cten(Fl), 1.0f, 0, TO, s))) return rc;
+  if ((rc = nhwc_to_nchw<T>(cten(TO), out, s))) return rc;
+  DFVO_CUDA(cudaStreamSynchronize(s));
+  return DFVO_OK;
+}
+
+template <typename T>
+static int stage_conv(const float* x, const HostTensor& w, const HostTensor* b, float* y, int B, int Cin, int H, int W, int Cout,
+                      int kh, int kw, int stride, int pad_y, int pad_x, int reflect, int act, cudaStream_t s) {
+  Arena a;
+  const bool is_bf16 = sizeof(T) == 2;
+  const int Cp = (Cin + 15) / 16 * 16, Cop = (Cout + 15) / 16 * 16;
+  const int Ho = (H + 2 * pad_y - kh) / stride + 1, Wo = (W + 2 * pad_x - kw) / stride + 1;
+  ConvLayer L;
+  int rc;
+  if ((rc = build_conv_layer(a, w, b, {{Cin, Cp}}, stride, pad_y, pad_x, reflect, is_bf16, !is_bf16, nullptr, nullptr, &L))) return rc;
+  float* f32 = a.alloc_t<float>((size_t)B * H * W * Cp);
+  T* ti = a.alloc_t<T>((size_t)B * H * W * Cp);
+  T* to = a.alloc_t<T>((size_t)B * Ho * Wo * Cop);
+  if (!f32 || !ti || !to) return DFVO_ENOMEM;
+  Ten<float> I = make_ten<float>(f32, B, H, W, Cp, Cp);
+  if ((rc = nchw_to_nhwc_f32(x, B, Cin, H, W, I, s))) return rc;
+  Ten<T> TI = make_ten<T>(ti, B, H, W, Cp, Cp);
+  if ((rc = convert_copy<float, T>(cten(I), TI, s))) return rc;
+  Ten<T> TO = make_ten<T>(to, B, Ho, Wo, Cout, Cop);
+  Ten<const T> none; memset(&none, 0, sizeof(none));
+  if ((rc = run_conv<T>(L, cten(TI), TO, act, none, 0, s))) return rc;
+  if ((rc = nhwc_to_nchw<T>(cten(TO), y, s))) return rc;
+  DFVO_CUDA(cudaStreamSynchronize(s));
+  return DFVO_OK;
+}
+
+extern "C" {
+
+const char* dfvo_last_error(void) { return dfvo::last_error(); }
+const char* dfvo_version(void) { return "dfvo_b200 0.1 (sm_100a)"; }
+int dfvo_is_device_build(void) {
+#ifdef DFVO_HOSTSIM
+  return 0;
+#else
+  return 1;
+#endif
+}
+
+int dfvo_create(dfvo_ctx** out, int device) {
+  API_BEGIN
+  DFVO_REQUIRE(out != nullptr, DFVO_EINVAL, "dfvo_create: null out");
+  DFVO_CUDA(cudaSetDevice(device));
+  *out = new dfvo_ctx();
+  (*out)->device = device;
+  return DFVO_OK;
+  API_END
+}
+
+int dfvo_destroy(dfvo_ctx* ctx) {
+  API_BEGIN
+  if (!ctx) return DFVO_OK;
+  delete ctx->lfn;
+  delete ctx;
+  return DFVO_OK;
+  API_END
+}
+
+int dfvo_load_weight(dfvo_ctx* ctx, int net, const char* key, const float* data, const int64_t* shape, int ndim) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && key && data && (net == 0 || net == 1) && ndim >= 0 && ndim <= 4, DFVO_EINVAL, "dfvo_load_weight args");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(data, data + n);
+  ctx->weights[net][key] = std::move(t);
+  return DFVO_OK;
+  API_END
+}
+
+int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int precision) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && pairs >= 1 && (precision == 0 || precision == 1), DFVO_EINVAL, "dfvo_liteflow_build args");
+  DFVO_CUDA(cudaSetDevice(ctx->device));
+  delete ctx->lfn;
+  ctx->lfn = nullptr;
+  return liteflownet_create(ctx->weights[DFVO_NET_LITEFLOWNET], height, width, pairs, precision, &ctx->lfn);
+  API_END
+}
+
+int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs, float* flow_fwd, float* flow_bwd, float* flow_diff,
+                          void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && ctx->lfn && imgs, DFVO_ESTATE, "dfvo_liteflow_forward: call dfvo_liteflow_build first");
+  return ctx->lfn->run(imgs, flow_fwd, flow_bwd, flow_diff, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_liteflow_level_flow(dfvo_ctx* ctx, int level, float* out) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && ctx->lfn && out, DFVO_ESTATE, "dfvo_liteflow_level_flow: no plan");
+  return ctx->lfn->debug_level_flow(level, 0, out);
+  API_END
+}
+
+int dfvo_liteflow_geometry(dfvo_ctx* ctx, int* net_h, int* net_w, int* batch) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && ctx->lfn, DFVO_ESTATE, "dfvo_liteflow_geometry: no plan");
+  ctx->lfn->geometry(net_h, net_w, batch);
+  return DFVO_OK;
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points: NCHW fp32 at the boundary, converted to the internal NHWC layout here
+// ------------------------------------------------------------------------------------------------
+
+int dfvo_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int stride, int leaky,
+                     int precision, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(first && second && out && B > 0 && C > 0 && H > 0 && W > 0, DFVO_EINVAL, "dfvo_correlation args");
+  if (precision == DFVO_PREC_FP32) return stage_correlation<float>(first, second, out, B, C, H, W, stride, leaky, (cudaStream_t)stream);
+  return stage_correlation<bf16>(first, second, out, B, C, H, W, stride, leaky, (cudaStream_t)stream);
+  API_END
+}
+
+
+int dfvo_backward_warp(const float* input, const float* flow, float* out, int B, int C, int H, int W, int precision, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(input && flow && out && B > 0 && C > 0 && H > 0 && W > 0, DFVO_EINVAL, "dfvo_backward_warp args");
+  if (precision == DFVO_PREC_FP32) return stage_warp<float>(input, flow, out, B, C, H, W, (cudaStream_t)stream);
+  return stage_warp<bf16>(input, flow, out, B, C, H, W, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_fb_consistency(const float* flow_fwd, const float* flow_bwd, float* diff, int H, int W, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(flow_fwd && flow_bwd && diff && H > 1 && W > 1, DFVO_EINVAL, "dfvo_fb_consistency args");
+  return fb_consistency(flow_fwd, flow_bwd, H, W, diff, (cudaStream_t)stream);
+  API_END
+}
+
+
+int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int H, int W, int Cout, int kh,
+                int kw, int stride, int pad_y, int pad_x, int reflect, int act, int precision, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(x && w_host && y && B > 0 && Cin > 0 && Cout > 0, DFVO_EINVAL, "dfvo_conv2d args");
+  HostTensor w, b;
+  w.shape = {Cout, Cin, kh, kw};
+  w.data.assign(w_host, w_host + (size_t)Cout * Cin * kh * kw);
+  if (bias_host) { b.shape = {Cout}; b.data.assign(bias_host, bias_host + Cout); }
+  if (precision == DFVO_PREC_FP32)
+    return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
+  DFVO_REQUIRE(stride == 1 && !reflect, DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1 and zero padding");
+  return stage_conv<bf16>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
+  API_END
+}
+
+}  // extern "C"

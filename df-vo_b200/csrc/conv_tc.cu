@@ -1,0 +1,477 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (stride 1, arbitrary tap set, up to 3 virtually
+// concatenated NHWC bf16 sources, fused bias + activation + residual epilogue).
+//
+// GEMM view:  D[128 pixels, BLOCK_N couts] += sum over (tap, source, 64-channel chunk) of
+//             A[128 pixels, 64 ch] * B[BLOCK_N couts, 64 ch]^T        (bf16 x bf16 -> fp32 in TMEM)
+//   * A tile = one TMA 4-D box {64 ch, tw, th, 1} of the NHWC source at pixel offset (dx,dy) of the
+//     tap: the box lands in shared memory as 128 rows x 128 B, K-major, 128-B swizzled -- exactly
+//     the canonical UMMA operand layout, so there is no im2col pass; out-of-image rows/columns
+//     (the convolution's zero padding) and channels beyond the source's C are zero-filled by TMA.
+//   * B tile = TMA 3-D box {64 k, BLOCK_N, 1 tap} of the packed weights [tap][Cout_pad][Ktot].
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread issues tcgen05.mma, accumulators
+//     double-buffered in TMEM), warps 2-5 = epilogue (tcgen05.ld -> bias/act/residual -> global).
+//   * persistent CTAs, static round-robin tile schedule, mbarrier full/empty smem ring.
+// Restates torch.nn.Conv2d(stride=1) + LeakyReLU/ELU/ReLU as used at lite_flow_net.py:98-240 and
+// depth_decoder.py / torchvision BasicBlock (BN folded by the weight packer).
+#include "ops.h"
+
+#ifndef DFVO_HOSTSIM
+#include <cuda.h>
+#endif
+#include <string.h>
+
+namespace dfvo {
+
+void conv_tc_tile_shape(int H, int W, int* tw, int* th) {
+  // 128 pixels per tile as tw x th (powers of two); minimise padded area, prefer wide tiles.
+  long long best = -1;
+  int bw = 128, bh = 1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    int h = 128 / w;
+    long long area = (long long)cdiv(W, w) * w * (long long)cdiv(H, h) * h;
+    if (best < 0 || area < best) { best = area; bw = w; bh = h; }
+  }
+  *tw = bw; *th = bh;
+}
+
+struct ConvTcK {
+  int N, H, W, tw, th, tiles_x, tiles_y, n_blocks, ntiles;
+  int nsrc, srcC[3];
+  int ntaps;
+  int8_t dy[49], dx[49];
+  int block_n, stages, acc_stride, tmem_cols;
+  int Cout, Cout_pad, act, out_f32, zero_pad_to;
+  const float* bias;
+  void* out; long long oN, oH, oW;
+  const void* res; long long rN, rH, rW;
+};
+
+#ifndef DFVO_HOSTSIM
+// =============================================================================================
+//                                       device side
+// =============================================================================================
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+}  // namespace tc
+
+#define TC_THREADS 192
+#define TC_A_BYTES 16384
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ ConvTcK p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.block_n * 128u;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;    // 8-byte aligned
+  // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * p.stages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)p.stages * stage_bytes + 8u * (2 * p.stages + 4));
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.Cout_pad; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int chunks_total = 0;
+  for (int s = 0; s < p.nsrc; ++s) chunks_total += (p.srcC[s] + 63) >> 6;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int n = t % p.N; const int nb = t / p.N;
+        const int x0 = tx * p.tw, y0 = ty * p.th;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          int kofs = 0;
+          for (int s = 0; s < p.nsrc; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+            for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_4d(sa, tm, full_bar(stage), c0, x0 + p.dx[tap], y0 + p.dy[tap], n);
+              tma_load_3d(sa + TC_A_BYTES, &tmB, full_bar(stage), kofs + c0, nb * p.block_n, tap);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            kofs += p.srcC[s];
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =========================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int s = 0; s < p.nsrc; ++s) {
+            for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+              const uint64_t adesc = make_desc_sw128(sa);
+              const uint64_t bdesc = make_desc_sw128(sa + TC_A_BYTES);
+              int rem = p.srcC[s] - c0;
+              const int nks = (rem >= 64 ? 64 : rem) >> 4;       // K=16 steps with real channels
+              for (int ks = 0; ks < nks; ++ks) {
+                // advance 32 B (= 16 bf16) inside the 128-B swizzle atom: +2 in 16-byte units
+                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, accumulate);
+                accumulate = 1;
+              }
+              tc_commit(empty_bar(stage));
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps ====================================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int n = t % p.N; const int nb = t / p.N;
+      const int x = tx * p.tw + (row % p.tw), y = ty * p.th + (row / p.tw);
+      const bool inb = x < p.W && y < p.H;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+      const int cbase = nb * p.block_n;
+      for (int col = 0; col < p.block_n; col += 16) {
+        uint32_t v[16];
+        __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
+        tc_ld16(taddr0 + (uint32_t)col, v);
+        const int c = cbase + col;
+        if (inb && c < p.zero_pad_to) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias_s[c + j];
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + n * p.oN + y * p.oH + x * p.oW + c;
+          const float* r = p.res ? reinterpret_cast<const float*>(p.res) + n * p.rN + y * p.rH + x * p.rW + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c + j < p.Cout) {
+              float val = f[j] + (r ? r[j] : 0.f);
+              o[j] = apply_act(val, p.act);
+            } else if (c + j < p.zero_pad_to) {
+              o[j] = 0.f;
+            }
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + n * p.oN + y * p.oH + x * p.oW + c;
+          const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + n * p.rN + y * p.rH + x * p.rW + c : nullptr;
+          const bool full = (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
+                            (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
+          if (full) {
+            if (r) {
+              uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[2 * j] += __uint_as_float(rw[j] << 16);
+                f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+              }
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c + j < p.Cout) {
+                float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
+                o[j] = __float2bfloat16_rn(apply_act(val, p.act));
+              } else if (c + j < p.zero_pad_to) {
+                o[j] = __float2bfloat16_rn(0.f);
+              }
+            }
+          }
+        }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// =============================================================================================
+//                                        host side
+// =============================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  DFVO_REQUIRE(enc != nullptr, DFVO_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFVO_REQUIRE(r == CUDA_SUCCESS, DFVO_ECUDA, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r,
+               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+  return DFVO_OK;
+}
+
+struct ConvTcPlanImpl {
+  CUtensorMap tmA[3], tmB;
+  ConvTcK k;
+  int grid;
+  size_t smem;
+};
+
+static int g_num_sms = 0;
+
+static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
+  DFVO_REQUIRE(c.nsrc >= 1 && c.nsrc <= 3 && c.ntaps >= 1 && c.ntaps <= 49, DFVO_EINVAL, "conv_tc: nsrc/ntaps");
+  DFVO_REQUIRE(c.Cout_pad % 16 == 0 && c.Cout_pad >= 16, DFVO_EINVAL, "conv_tc: Cout_pad %d must be a multiple of 16", c.Cout_pad);
+  ConvTcK& k = pl->k;
+  memset(&k, 0, sizeof(k));
+  k.N = c.N; k.H = c.H; k.W = c.W;
+  conv_tc_tile_shape(c.H, c.W, &k.tw, &k.th);
+  k.tiles_x = cdiv(c.W, k.tw); k.tiles_y = cdiv(c.H, k.th);
+  // N tile: whole Cout_pad if <= 256 else 128-wide blocks
+  k.block_n = c.Cout_pad <= 256 ? c.Cout_pad : 128;
+  DFVO_REQUIRE(c.Cout_pad % k.block_n == 0, DFVO_EINVAL, "conv_tc: Cout_pad %d not divisible by block_n %d", c.Cout_pad, k.block_n);
+  k.n_blocks = c.Cout_pad / k.block_n;
+  k.ntiles = k.tiles_x * k.tiles_y * c.N * k.n_blocks;
+  k.nsrc = c.nsrc; k.ntaps = c.ntaps;
+  int ktot = 0;
+  for (int s = 0; s < c.nsrc; ++s) {
+    DFVO_REQUIRE(c.src[s].C % 16 == 0 && c.src[s].C > 0, DFVO_EINVAL, "conv_tc: source %d channels %d not a multiple of 16", s, c.src[s].C);
+    DFVO_REQUIRE(((uintptr_t)c.src[s].p & 15) == 0 && c.src[s].sW % 8 == 0 && c.src[s].sH % 8 == 0 && c.src[s].sN % 8 == 0,
+                 DFVO_EINVAL, "conv_tc: source %d not 16-byte aligned/strided", s);
+    k.srcC[s] = c.src[s].C; ktot += c.src[s].C;
+  }
+  memcpy(k.dy, c.dy, sizeof(k.dy)); memcpy(k.dx, c.dx, sizeof(k.dx));
+  k.Cout = c.Cout; k.Cout_pad = c.Cout_pad; k.act = c.act; k.out_f32 = c.out_f32;
+  k.zero_pad_to = c.zero_pad_to > c.Cout ? c.zero_pad_to : c.Cout;
+  k.bias = c.bias; k.out = c.out; k.oN = c.oN; k.oH = c.oH; k.oW = c.oW;
+  k.res = c.residual; k.rN = c.rN; k.rH = c.rH; k.rW = c.rW;
+  // TMEM: two accumulators of block_n columns
+  int acc_stride = 32; while (acc_stride < k.block_n) acc_stride <<= 1;
+  k.acc_stride = acc_stride; k.tmem_cols = 2 * acc_stride;
+  const size_t stage_bytes = TC_A_BYTES + (size_t)k.block_n * 128;
+  const size_t fixed = 1024 /*align slack*/ + 8 * 64 /*barriers*/ + 64 + (size_t)c.Cout_pad * 4;
+  int stages = (int)((200 * 1024 - fixed) / stage_bytes);
+  if (stages > 8) stages = 8;
+  DFVO_REQUIRE(stages >= 2, DFVO_EINVAL, "conv_tc: tile does not fit in shared memory");
+  k.stages = stages;
+  pl->smem = fixed + (size_t)stages * stage_bytes;
+  if (!g_num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  pl->grid = k.ntiles < g_num_sms ? k.ntiles : g_num_sms;
+  // tensor maps
+  for (int s = 0; s < 3; ++s) {
+    const ConvTcSource& src = c.src[s < c.nsrc ? s : 0];
+    cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+    cuuint64_t str[3] = {(cuuint64_t)src.sW * 2, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sN * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)k.tw, (cuuint32_t)k.th, 1};
+    int rc = encode_map(&pl->tmA[s], src.p, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)c.Cout_pad, (cuuint64_t)c.ntaps};
+    cuuint64_t str[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * 2 * (cuuint64_t)c.Cout_pad};
+    cuuint32_t box[3] = {64, (cuuint32_t)k.block_n, 1};
+    int rc = encode_map(&pl->tmB, c.w, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  return DFVO_OK;
+}
+
+int conv_tc(const ConvTc& c, cudaStream_t s) {
+  ConvTcPlanImpl pl;
+  int rc = build_plan(c, &pl);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  k_conv_tc<<<pl.grid, TC_THREADS, pl.smem, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+#else  // DFVO_HOSTSIM ---------------------------------------------------------------------------
+// CPU test build only: consumes the SAME ConvTc description and packed weights as the device
+// kernel and applies the same TMA semantics (zero fill outside the image / beyond a source's C,
+// virtual concat of sources, tap offsets), so the layer wiring and the weight packer can be
+// validated without a GPU.  Never compiled into the product library.
+int conv_tc(const ConvTc& c, cudaStream_t) {
+  int ktot = 0;
+  for (int s = 0; s < c.nsrc; ++s) ktot += c.src[s].C;
+  int zp = c.zero_pad_to > c.Cout ? c.zero_pad_to : c.Cout;
+  std::vector<float> acc(c.Cout_pad);
+  for (int n = 0; n < c.N; ++n)
+    for (int y = 0; y < c.H; ++y)
+      for (int x = 0; x < c.W; ++x) {
+        for (int co = 0; co < c.Cout_pad; ++co) acc[co] = 0.f;
+        for (int t = 0; t < c.ntaps; ++t) {
+          int iy = y + c.dy[t], ix = x + c.dx[t];
+          if (iy < 0 || iy >= c.H || ix < 0 || ix >= c.W) continue;
+          int kofs = 0;
+          for (int s = 0; s < c.nsrc; ++s) {
+            const bf16* a = c.src[s].p + n * c.src[s].sN + iy * c.src[s].sH + ix * c.src[s].sW;
+            for (int ci = 0; ci < c.src[s].C; ++ci) {
+              float av = __bfloat162float(a[ci]);
+              if (av == 0.f) continue;
+              const bf16* w = c.w + ((size_t)t * c.Cout_pad) * ktot + kofs + ci;
+              for (int co = 0; co < c.Cout_pad; ++co) acc[co] += av * __bfloat162float(w[(size_t)co * ktot]);
+            }
+            kofs += c.src[s].C;
+          }
+        }
+        for (int co = 0; co < zp; ++co) {
+          float v = 0.f;
+          if (co < c.Cout) {
+            v = acc[co] + (c.bias ? c.bias[co] : 0.f);
+            if (c.residual) {
+              if (c.out_f32) v += ((const float*)c.residual)[n * c.rN + y * c.rH + x * c.rW + co];
+              else v += __bfloat162float(((const bf16*)c.residual)[n * c.rN + y * c.rH + x * c.rW + co]);
+            }
+            v = apply_act(v, c.act);
+          }
+          if (c.out_f32) ((float*)c.out)[n * c.oN + y * c.oH + x * c.oW + co] = v;
+          else ((bf16*)c.out)[n * c.oN + y * c.oH + x * c.oW + co] = __float2bfloat16_rn(v);
+        }
+      }
+  return DFVO_OK;
+}
+#endif
+
+}  // namespace dfvo

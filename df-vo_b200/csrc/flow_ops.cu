@@ -1,0 +1,557 @@
+// Memory-bound kernels of the LiteFlowNet path: image prep / resizes, depthwise deconv, backward
+// warp, 49-channel correlation, Regularization prep + tail, final flow upsample and the
+// forward-backward consistency map.  Reference lines are cited per kernel; layouts are NHWC.
+#include "ops.h"
+
+namespace dfvo {
+
+// ---------------------------------------------------------------------------------------------
+// bilinear helpers (torch upsample_bilinear2d semantics)
+// ---------------------------------------------------------------------------------------------
+struct Lerp { int i0, i1; float l0, l1; };
+
+DFVO_D Lerp lerp_coord(int dst, int in_size, int out_size, int align_corners) {
+  Lerp r;
+  float src;
+  if (align_corners) {
+    float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+    src = scale * (float)dst;
+  } else {
+    float scale = (float)in_size / (float)out_size;
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  r.i0 = (int)src;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+// deep_models.py:160-163 (img/255 in float64 -> float32) + lite_flow.py:72-76 (bilinear, AC=True)
+__global__ void k_prep_image_u8(const uint8_t* __restrict__ img, int H0, int W0, Ten<float> out, int n) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= out.W) return;
+  Lerp ly = lerp_coord(y, H0, out.H, 1), lx = lerp_coord(x, W0, out.W, 1);
+  float* o = out.at(n, y, x);
+  for (int c = 0; c < 3; ++c) {
+    float v00 = (float)((double)img[((size_t)ly.i0 * W0 + lx.i0) * 3 + c] / 255.0);
+    float v01 = (float)((double)img[((size_t)ly.i0 * W0 + lx.i1) * 3 + c] / 255.0);
+    float v10 = (float)((double)img[((size_t)ly.i1 * W0 + lx.i0) * 3 + c] / 255.0);
+    float v11 = (float)((double)img[((size_t)ly.i1 * W0 + lx.i1) * 3 + c] / 255.0);
+    o[c] = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+  }
+  for (int c = 3; c < out.C; ++c) o[c] = 0.f;
+}
+
+int prep_image_u8(const uint8_t* img, int H0, int W0, Ten<float> out, int n, cudaStream_t s) {
+  dim3 block(128), grid(cdiv(out.W, 128), out.H);
+  DFVO_LAUNCH(k_prep_image_u8, grid, block, 0, s, img, H0, W0, out, n);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+__global__ void k_resize_bilinear_f32(Ten<const float> in, Ten<float> out, int ac) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.W) return;
+  Lerp ly = lerp_coord(y, in.H, out.H, ac), lx = lerp_coord(x, in.W, out.W, ac);
+  const float* p00 = in.at(n, ly.i0, lx.i0);
+  const float* p01 = in.at(n, ly.i0, lx.i1);
+  const float* p10 = in.at(n, ly.i1, lx.i0);
+  const float* p11 = in.at(n, ly.i1, lx.i1);
+  float* o = out.at(n, y, x);
+  for (int c = 0; c < in.C; ++c)
+    o[c] = ly.l0 * (lx.l0 * p00[c] + lx.l1 * p01[c]) + ly.l1 * (lx.l0 * p10[c] + lx.l1 * p11[c]);
+  for (int c = in.C; c < out.C; ++c) o[c] = 0.f;
+}
+
+int resize_bilinear_f32(Ten<const float> in, Ten<float> out, int align_corners, cudaStream_t s) {
+  dim3 block(128), grid(cdiv(out.W, 128), out.H, out.N);
+  DFVO_LAUNCH(k_resize_bilinear_f32, grid, block, 0, s, in, out, align_corners);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise ConvTranspose2d(k=4, s=2, p=1, groups=C, bias=False)  (lite_flow_net.py:109,117)
+// out[oy] += in[iy] * w[ky] with oy = 2*iy - 1 + ky
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_deconv4x4s2_dw(Ten<const T> in, const float* __restrict__ w, Ten<T> out) {
+  int c = threadIdx.x % out.C, xi = threadIdx.x / out.C;
+  int px_per_block = blockDim.x / out.C;
+  int x = blockIdx.x * px_per_block + xi;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (xi >= px_per_block || x >= out.W) return;
+  float acc = 0.f;
+  if (c < in.C) {
+    int ky0 = (y + 1) & 1, kx0 = (x + 1) & 1;
+    for (int a = 0; a < 2; ++a) {
+      int ky = ky0 + 2 * a;
+      int iy = (y + 1 - ky) / 2;
+      if ((y + 1 - ky) < 0 || iy >= in.H) continue;
+      for (int b = 0; b < 2; ++b) {
+        int kx = kx0 + 2 * b;
+        int ix = (x + 1 - kx) / 2;
+        if ((x + 1 - kx) < 0 || ix >= in.W) continue;
+        acc += to_f(in.at(n, iy, ix)[c]) * w[c * 16 + ky * 4 + kx];
+      }
+    }
+  }
+  out.at(n, y, x)[c] = from_f<T>(acc);
+}
+
+template <typename T>
+int deconv4x4s2_dw(Ten<const T> in, const float* w, Ten<T> out, cudaStream_t s) {
+  DFVO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C <= 256, DFVO_ESHAPE, "deconv4x4s2 shape");
+  int ppb = 256 / out.C;
+  if (ppb < 1) ppb = 1;
+  dim3 block(ppb * out.C), grid(cdiv(out.W, ppb), out.H, out.N);
+  auto k = k_deconv4x4s2_dw<T>;
+  DFVO_LAUNCH(k, grid, block, 0, s, in, w, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int deconv4x4s2_dw<float>(Ten<const float>, const float*, Ten<float>, cudaStream_t);
+template int deconv4x4s2_dw<bf16>(Ten<const bf16>, const float*, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// Backward warp: bilinear gather, zeros padding, pixel coords (x+fx*scale, y+fy*scale)
+// (lite_flow_net.py:10-28 under the pinned align_corners=True semantics)
+// ---------------------------------------------------------------------------------------------
+struct Bil { int x0, y0; float w00, w01, w10, w11; };   // weights already zeroed when out of bounds
+
+DFVO_D Bil bilinear_zeros(float px, float py, int W, int H) {
+  Bil b;
+  float fx0 = floorf(px), fy0 = floorf(py);
+  b.x0 = (int)fx0; b.y0 = (int)fy0;
+  float wx1 = px - fx0, wy1 = py - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  bool xin0 = b.x0 >= 0 && b.x0 <= W - 1, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 <= W - 1;
+  bool yin0 = b.y0 >= 0 && b.y0 <= H - 1, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 <= H - 1;
+  // non-finite coordinates sample nothing
+  bool fin = (px == px) && (py == py) && fabsf(px) < 1e9f && fabsf(py) < 1e9f;
+  b.w00 = (fin && xin0 && yin0) ? wx0 * wy0 : 0.f;
+  b.w01 = (fin && xin1 && yin0) ? wx1 * wy0 : 0.f;
+  b.w10 = (fin && xin0 && yin1) ? wx0 * wy1 : 0.f;
+  b.w11 = (fin && xin1 && yin1) ? wx1 * wy1 : 0.f;
+  if (!fin) { b.x0 = 0; b.y0 = 0; }
+  return b;
+}
+
+template <typename T>
+__global__ void k_warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int nxor, Ten<T> out) {
+  // one thread per (pixel, channel); channel fastest so neighbouring lanes read neighbouring bytes
+  int C = out.C;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long npix = (long long)out.N * out.H * out.W;
+  if (gid >= npix * C) return;
+  int c = (int)(gid % C);
+  long long p = gid / C;
+  int x = (int)(p % out.W);
+  int y = (int)((p / out.W) % out.H);
+  int n = (int)(p / ((long long)out.W * out.H));
+  const float* f = flow.at(n, y, x);
+  float px = (float)x + f[0] * scale, py = (float)y + f[1] * scale;
+  Bil b = bilinear_zeros(px, py, in.W, in.H);
+  float v = 0.f;
+  const int ns = n ^ nxor;
+  if (c < in.C) {
+    if (b.w00 != 0.f) v += to_f(in.at(ns, b.y0, b.x0)[c]) * b.w00;
+    if (b.w01 != 0.f) v += to_f(in.at(ns, b.y0, b.x0 + 1)[c]) * b.w01;
+    if (b.w10 != 0.f) v += to_f(in.at(ns, b.y0 + 1, b.x0)[c]) * b.w10;
+    if (b.w11 != 0.f) v += to_f(in.at(ns, b.y0 + 1, b.x0 + 1)[c]) * b.w11;
+  }
+  out.at(n, y, x)[c] = from_f<T>(v);
+}
+
+template <typename T>
+int warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int in_nxor, Ten<T> out, cudaStream_t s) {
+  long long total = (long long)out.N * out.H * out.W * out.C;
+  dim3 block(256), grid((unsigned)((total + 255) / 256));
+  auto k = k_warp_bilinear<T>;
+  DFVO_LAUNCH(k, grid, block, 0, s, in, flow, scale, in_nxor, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int warp_bilinear<float>(Ten<const float>, Ten<const float>, float, int, Ten<float>, cudaStream_t);
+template int warp_bilinear<bf16>(Ten<const bf16>, Ten<const float>, float, int, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// 49-channel correlation (correlation.py:38-106).  Output pixel (y,x) reads first at (y*s, x*s)
+// and second at (y*s + dy*s, x*s + dx*s), dy,dx in [-3,3], zero outside; result / C; optional
+// LeakyReLU(0.1) (lite_flow_net.py:145-149).  For s=2 only even pixels are ever touched.
+// Tile: 32x4 output pixels per 128-thread block; the second feature map's (4+6)x(32+6) patch is
+// staged in shared memory 16 words (16 floats / 32 bf16) of channels at a time with a 20-word
+// pixel pitch (conflict-free 128-bit reads); each thread keeps its 49 accumulators in registers.
+// ---------------------------------------------------------------------------------------------
+#define CORR_TW 32
+#define CORR_TH 4
+#define CORR_PW (CORR_TW + 6)
+#define CORR_PH (CORR_TH + 6)
+#define CORR_PITCH 20
+
+template <typename T> struct CorrVec;
+template <> struct CorrVec<float> { enum { CK = 16 }; };
+template <> struct CorrVec<bf16> { enum { CK = 32 }; };
+
+DFVO_D void corr_unpack(const uint32_t* w, float* f, float) {
+  for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(w[i]);
+}
+DFVO_D int corr_unpack_n(float) { return 4; }
+DFVO_D void corr_unpack8(const uint32_t* w, float* f) {     // 4 words of bf16x2 -> 8 floats
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CORR_TW* CORR_TH)
+k_correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out) {
+  constexpr int CK = CorrVec<T>::CK;          // channels per 16-word chunk
+  constexpr int EPW = CK / 16;                // elements per 32-bit word (1 or 2)
+  __shared__ __align__(16) uint32_t patch[CORR_PH * CORR_PW * CORR_PITCH];
+  const int tx = threadIdx.x % CORR_TW, ty = threadIdx.x / CORR_TW;
+  const int x0 = blockIdx.x * CORR_TW, y0 = blockIdx.y * CORR_TH, n = blockIdx.z;
+  const int ox = x0 + tx, oy = y0 + ty;
+  const bool active = ox < out.W && oy < out.H;
+  const int C = f1.C;
+  float acc[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) acc[i] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += CK) {
+    __syncthreads();
+    // stage second-map patch: pixel (py,px) of the patch <-> source ((y0+py-3)*s, (x0+px-3)*s)
+    for (int i = threadIdx.x; i < CORR_PH * CORR_PW * 4; i += blockDim.x) {
+      int q = i & 3, pp = i >> 2;
+      int px = pp % CORR_PW, py = pp / CORR_PW;
+      int sy = (y0 + py - 3) * stride, sx = (x0 + px - 3) * stride;
+      uint32_t wv[4] = {0u, 0u, 0u, 0u};
+      if (sy >= 0 && sy < f2.H && sx >= 0 && sx < f2.W) {
+        const T* src = f2.at(n ^ f2_nxor, sy, sx) + c0 + q * 4 * EPW;
+        for (int j = 0; j < 4; ++j) {
+          if (EPW == 1) {
+            int c = c0 + q * 4 + j;
+            wv[j] = (c < C) ? __float_as_uint(to_f(src[j])) : 0u;
+          } else {
+            int c = c0 + (q * 4 + j) * 2;
+            uint32_t lo = 0u, hi = 0u;
+            if (c < C) lo = __float_as_uint(to_f(src[2 * j])) >> 16;
+            if (c + 1 < C) hi = __float_as_uint(to_f(src[2 * j + 1])) & 0xffff0000u;
+            wv[j] = lo | hi;
+          }
+        }
+      }
+      uint32_t* dst = &patch[pp * CORR_PITCH + q * 4];
+      dst[0] = wv[0]; dst[1] = wv[1]; dst[2] = wv[2]; dst[3] = wv[3];
+    }
+    __syncthreads();
+    if (!active) continue;
+    // this thread's first-map chunk
+    float a[CK];
+    {
+      const T* src = f1.at(n, oy * stride, ox * stride) + c0;
+      for (int j = 0; j < CK; ++j) a[j] = (c0 + j < C) ? to_f(src[j]) : 0.f;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const uint32_t* pw = &patch[((ty + dy) * CORR_PW + tx + dx) * CORR_PITCH];
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t wv[4] = {pw[q * 4], pw[q * 4 + 1], pw[q * 4 + 2], pw[q * 4 + 3]};
+          if (EPW == 1) {
+            for (int j = 0; j < 4; ++j) sum += a[q * 4 + j] * __uint_as_float(wv[j]);
+          } else {
+            float b[8];
+            corr_unpack8(wv, b);
+            for (int j = 0; j < 8; ++j) sum += a[q * 8 + j] * b[j];
+          }
+        }
+        acc[dy * 7 + dx] += sum;
+      }
+    }
+  }
+  if (!active) return;
+  T* o = out.at(n, oy, ox);
+  const float inv = 1.f / (float)C;
+#pragma unroll
+  for (int i = 0; i < 49; ++i) {
+    float v = acc[i] * inv;
+    if (leaky) v = v > 0.f ? v : 0.1f * v;
+    o[i] = from_f<T>(v);
+  }
+  for (int i = 49; i < out.C; ++i) o[i] = from_f<T>(0.f);
+}
+
+template <typename T>
+int correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out, cudaStream_t s) {
+  DFVO_REQUIRE(stride == 1 || stride == 2, DFVO_EINVAL, "correlation stride must be 1 or 2");
+  DFVO_REQUIRE(out.H == (f1.H + stride - 1) / stride && out.W == (f1.W + stride - 1) / stride &&
+                   out.C >= 49 && f1.C == f2.C && f1.H == f2.H && f1.W == f2.W,
+               DFVO_ESHAPE, "correlation shapes");
+  dim3 block(CORR_TW * CORR_TH), grid(cdiv(out.W, CORR_TW), cdiv(out.H, CORR_TH), out.N);
+  auto k = k_correlation49<T>;
+  DFVO_LAUNCH(k, grid, block, 0, s, f1, f2, f2_nxor, stride, leaky, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int correlation49<float>(Ten<const float>, Ten<const float>, int, int, int, Ten<float>, cudaStream_t);
+template int correlation49<bf16>(Ten<const bf16>, Ten<const bf16>, int, int, int, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// flow mean (lite_flow_net.py:257: tensorFlow.view(N,2,-1).mean(2))  -- one block per n
+// ---------------------------------------------------------------------------------------------
+__global__ void k_flow_mean(Ten<const float> flow, float* __restrict__ mean) {
+  __shared__ double sx[256], sy[256];
+  int n = blockIdx.x;
+  int npix = flow.H * flow.W;
+  double ax = 0.0, ay = 0.0;
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const float* f = flow.at(n, p / flow.W, p % flow.W);
+    ax += (double)f[0]; ay += (double)f[1];
+  }
+  sx[threadIdx.x] = ax; sy[threadIdx.x] = ay;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) { sx[threadIdx.x] += sx[threadIdx.x + off]; sy[threadIdx.x] += sy[threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    mean[n * 2 + 0] = (float)(sx[0] / (double)npix);
+    mean[n * 2 + 1] = (float)(sy[0] / (double)npix);
+  }
+}
+
+int flow_mean(Ten<const float> flow, float* mean, cudaStream_t s) {
+  DFVO_LAUNCH(k_flow_mean, dim3(flow.N), dim3(256), 0, s, flow, mean);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Regularization prep (lite_flow_net.py:244-257)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_reg_prep(Ten<const float> img1, Ten<const float> img2, int nxor, Ten<const float> flow,
+                           const float* __restrict__ mean, float scale, Ten<T> out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.W) return;
+  const float* f = flow.at(n, y, x);
+  float px = (float)x + f[0] * scale, py = (float)y + f[1] * scale;
+  Bil b = bilinear_zeros(px, py, img2.W, img2.H);
+  const float* a = img1.at(n, y, x);
+  float ss = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    float v = 0.f;
+    if (b.w00 != 0.f) v += img2.at(n ^ nxor, b.y0, b.x0)[c] * b.w00;
+    if (b.w01 != 0.f) v += img2.at(n ^ nxor, b.y0, b.x0 + 1)[c] * b.w01;
+    if (b.w10 != 0.f) v += img2.at(n ^ nxor, b.y0 + 1, b.x0)[c] * b.w10;
+    if (b.w11 != 0.f) v += img2.at(n ^ nxor, b.y0 + 1, b.x0 + 1)[c] * b.w11;
+    float d = a[c] - v;
+    ss += d * d;
+  }
+  T* o = out.at(n, y, x);
+  o[0] = from_f<T>(sqrtf(ss + 1e-6f));
+  o[1] = from_f<T>(f[0] - mean[n * 2 + 0]);
+  o[2] = from_f<T>(f[1] - mean[n * 2 + 1]);
+  for (int c = 3; c < out.C; ++c) o[c] = from_f<T>(0.f);
+}
+
+template <typename T>
+int reg_prep(Ten<const float> img1, Ten<const float> img2, int img2_nxor, Ten<const float> flow, const float* mean,
+             float scale, Ten<T> out, cudaStream_t s) {
+  dim3 block(128), grid(cdiv(out.W, 128), out.H, out.N);
+  auto k = k_reg_prep<T>;
+  DFVO_LAUNCH(k, grid, block, 0, s, img1, img2, img2_nxor, flow, mean, scale, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int reg_prep<float>(Ten<const float>, Ten<const float>, int, Ten<const float>, const float*, float, Ten<float>, cudaStream_t);
+template int reg_prep<bf16>(Ten<const float>, Ten<const float>, int, Ten<const float>, const float*, float, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// Regularization tail (lite_flow_net.py:258-264).  dist channel j <-> unfold offset
+// (j / k - k/2, j % k - k/2) (torch.nn.functional.unfold ordering), zero padding.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_reg_tail(Ten<const T> dist, Ten<const float> flow, int k, const float* __restrict__ wx,
+                           const float* __restrict__ wy, float bx, float by, Ten<float> out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.W) return;
+  const int cd = k * k, r = k / 2;
+  const T* d = dist.at(n, y, x);
+  float m = -3.4e38f;
+  for (int j = 0; j < cd; ++j) {
+    float v = to_f(d[j]);
+    float nv = -(v * v);
+    m = nv > m ? nv : m;
+  }
+  float se = 0.f, ax = 0.f, ay = 0.f;
+  for (int j = 0; j < cd; ++j) {
+    float v = to_f(d[j]);
+    float e = expf(-(v * v) - m);
+    se += e;
+    int yy = y + j / k - r, xx = x + j % k - r;
+    if (yy >= 0 && yy < flow.H && xx >= 0 && xx < flow.W) {
+      const float* f = flow.at(n, yy, xx);
+      ax += wx[j] * (e * f[0]);
+      ay += wy[j] * (e * f[1]);
+    }
+  }
+  float inv = 1.f / se;
+  float* o = out.at(n, y, x);
+  o[0] = (ax + bx) * inv;
+  o[1] = (ay + by) * inv;
+}
+
+template <typename T>
+int reg_tail(Ten<const T> dist, Ten<const float> flow, int k, const float* wx, const float* wy, float bx,
+             float by, Ten<float> out, cudaStream_t s) {
+  dim3 block(128), grid(cdiv(out.W, 128), out.H, out.N);
+  auto kk = k_reg_tail<T>;
+  DFVO_LAUNCH(kk, grid, block, 0, s, dist, flow, k, wx, wy, bx, by, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int reg_tail<float>(Ten<const float>, Ten<const float>, int, const float*, const float*, float, float, Ten<float>, cudaStream_t);
+template int reg_tail<bf16>(Ten<const bf16>, Ten<const float>, int, const float*, const float*, float, float, Ten<float>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// flows[1]*mul -> bilinear(AC=True) to HxW -> *(W/w, H/h)   (lite_flow_net.py:322-324, deep_flow.py:107-129)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_flow_upsample_final(Ten<const float> flow, float mul, int H, int W, float rw, float rh,
+                                      float* __restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= W) return;
+  Lerp ly = lerp_coord(y, flow.H, H, 1), lx = lerp_coord(x, flow.W, W, 1);
+  const float* p00 = flow.at(n, ly.i0, lx.i0);
+  const float* p01 = flow.at(n, ly.i0, lx.i1);
+  const float* p10 = flow.at(n, ly.i1, lx.i0);
+  const float* p11 = flow.at(n, ly.i1, lx.i1);
+  for (int c = 0; c < 2; ++c) {
+    float v = ly.l0 * (lx.l0 * (p00[c] * mul) + lx.l1 * (p01[c] * mul)) +
+              ly.l1 * (lx.l0 * (p10[c] * mul) + lx.l1 * (p11[c] * mul));
+    out[(((size_t)n * 2 + c) * H + y) * W + x] = v * (c == 0 ? rw : rh);
+  }
+}
+
+int flow_upsample_final(Ten<const float> flow, float mul, int H, int W, float* out, cudaStream_t s) {
+  float rw = (float)((double)W / (double)flow.W), rh = (float)((double)H / (double)flow.H);
+  dim3 block(128), grid(cdiv(W, 128), H, flow.N);
+  DFVO_LAUNCH(k_flow_upsample_final, grid, block, 0, s, flow, mul, H, W, rw, rh, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward-backward consistency (layers.py:213-229 FlowToPix normalisation, deep_flow.py:171-196).
+// Keeps the reference's normalise -> un-normalise arithmetic so coordinates round the same way.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fb_consistency(const float* __restrict__ fwd, const float* __restrict__ bwd, int H, int W,
+                                 float* __restrict__ diff) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= W) return;
+  size_t hw = (size_t)H * W, i = (size_t)y * W + x;
+  float fx = fwd[i], fy = fwd[hw + i];
+  float gx = (((float)x + fx) / (float)(W - 1) - 0.5f) * 2.f;
+  float gy = (((float)y + fy) / (float)(H - 1) - 0.5f) * 2.f;
+  float px = ((gx + 1.f) / 2.f) * (float)(W - 1);
+  float py = ((gy + 1.f) / 2.f) * (float)(H - 1);
+  Bil b = bilinear_zeros(px, py, W, H);
+  float wx = 0.f, wy = 0.f;
+  if (b.w00 != 0.f) { size_t j = (size_t)b.y0 * W + b.x0; wx += -bwd[j] * b.w00; wy += -bwd[hw + j] * b.w00; }
+  if (b.w01 != 0.f) { size_t j = (size_t)b.y0 * W + b.x0 + 1; wx += -bwd[j] * b.w01; wy += -bwd[hw + j] * b.w01; }
+  if (b.w10 != 0.f) { size_t j = (size_t)(b.y0 + 1) * W + b.x0; wx += -bwd[j] * b.w10; wy += -bwd[hw + j] * b.w10; }
+  if (b.w11 != 0.f) { size_t j = (size_t)(b.y0 + 1) * W + b.x0 + 1; wx += -bwd[j] * b.w11; wy += -bwd[hw + j] * b.w11; }
+  float dx = fx - wx, dy = fy - wy;
+  diff[i] = sqrtf(dx * dx + dy * dy);
+}
+
+int fb_consistency(const float* fwd, const float* bwd, int H, int W, float* diff, cudaStream_t s) {
+  dim3 block(128), grid(cdiv(W, 128), H);
+  DFVO_LAUNCH(k_fb_consistency, grid, block, 0, s, fwd, bwd, H, W, diff);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout / dtype helpers
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void k_convert_copy(Ten<const TI> in, Ten<TO> out) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)out.N * out.H * out.W * out.C;
+  if (gid >= total) return;
+  int c = (int)(gid % out.C);
+  long long p = gid / out.C;
+  int x = (int)(p % out.W), y = (int)((p / out.W) % out.H), n = (int)(p / ((long long)out.W * out.H));
+  float v = c < in.C ? to_f(in.at(n, y, x)[c]) : 0.f;
+  out.at(n, y, x)[c] = from_f<TO>(v);
+}
+
+template <typename TI, typename TO>
+int convert_copy(Ten<const TI> in, Ten<TO> out, cudaStream_t s) {
+  long long total = (long long)out.N * out.H * out.W * out.C;
+  auto k = k_convert_copy<TI, TO>;
+  DFVO_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, in, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int convert_copy<float, bf16>(Ten<const float>, Ten<bf16>, cudaStream_t);
+template int convert_copy<bf16, float>(Ten<const bf16>, Ten<float>, cudaStream_t);
+template int convert_copy<float, float>(Ten<const float>, Ten<float>, cudaStream_t);
+template int convert_copy<bf16, bf16>(Ten<const bf16>, Ten<bf16>, cudaStream_t);
+
+__global__ void k_nchw_to_nhwc_f32(const float* __restrict__ in, int C, Ten<float> out) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)out.N * out.H * out.W * out.C;
+  if (gid >= total) return;
+  int c = (int)(gid % out.C);
+  long long p = gid / out.C;
+  int x = (int)(p % out.W), y = (int)((p / out.W) % out.H), n = (int)(p / ((long long)out.W * out.H));
+  out.at(n, y, x)[c] = c < C ? in[(((size_t)n * C + c) * out.H + y) * out.W + x] : 0.f;
+}
+
+int nchw_to_nhwc_f32(const float* in, int N, int C, int H, int W, Ten<float> out, cudaStream_t s) {
+  long long total = (long long)N * H * W * out.C;
+  DFVO_LAUNCH(k_nchw_to_nhwc_f32, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, in, C, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+template <typename T>
+__global__ void k_nhwc_to_nchw(Ten<const T> in, float* __restrict__ out) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)in.N * in.H * in.W * in.C;
+  if (gid >= total) return;
+  int x = (int)(gid % in.W);
+  long long r = gid / in.W;
+  int y = (int)(r % in.H); r /= in.H;
+  int c = (int)(r % in.C);
+  int n = (int)(r / in.C);
+  out[gid] = to_f(in.at(n, y, x)[c]);
+}
+
+template <typename T>
+int nhwc_to_nchw(Ten<const T> in, float* out, cudaStream_t s) {
+  long long total = (long long)in.N * in.H * in.W * in.C;
+  auto k = k_nhwc_to_nchw<T>;
+  DFVO_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, in, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int nhwc_to_nchw<float>(Ten<const float>, float*, cudaStream_t);
+template int nhwc_to_nchw<bf16>(Ten<const bf16>, float*, cudaStream_t);
+
+}  // namespace dfvo

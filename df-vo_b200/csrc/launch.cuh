@@ -1,0 +1,10 @@
+// Kernel-launch macro: real <<<>>> launch under nvcc; under -DDFVO_HOSTSIM (CPU test build, see
+// tests/hostsim/cuda_hostsim.h) the same kernel body runs inside a fiber-based emulator.
+#pragma once
+#ifdef DFVO_HOSTSIM
+#include "cuda_hostsim.h"
+#else
+#include <cuda_runtime.h>
+#define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
+  kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif

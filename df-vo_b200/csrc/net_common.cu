@@ -1,0 +1,194 @@
+#include "net_common.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace dfvo {
+
+// ---- error plumbing (thread-local last-error string, SURVEY 8b: never throw across the boundary)
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return DFVO_ECUDA;
+}
+
+void* Arena::alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess || !p) {
+    set_error("cudaMalloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  cudaMemset(p, 0, bytes);
+  chunks_.push_back(p);
+  total_ += bytes;
+  return p;
+}
+void Arena::release() {
+  for (void* p : chunks_) cudaFree(p);
+  chunks_.clear();
+  total_ = 0;
+}
+
+const HostTensor* find_weight(const WeightStore& ws, const std::string& key) {
+  auto it = ws.find(key);
+  return it == ws.end() ? nullptr : &it->second;
+}
+
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fff;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, const std::vector<Seg>& segs,
+                     int stride, int pad_y, int pad_x, int reflect, bool want_tc, bool want_direct,
+                     const float* scale, const float* shift, ConvLayer* L) {
+  DFVO_REQUIRE(w.shape.size() == 4, DFVO_ESHAPE, "conv weight must be 4-D");
+  const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], kh = (int)w.shape[2], kw = (int)w.shape[3];
+  int real = 0, ktot = 0;
+  for (const Seg& sg : segs) { real += sg.real; ktot += sg.padded; }
+  DFVO_REQUIRE(real == Cin, DFVO_ESHAPE, "conv segments cover %d channels, weight has %d", real, Cin);
+  L->Cin_ref = Cin; L->Cout = Cout; L->kh = kh; L->kw = kw; L->stride = stride;
+  L->pad_y = pad_y; L->pad_x = pad_x; L->reflect = reflect; L->Ktot = ktot;
+  L->Cout_pad = (Cout + 15) / 16 * 16;
+  L->tc = want_tc;
+  // padded-k -> reference channel (or -1)
+  std::vector<int> kmap(ktot, -1);
+  {
+    int kb = 0, rb = 0;
+    for (const Seg& sg : segs) {
+      for (int c = 0; c < sg.real; ++c) kmap[kb + c] = rb + c;
+      kb += sg.padded; rb += sg.real;
+    }
+  }
+  auto W = [&](int co, int ci, int ky, int kx) {
+    float v = w.data[(((size_t)co * Cin + ci) * kh + ky) * kw + kx];
+    return scale ? v * scale[co] : v;
+  };
+  // bias
+  {
+    std::vector<float> b(L->Cout_pad, 0.f);
+    for (int co = 0; co < Cout; ++co) {
+      float v = bias ? bias->data[co] : 0.f;
+      if (scale) v *= scale[co];
+      if (shift) v += shift[co];
+      b[co] = v;
+    }
+    L->bias = arena.alloc_t<float>(L->Cout_pad);
+    if (!L->bias) return DFVO_ENOMEM;
+    DFVO_CUDA(cudaMemcpy(L->bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (want_direct) {
+    L->w_pitch = (Cout + 3) / 4 * 4;
+    std::vector<float> h((size_t)kh * kw * ktot * L->w_pitch, 0.f);
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int k = 0; k < ktot; ++k) {
+          if (kmap[k] < 0) continue;
+          float* dst = &h[(((size_t)ky * kw + kx) * ktot + k) * L->w_pitch];
+          for (int co = 0; co < Cout; ++co) dst[co] = W(co, kmap[k], ky, kx);
+        }
+    L->w_direct = arena.alloc_t<float>(h.size());
+    if (!L->w_direct) return DFVO_ENOMEM;
+    DFVO_CUDA(cudaMemcpy(L->w_direct, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (want_tc) {
+    DFVO_REQUIRE(stride == 1 && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1, zero pad, K %% 16 == 0");
+    std::vector<uint16_t> h((size_t)kh * kw * L->Cout_pad * ktot, 0);
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int co = 0; co < Cout; ++co) {
+          uint16_t* dst = &h[(((size_t)ky * kw + kx) * L->Cout_pad + co) * ktot];
+          for (int k = 0; k < ktot; ++k)
+            if (kmap[k] >= 0) dst[k] = f2bf(W(co, kmap[k], ky, kx));
+        }
+    L->w_tc = reinterpret_cast<bf16*>(arena.alloc(h.size() * 2));
+    if (!L->w_tc) return DFVO_ENOMEM;
+    DFVO_CUDA(cudaMemcpy(L->w_tc, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  }
+  return DFVO_OK;
+}
+
+static void fill_taps(const ConvLayer& L, ConvTc* c) {
+  c->ntaps = L.kh * L.kw;
+  for (int ky = 0; ky < L.kh; ++ky)
+    for (int kx = 0; kx < L.kw; ++kx) {
+      c->dy[ky * L.kw + kx] = (int8_t)(ky - L.pad_y);
+      c->dx[ky * L.kw + kx] = (int8_t)(kx - L.pad_x);
+    }
+}
+
+static ConvDirect to_direct(const ConvLayer& L, int act) {
+  ConvDirect d;
+  d.Cin = L.Ktot; d.Cout = L.Cout; d.kh = L.kh; d.kw = L.kw; d.stride = L.stride;
+  d.pad_y = L.pad_y; d.pad_x = L.pad_x; d.reflect = L.reflect; d.act = act;
+  d.w = L.w_direct; d.w_pitch = L.w_pitch; d.bias = L.bias;
+  return d;
+}
+
+template <>
+int run_conv<float>(const ConvLayer& L, Ten<const float> in, Ten<float> out, int act, Ten<const float> residual,
+                    int zero_pad_to, cudaStream_t s) {
+  DFVO_REQUIRE(L.w_direct, DFVO_ESTATE, "conv layer has no fp32 weights");
+  // pad channels of fp32 buffers are zero from allocation and never written; nothing to do for zero_pad_to
+  (void)zero_pad_to;
+  return conv_direct<float, float>(to_direct(L, act), in, out, residual, s);
+}
+
+template <>
+int run_conv<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<bf16> out, int act, Ten<const bf16> residual,
+                   int zero_pad_to, cudaStream_t s) {
+  if (!L.tc) {
+    DFVO_REQUIRE(L.w_direct, DFVO_ESTATE, "conv layer has no direct weights");
+    return conv_direct<bf16, bf16>(to_direct(L, act), in, out, residual, s);
+  }
+  DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc conv: input view has %d channels, layer expects %d", in.C, L.Ktot);
+  ConvTc c;
+  memset(&c, 0, sizeof(c));
+  c.N = in.N; c.H = in.H; c.W = in.W;
+  c.nsrc = 1;
+  c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
+  fill_taps(L, &c);
+  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = 0;
+  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
+  c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
+  c.zero_pad_to = zero_pad_to;
+  return conv_tc(c, s);
+}
+
+template <>
+int run_conv_f32out<float>(const ConvLayer& L, Ten<const float> in, Ten<float> out, int act,
+                           Ten<const float> residual, cudaStream_t s) {
+  return conv_direct<float, float>(to_direct(L, act), in, out, residual, s);
+}
+
+template <>
+int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out, int act, Ten<const float> residual,
+                          cudaStream_t s) {
+  if (!L.tc) return conv_direct<bf16, float>(to_direct(L, act), in, out, residual, s);
+  DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc head: input view has %d channels, layer expects %d", in.C, L.Ktot);
+  ConvTc c;
+  memset(&c, 0, sizeof(c));
+  c.N = in.N; c.H = in.H; c.W = in.W;
+  c.nsrc = 1;
+  c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
+  fill_taps(L, &c);
+  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = 1;
+  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
+  c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
+  c.zero_pad_to = 0;
+  return conv_tc(c, s);
+}
+
+}  // namespace dfvo

@@ -1,0 +1,100 @@
+// Internal C++ interface of the dfvo_b200 kernels (one declaration per launcher).
+// All tensors are device memory, NHWC with explicit strides (common.cuh::Ten); every launcher
+// enqueues on the caller's stream and returns DFVO_OK or a negative error code.
+#pragma once
+#include "common.cuh"
+
+namespace dfvo {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- image / flow plumbing (flow_ops.cu) -------------------------------------------------
+// u8 HWC [H0,W0,3] -> float(/255) -> bilinear(align_corners=True) to [th,tw] -> out[n] (pitch>=3).
+// (deep_models.py:160-163 + lite_flow.py:72-76).  If norm_mean/std given: (v-mean)/std after resize.
+int prep_image_u8(const uint8_t* img, int H0, int W0, Ten<float> out, int n, cudaStream_t s);
+// generic bilinear resize of float NHWC (C<=4), align_corners flag (lite_flow_net.py:307-309)
+int resize_bilinear_f32(Ten<const float> in, Ten<float> out, int align_corners, cudaStream_t s);
+// depthwise ConvTranspose2d k4 s2 p1, no bias (lite_flow_net.py:109,117); w = [C][4][4] float
+template <typename T>
+int deconv4x4s2_dw(Ten<const T> in, const float* w, Ten<T> out, cudaStream_t s);
+// Backward warp (lite_flow_net.py:10-28): out = bilinear(in at (x,y) + flow*scale), zeros outside
+// in_nxor: the source is read at batch index (n ^ in_nxor) -- "second image" addressing, see liteflownet.cu
+template <typename T>
+int warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int in_nxor, Ten<T> out, cudaStream_t s);
+// 49-channel correlation + fused LeakyReLU(0.1) (correlation.py:38-106, lite_flow_net.py:145-149)
+template <typename T>
+int correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out, cudaStream_t s);
+// per-(n,c) spatial mean of a 2-channel float field (lite_flow_net.py:257) -> mean[n*2+c]
+int flow_mean(Ten<const float> flow, float* mean, cudaStream_t s);
+// Regularization input prep (lite_flow_net.py:244-257): out[...,0]=sqrt(sum((img1-warp(img2))^2)+1e-6),
+// out[...,1:3] = flow - mean, remaining channels of out (up to out.C) zero.
+template <typename T>
+int reg_prep(Ten<const float> img1, Ten<const float> img2, int img2_nxor, Ten<const float> flow, const float* mean,
+             float scale, Ten<T> out, cudaStream_t s);
+// Regularization tail (lite_flow_net.py:258-264): dist -> exp(-(d^2)-max) weights, weighted local flow
+// average through ScaleX/ScaleY (1x1 convs, weights wx/wy[cd], biases bx/by) / sum of weights.
+template <typename T>
+int reg_tail(Ten<const T> dist, Ten<const float> flow, int k, const float* wx, const float* wy,
+             float bx, float by, Ten<float> out, cudaStream_t s);
+// flows[1] * 10 -> bilinear(align_corners=True) to [H,W] -> * (W/w, H/h); planar [n][2][H][W] out
+// (lite_flow_net.py:322-324, deep_flow.py:107-129)
+int flow_upsample_final(Ten<const float> flow, float mul, int H, int W, float* out_planar, cudaStream_t s);
+// forward-backward consistency (layers.py:213-229, deep_flow.py:171-196); planar [2][H][W] inputs
+int fb_consistency(const float* flow_fwd, const float* flow_bwd, int H, int W, float* diff, cudaStream_t s);
+// converts / layout helpers (used by stage-level parity entry points)
+template <typename TI, typename TO>
+int convert_copy(Ten<const TI> in, Ten<TO> out, cudaStream_t s);          // NHWC -> NHWC (C=min)
+int nchw_to_nhwc_f32(const float* in, int N, int C, int H, int W, Ten<float> out, cudaStream_t s);
+template <typename T>
+int nhwc_to_nchw(Ten<const T> in, float* out, cudaStream_t s);
+
+// ---- CUDA-core convolution (conv_direct.cu) -------------------------------------------------
+struct ConvDirect {
+  int Cin, Cout, kh, kw, stride, pad_y, pad_x;
+  int reflect;            // 0: zero padding, 1: reflection padding (layers.py:127-128)
+  int act;                // Act
+  const float* w;         // [kh*kw*Cin][Cout_pitch] fp32, k = (ky*kw+kx)*Cin + ci
+  int w_pitch;            // Cout rounded up to 4
+  const float* bias;      // [Cout] or nullptr
+};
+template <typename TI, typename TO>
+int conv_direct(const ConvDirect& c, Ten<const TI> in, Ten<TO> out, Ten<const TO> residual,
+                cudaStream_t s);
+
+// ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) -------------------------------------------
+struct ConvTcSource {
+  const bf16* p;          // NHWC bf16 view (channel slice allowed)
+  int C;                  // channels in this source (multiple of 16; zero-padded by the producer)
+  long long sN, sH, sW;   // strides in elements
+};
+struct ConvTc {
+  int N, H, W;            // output spatial size == input spatial size (stride 1)
+  int nsrc;               // 1..3 virtual-concat sources
+  ConvTcSource src[3];
+  int ntaps;              // kh*kw
+  int8_t dy[49], dx[49];  // tap offsets (already include -pad)
+  const bf16* w;          // packed [ntaps][Cout_pad][Ktot] bf16, Ktot = sum(src[i].C)
+  int Cout_pad;           // multiple of 16
+  int Cout;               // real output channels written
+  const float* bias;      // [Cout_pad] fp32
+  int act;
+  int out_f32;            // 0: bf16 output, 1: float output
+  void* out;              // NHWC, pointer already offset to the first output channel
+  long long oN, oH, oW;   // output strides (elements of the output type)
+  const void* residual;   // optional, same type/strides family as out
+  long long rN, rH, rW;
+  int zero_pad_to;        // if > Cout: also write zeros to channels [Cout, zero_pad_to)
+};
+int conv_tc(const ConvTc& c, cudaStream_t s);
+// tile shape chooser shared with tests
+void conv_tc_tile_shape(int H, int W, int* tw, int* th);
+
+// ---- keypoint selection (select.cu) -------------------------------------------------------------
+int local_bestn(const float* diff, const float* depth_diff, int H, int W, int rows, int cols, int n_best,
+                float thre, float depth_thre, int N_total, int32_t* idx_out, int32_t* cell_counts,
+                int32_t* status, cudaStream_t s);
+int bestn(const float* diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t ws_bytes,
+          cudaStream_t s);
+size_t bestn_workspace_bytes(int H, int W);
+
+}  // namespace dfvo

@@ -1,0 +1,98 @@
+/* dfvo_b200 -- C ABI of the B200-native DF-VO tracking hot path (libdfvo_b200.so).
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): the reference is pure Python and has no
+ * FFI of its own, so every entry point below names the reference *Python* interface it replaces
+ * (file:line under the DF-VO repository) -- the `libs.*` mirror under df-vo_b200/libs binds these
+ * through ctypes.
+ *
+ * Conventions
+ *   - return 0 on success, negative DFVO_E* on failure; dfvo_last_error() gives a message
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - every pointer is caller-owned DEVICE memory unless the name ends in `_host`;
+ *   - work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*)
+ *     and is asynchronous: outputs are valid after the caller synchronises that stream;
+ *   - a handle owns packed weights, workspaces and plans; it is not thread-safe (one per device /
+ *     stream of work).
+ */
+#ifndef DFVO_B200_H_
+#define DFVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFVO_OK 0
+#define DFVO_EINVAL (-1)
+#define DFVO_ECUDA (-2)
+#define DFVO_ESHAPE (-3)
+#define DFVO_ENOMEM (-4)
+#define DFVO_ESTATE (-5)
+
+#define DFVO_NET_LITEFLOWNET 0
+#define DFVO_NET_MONODEPTH2 1
+
+#define DFVO_PREC_FP32 0 /* every conv on CUDA cores in fp32 (parity mode)            */
+#define DFVO_PREC_BF16 1 /* bf16 activations, tcgen05 tensor-core convs, fp32 accum   */
+
+#define DFVO_ACT_NONE 0
+#define DFVO_ACT_LEAKY 1 /* LeakyReLU(0.1) */
+#define DFVO_ACT_RELU 2
+#define DFVO_ACT_ELU 3
+#define DFVO_ACT_SIGMOID 4
+
+typedef struct dfvo_ctx dfvo_ctx;
+
+const char* dfvo_last_error(void);
+const char* dfvo_version(void);
+/* 1 if this library was built by nvcc for sm_100a, 0 for the CPU test build (tests/hostsim). */
+int dfvo_is_device_build(void);
+
+int dfvo_create(dfvo_ctx** out, int device);
+int dfvo_destroy(dfvo_ctx* ctx);
+
+/* ---- weights --------------------------------------------------------------------------------
+ * Replaces torch.load + load_state_dict: LiteFlow.initialize_network_model (lite_flow.py:31-53)
+ * and Monodepth2DepthNet.initialize_network_model (monodepth2.py:29-71).  `key` is the reference
+ * state-dict key (e.g. "moduleFeatures.moduleOne.0.weight", "encoder.layer1.0.conv1.weight",
+ * "decoder.0.conv.conv.weight"); data_host is fp32, C-contiguous. */
+int dfvo_load_weight(dfvo_ctx* ctx, int net, const char* key, const float* data_host,
+                     const int64_t* shape, int ndim);
+
+/* ---- LiteFlowNet: DeepModel.forward_flow (deep_models.py:144-182) ------------------------------
+ * Build the plan for `pairs` image pairs of height x width uint8 RGB frames. */
+int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int precision);
+/* imgs: 2*pairs device pointers (host array of device pointers) to HWC uint8 frames ordered
+ * [ref0, cur0, ref1, cur1, ...].  Outputs (any may be NULL): flow_fwd / flow_bwd
+ * [pairs][2][H][W] fp32 (= flows[(ref,cur)], flows[(cur,ref)]), flow_diff [pairs][H][W] fp32
+ * (= flows[(ref,cur,'diff')], deep_flow.py:171-196). */
+int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs_host_array, float* flow_fwd,
+                          float* flow_bwd, float* flow_diff, void* stream);
+/* parity helper: regularised flow of pyramid level (2..6), NHWC [2*pairs][h][w][2] fp32 */
+int dfvo_liteflow_level_flow(dfvo_ctx* ctx, int level, float* out);
+int dfvo_liteflow_geometry(dfvo_ctx* ctx, int* net_h, int* net_w, int* batch);
+
+/* ---- stage-level entry points (parity tests; NCHW fp32 at the boundary like the reference) -----
+ * FunctionCorrelation (correlation.py:400-402) [+ LeakyReLU if leaky]: first/second [B,C,H,W]
+ * -> out [B,49,ceil(H/s),ceil(W/s)].  precision selects the fp32 or bf16 kernel. */
+int dfvo_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W,
+                     int stride, int leaky, int precision, void* stream);
+/* Backward (lite_flow_net.py:10-28): input [B,C,H,W], flow [B,2,H,W] (already scaled) -> [B,C,H,W] */
+int dfvo_backward_warp(const float* input, const float* flow, float* out, int B, int C, int H, int W,
+                       int precision, void* stream);
+/* FlowToPix + forward_backward_consistency (layers.py:213-229, deep_flow.py:171-196):
+ * flow_fwd / flow_bwd [2,H,W] -> diff [H,W] */
+int dfvo_fb_consistency(const float* flow_fwd, const float* flow_bwd, float* diff, int H, int W,
+                        void* stream);
+/* torch.nn.Conv2d (+ activation): x [B,Cin,H,W], w_host [Cout,Cin,kh,kw], bias_host [Cout] or NULL
+ * -> y [B,Cout,Ho,Wo].  precision DFVO_PREC_BF16 runs the tcgen05 kernel (stride must be 1). */
+int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin,
+                int H, int W, int Cout, int kh, int kw, int stride, int pad_y, int pad_x, int reflect,
+                int act, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFVO_B200_H_ */
