@@ -34,7 +34,7 @@ SIGNATURES = {
     "dfvo_liteflow_forward": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_liteflow_level_flow": (c_int, [c_void_p, c_int, c_void_p]),
     "dfvo_liteflow_geometry": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
-    "dfvo_correlation": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "dfvo_correlation": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "dfvo_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "dfvo_fb_consistency": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dfvo_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),

@@ -20,6 +20,27 @@ static const int kFeatC[7] = {0, 32, 32, 64, 96, 128, 192};
 static const int kKLast[7] = {0, 0, 7, 5, 5, 3, 3};
 static const float kBackward[7] = {0.f, 0.f, 10.f, 5.f, 2.5f, 1.25f, 0.625f};
 
+// DeepFlow.get_target_size (deep_flow.py:89-105), operation for operation in float64: the reference
+// shadows h,w with the candidate arrays, so it minimises |h_i*(1/w_j) - h_j/w_j|; the diagonal is zero
+// only up to one rounding, hence floor multiples of 32 for 376x1241 but ceil multiples for 192x640.
+void liteflow_target_size(int h, int w, int* th, int* tw) {
+  const double hh[2] = {32.0 * (h / 32), 32.0 * (h / 32 + 1)};
+  const double ww[2] = {32.0 * (w / 32), 32.0 * (w / 32 + 1)};
+  int best = 0;
+  double bestv = 0.0;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) {
+      volatile double inv = 1.0 / ww[j];
+      volatile double prod = hh[i] * inv;
+      volatile double quot = hh[j] / ww[j];
+      double r = prod - quot;
+      if (r < 0) r = -r;
+      if ((i == 0 && j == 0) || r < bestv) { bestv = r; best = i * 2 + j; }
+    }
+  *th = (int)hh[best / 2];
+  *tw = (int)ww[best % 2];
+}
+
 template <typename T> struct IsBf16 { enum { v = 0 }; };
 template <> struct IsBf16<bf16> { enum { v = 1 }; };
 
@@ -81,7 +102,7 @@ struct LfnImpl : public LiteFlowNetBase {
 
   int build(const WeightStore& ws, int H0_, int W0_, int pairs) {
     H0 = H0_; W0 = W0_; P = pairs; B = 2 * pairs;
-    th = 32 * (H0 / 32); tw = 32 * (W0 / 32);        // deep_flow.py:89-105 (always floors, Appendix D #1)
+    liteflow_target_size(H0, W0, &th, &tw);
     DFVO_REQUIRE(th >= 64 && tw >= 64, DFVO_ESHAPE, "image %dx%d too small for LiteFlowNet", H0, W0);
     for (int L = 1; L <= 6; ++L) { lh[L] = th >> (L - 1); lw[L] = tw >> (L - 1); }
     // ---------------- weights ----------------

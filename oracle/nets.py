@@ -209,10 +209,16 @@ def liteflownet_forward(p, img1, img2, return_intermediates=False):
 
 
 def get_target_size(h, w):
-    """``DeepFlow.get_target_size`` (deep_flow.py:89-105).  Because the arguments are shadowed
-    by the candidate arrays before ``h / w`` is evaluated, the function always returns the
-    floor multiples of 32 (SURVEY Appendix D #1)."""
-    return 32 * (h // 32), 32 * (w // 32)
+    """``DeepFlow.get_target_size`` (deep_flow.py:89-105), restated operation for operation.
+    The arguments are shadowed by the 1x2 candidate arrays before ``h / w`` is evaluated, so the
+    "ratio" matrix is ``|h_i * (1/w_j) - h_j / w_j|`` whose diagonal is zero *up to one rounding*:
+    the result is the floor multiple of 32 when ``h0 * (1/w0) == h0 / w0`` in float64 (376x1241,
+    370x1226 -> 352x1216) and the ceil multiples otherwise (192x640 -> 224x672).  Golden-pinned."""
+    hh = 32 * np.array([[math.floor(h / 32), math.floor(h / 32) + 1]])
+    ww = 32 * np.array([[math.floor(w / 32), math.floor(w / 32) + 1]])
+    ratio = np.abs(np.matmul(np.transpose(hh), 1 / ww) - hh / ww)
+    index = int(np.argmin(ratio))
+    return int(hh[0, index // 2]), int(ww[0, index % 2])
 
 
 def resize_dense_flow(flow, H, W):

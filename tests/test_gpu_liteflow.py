@@ -1,0 +1,64 @@
+"""GPU parity of the LiteFlowNet path (DeepModel.forward_flow, deep_models.py:144-182) through the
+C ABI against the CPU oracle, on seeded synthetic weights / frames (oracle/synth.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from b200 import native
+from oracle import nets, synth
+from util import dptr, img_to_tensor
+
+pytestmark = pytest.mark.gpu
+
+
+def run_device(lib, H, W, ref, cur, prec, w):
+    ctx = native.Context(lib)
+    ctx.load_weights(native.NET_LITEFLOWNET, w)
+    ctx.liteflow_build(H, W, 1, prec)
+    d_ref, d_cur = torch.from_numpy(ref).cuda(), torch.from_numpy(cur).cuda()
+    fwd = torch.zeros((2, H, W), dtype=torch.float32, device="cuda")
+    bwd = torch.zeros_like(fwd)
+    diff = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+    ctx.liteflow_forward([d_ref.data_ptr(), d_cur.data_ptr()], dptr(fwd), dptr(bwd), dptr(diff))
+    torch.cuda.synchronize()
+    out = fwd.cpu().numpy(), bwd.cpu().numpy(), diff.cpu().numpy()
+    ctx.close()
+    return out
+
+
+@pytest.mark.parametrize("H,W", [(70, 150), (128, 416)])
+def test_liteflow_small_vs_oracle(dev_lib, H, W):
+    ref, cur = synth.value_noise_image(H, W, 1), synth.value_noise_image(H, W, 2)
+    w = synth.liteflownet_weights()
+    with torch.no_grad():
+        o = nets.liteflow_inference_flow(nets.to_torch(w), img_to_tensor(ref), img_to_tensor(cur))
+    of, ob, od = o["forward"][0].numpy(), o["backward"][0].numpy(), o["flow_diff"][0, :, :, 0].numpy()
+    # fp32 mode: summation-order differences only
+    f, b, d = run_device(dev_lib, H, W, ref, cur, native.PREC_FP32, w)
+    assert np.abs(f - of).max() < 2e-4 and np.abs(b - ob).max() < 2e-4 and np.abs(d - od).max() < 5e-4
+    # bf16 tensor-core mode: flows of several px agree to a small fraction of a pixel (end-point error)
+    f, b, d = run_device(dev_lib, H, W, ref, cur, native.PREC_BF16, w)
+    epe = np.sqrt(((f - of) ** 2).sum(0))
+    assert epe.mean() < 0.05 and epe.max() < 0.5, (epe.mean(), epe.max())
+    assert np.abs(d - od).mean() < 0.08
+
+
+def test_liteflow_full_size_properties(dev_lib):
+    """BASELINE size 376x1241: no oracle run (minutes on CPU); size-independent properties instead:
+    (1) swapping the two frames swaps forward and backward flow exactly (same kernels, same data);
+    (2) identical frames through a symmetric path give fwd == bwd;
+    (3) fp32 and bf16 modes agree to a fraction of a pixel."""
+    H, W = 376, 1241
+    ref, cur = synth.value_noise_image(H, W, 11), synth.value_noise_image(H, W, 12)
+    w = synth.liteflownet_weights()
+    f1, b1, d1 = run_device(dev_lib, H, W, ref, cur, native.PREC_BF16, w)
+    f2, b2, d2 = run_device(dev_lib, H, W, cur, ref, native.PREC_BF16, w)
+    assert np.array_equal(f1, b2) and np.array_equal(b1, f2)
+    f3, b3, d3 = run_device(dev_lib, H, W, ref, ref, native.PREC_BF16, w)
+    assert np.array_equal(f3, b3)
+    assert np.isfinite(f1).all() and np.isfinite(d1).all()
+    f4, b4, d4 = run_device(dev_lib, H, W, ref, cur, native.PREC_FP32, w)
+    epe = np.sqrt(((f1 - f4) ** 2).sum(0))
+    assert epe.mean() < 0.1, epe.mean()

@@ -1,0 +1,159 @@
+"""GPU parity of the stage-level C-ABI entry points against the CPU oracle (oracle/nets.py).
+
+Tolerances (floating point):
+  * fp32 kernels vs fp32 oracle: 2e-5 abs on O(1) data (summation order only);
+  * bf16/tcgen05 kernels vs an fp32 oracle evaluated on bf16-rounded operands: 1e-2 relative
+    (fp32 accumulation, outputs rounded to bf16).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nets
+from util import bf16_round, dptr
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("B,C,H,W,s", [(2, 192, 11, 38, 1), (2, 128, 22, 76, 1), (2, 96, 44, 152, 1),
+                                       (2, 64, 88, 304, 2), (1, 64, 35, 51, 2), (1, 32, 9, 13, 1)])
+@pytest.mark.parametrize("prec", [0, 1])
+def test_correlation(dev_lib, B, C, H, W, s, prec):
+    rs = np.random.RandomState(C + H)
+    a = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    b = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    if prec == 1:
+        a, b = bf16_round(a), bf16_round(b)
+    ref = F.leaky_relu(nets.correlation(torch.from_numpy(a), torch.from_numpy(b), s), 0.1).numpy()
+    da, db = cu(a), cu(b)
+    out = torch.zeros(ref.shape, dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_correlation(dptr(da), dptr(db), dptr(out), B, C, H, W, s, 1, prec, None))
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - ref)
+    if prec == 0:
+        assert err.max() < 2e-5
+    else:
+        assert (err <= 1e-2 * np.abs(ref) + 2e-3).all(), err.max()
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_backward_warp(dev_lib, prec):
+    rs = np.random.RandomState(3)
+    B, C, H, W = 2, 64, 44, 152
+    x = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    flow = (rs.standard_normal((B, 2, H, W)) * 6).astype(np.float32)
+    flow[0, :, :3, :3] = 1e4          # far out of bounds -> zeros
+    if prec == 1:
+        x = bf16_round(x)
+    ref = nets.backward_warp(torch.from_numpy(x), torch.from_numpy(flow)).numpy()
+    dx, df = cu(x), cu(flow)
+    out = torch.zeros_like(dx)
+    dev_lib.check(dev_lib.dfvo_backward_warp(dptr(dx), dptr(df), dptr(out), B, C, H, W, prec, None))
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - ref)
+    assert err.max() < (2e-5 if prec == 0 else 2e-2)
+
+
+def test_fb_consistency(dev_lib):
+    rs = np.random.RandomState(5)
+    H, W = 376, 1241
+    fwd = (rs.standard_normal((1, 2, H, W)) * 4).astype(np.float32)
+    bwd = (-fwd + rs.standard_normal((1, 2, H, W)) * 0.1).astype(np.float32)
+    ref = nets.fb_consistency(torch.from_numpy(fwd), torch.from_numpy(bwd))[0, :, :, 0].numpy()
+    dfw, dbw = cu(fwd[0]), cu(bwd[0])
+    out = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_fb_consistency(dptr(dfw), dptr(dbw), dptr(out), H, W, None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    err = np.abs(got - ref)
+    assert err.max() < 1e-4
+    # mask agreement at the reference threshold (kp_selection.thre = 0.1) is reported, not asserted bit-exact
+    flips = ((got < 0.1) != (ref < 0.1)).mean()
+    assert flips < 1e-4
+
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, act
+    (2, 3, 40, 72, 32, 7, 7, 1, 3, 3, 1),
+    (2, 32, 40, 72, 32, 3, 3, 2, 1, 1, 1),
+    (1, 64, 22, 38, 96, 3, 3, 2, 1, 1, 1),
+    (2, 32, 33, 47, 2, 7, 7, 1, 3, 3, 0),
+    (1, 16, 24, 40, 1, 3, 3, 1, 1, 1, 4),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fp32(dev_lib, case):
+    B, Cin, H, W, Cout, kh, kw, st, py, px, act = case
+    rs = np.random.RandomState(Cin * 7 + Cout)
+    x = rs.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (rs.standard_normal((Cout, Cin, kh, kw)) / np.sqrt(Cin * kh * kw)).astype(np.float32)
+    b = rs.standard_normal(Cout).astype(np.float32) * 0.1
+    y = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=st, padding=(py, px))
+    y = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.1), 4: torch.sigmoid}[act](y).numpy()
+    dx = cu(x)
+    out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_conv2d(dptr(dx), w.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                      dptr(out), B, Cin, H, W, Cout, kh, kw, st, py, px, 0, act, 0, None))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - y).max() < 3e-5
+
+
+def test_conv2d_fp32_reflect(dev_lib):
+    rs = np.random.RandomState(11)
+    B, Cin, H, W, Cout = 1, 48, 12, 40, 32
+    x = rs.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (rs.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9)).astype(np.float32)
+    b = rs.standard_normal(Cout).astype(np.float32) * 0.1
+    y = F.elu(F.conv2d(F.pad(torch.from_numpy(x), (1, 1, 1, 1), mode="reflect"), torch.from_numpy(w), torch.from_numpy(b))).numpy()
+    dx = cu(x)
+    out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_conv2d(dptr(dx), w.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                      dptr(out), B, Cin, H, W, Cout, 3, 3, 1, 1, 1, 1, 3, 0, None))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - y).max() < 3e-5
+
+
+TC_CASES = [
+    # B, Cin, H, W, Cout, kh, kw, pad_y, pad_x, act  -- the LiteFlowNet layer shapes (small spatial)
+    (2, 128, 16, 64, 128, 3, 3, 1, 1, 1),      # single full tile row group
+    (2, 64, 44, 152, 32, 3, 3, 1, 1, 1),
+    (2, 49, 22, 76, 128, 3, 3, 1, 1, 1),       # Cin padded 49 -> 64
+    (1, 130, 44, 152, 128, 3, 3, 1, 1, 1),     # Cin 130 -> 144 (partial last K chunk)
+    (1, 386, 11, 38, 128, 3, 3, 1, 1, 1),      # many K chunks, tiny image, tile wider than image
+    (2, 32, 40, 72, 2, 7, 7, 3, 3, 0),         # flow head: 49 taps, Cout 2 -> 16
+    (1, 32, 22, 76, 49, 7, 1, 3, 0, 0),        # separable dist conv (7x1)
+    (1, 49, 22, 76, 49, 1, 7, 0, 3, 0),        # (1x7), Cin 49 -> 64
+    (1, 32, 24, 40, 64, 1, 1, 0, 0, 1),        # 1x1
+    (1, 96, 24, 40, 192, 3, 3, 1, 1, 1),       # N = 192
+    (1, 256, 6, 20, 512, 3, 3, 1, 1, 2),       # N blocks (512 = 4 x 128), relu
+    (3, 16, 9, 130, 16, 3, 3, 1, 1, 3),        # odd sizes, elu, minimum channels
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tcgen05(dev_lib, case):
+    B, Cin, H, W, Cout, kh, kw, py, px, act = case
+    rs = np.random.RandomState(Cin + 13 * Cout + kh)
+    x = bf16_round(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
+    w = bf16_round((rs.standard_normal((Cout, Cin, kh, kw)) / np.sqrt(Cin * kh * kw)).astype(np.float32))
+    b = (rs.standard_normal(Cout) * 0.1).astype(np.float32)
+    y = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=(py, px))
+    y = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.1), 2: F.relu, 3: F.elu}[act](y).float().numpy()
+    dx = cu(x)
+    out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_conv2d(dptr(dx), w.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                      dptr(out), B, Cin, H, W, Cout, kh, kw, 1, py, px, 0, act, 1, None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    err = np.abs(got - y)
+    tol = 8e-3 * np.abs(y) + 4e-3          # bf16 output rounding (2^-9 rel) + fp32 accumulation order
+    assert (err <= tol).all(), "max err %g at %s (ref %g got %g)" % (
+        err.max(), np.unravel_index(err.argmax(), err.shape), y.flat[err.argmax()], got.flat[err.argmax()])
