@@ -7,6 +7,7 @@
 
 #include "liteflownet.h"
 #include "net_common.h"
+#include "ransac.h"
 
 namespace dfvo { const char* last_error(); }
 
@@ -220,6 +221,69 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
     return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
   DFVO_REQUIRE(stride == 1 && !reflect, DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1 and zero padding");
   return stage_conv<bf16>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_local_bestn(const float* flow_diff, const float* depth_diff, int H, int W, int rows, int cols, int num_bestN, float thre,
+                     float depth_thre, int32_t* idx_out, int32_t* cell_counts, int32_t* status, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(flow_diff && idx_out && cell_counts && status && H > 0 && W > 0 && rows > 0 && cols > 0, DFVO_EINVAL, "dfvo_local_bestn args");
+  int quota = num_bestN / (rows * cols);
+  DFVO_REQUIRE(quota > 0, DFVO_EINVAL, "dfvo_local_bestn: num_bestN < rows*cols");
+  return local_bestn(flow_diff, depth_diff, H, W, rows, cols, quota, thre, depth_thre, num_bestN, idx_out, cell_counts, status,
+                     (cudaStream_t)stream);
+  API_END
+}
+
+size_t dfvo_bestn_workspace_bytes(int H, int W) { return bestn_workspace_bytes(H, W); }
+
+int dfvo_bestn(const float* flow_diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(flow_diff && idx_out && workspace, DFVO_EINVAL, "dfvo_bestn args");
+  return bestn(flow_diff, H, W, N, idx_out, workspace, workspace_bytes, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int quota, const float* flow_fwd, int H, int W,
+                          double* kp1, double* kp2, int32_t* n_out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(idx && flow_fwd && kp1 && kp2, DFVO_EINVAL, "dfvo_gather_keypoints args");
+  return gather_keypoints(idx, cell_counts, ncells, quota, flow_fwd, H, W, kp1, kp2, n_out, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_five_point(const double* x1, const double* x2, int M, double* E, int32_t* n, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(x1 && x2 && E && n && M > 0, DFVO_EINVAL, "dfvo_five_point args");
+  return five_point(x1, x2, M, E, n, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_score_hypotheses(const double* E, int M, const double* x1, const double* x2, int N, double thr2, int32_t* counts,
+                          void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(E && x1 && x2 && counts && M > 0 && N > 0, DFVO_EINVAL, "dfvo_score_hypotheses args");
+  return score_hypotheses(E, M, x1, x2, N, thr2, counts, (cudaStream_t)stream);
+  API_END
+}
+
+size_t dfvo_essential_workspace_bytes(int N, int R, int max_iters) { return essential_workspace_bytes(N, R, max_iters); }
+
+int dfvo_essential_ransac(const double* p1, const double* p2, int N, const int32_t* perm, int R, const int32_t* subsets, int max_iters,
+                          double fx, double fy, double cx, double cy, double threshold, double prob, void* workspace,
+                          size_t workspace_bytes, double* E_out, uint8_t* mask_out, int32_t* info, double* gric, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(p1 && p2 && subsets && workspace && E_out && mask_out && info && gric, DFVO_EINVAL, "dfvo_essential_ransac args");
+  return essential_ransac(p1, p2, N, perm, R, subsets, max_iters, fx, fy, cx, cy, threshold, prob, workspace, workspace_bytes, E_out,
+                          mask_out, info, gric, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
+                      uint8_t* mask_out, int32_t* info, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(E && p1 && p2 && Rt_out && mask_out && info && N > 0, DFVO_EINVAL, "dfvo_recover_pose args");
+  return recover_pose(E, p1, p2, N, focal, cx, cy, Rt_out, mask_out, info, (cudaStream_t)stream);
   API_END
 }
 

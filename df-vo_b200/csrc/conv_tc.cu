@@ -9,7 +9,7 @@
 //     (the convolution's zero padding) and channels beyond the source's C are zero-filled by TMA.
 //   * B tile = TMA 3-D box {64 k, BLOCK_N, 1 tap} of the packed weights [tap][Cout_pad][Ktot].
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread issues tcgen05.mma, accumulators
-//     double-buffered in TMEM), warps 2-5 = epilogue (tcgen05.ld -> bias/act/residual -> global).
+//     double-buffered in TMEM), warps 2-9 = epilogue (tcgen05.ld -> bias/act/residual -> global).
 //   * persistent CTAs, static round-robin tile schedule, mbarrier full/empty smem ring.
 // Restates torch.nn.Conv2d(stride=1) + LeakyReLU/ELU/ReLU as used at lite_flow_net.py:98-240 and
 // depth_decoder.py / torchvision BasicBlock (BN folded by the weight packer).
@@ -94,6 +94,21 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// wait for outstanding tcgen05.ld; the registers are in/out operands so no use can be hoisted above it
+__device__ __forceinline__ void tc_ld_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -116,7 +131,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 
 }  // namespace tc
 
-#define TC_THREADS 192
+#define TC_THREADS 320
 #define TC_A_BYTES 16384
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -144,7 +159,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -224,8 +239,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
   } else {
     // ===================================== epilogue warps ====================================
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), two warps per quadrant split the columns.
+    const int ew = warp - 2;
+    const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int nchunks = p.block_n >> 4;
+    const int ch_begin = (ew < 4) ? 0 : ((nchunks + 1) >> 1);
+    const int ch_end = (ew < 4) ? ((nchunks + 1) >> 1) : nchunks;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
@@ -234,39 +255,33 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       const int n = t % p.N; const int nb = t / p.N;
       const int x = tx * p.tw + (row % p.tw), y = ty * p.th + (row / p.tw);
       const bool inb = x < p.W && y < p.H;
+      const int cbase = nb * p.block_n;
+      const long long opix = n * p.oN + y * p.oH + x * p.oW;
+      const long long rpix = n * p.rN + y * p.rH + x * p.rW;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-      const int cbase = nb * p.block_n;
-      for (int col = 0; col < p.block_n; col += 16) {
-        uint32_t v[16];
-        __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
-        tc_ld16(taddr0 + (uint32_t)col, v);
+
+      auto process = [&](const uint32_t* v, int col) {
         const int c = cbase + col;
-        if (inb && c < p.zero_pad_to) {
+        if (!(inb && c < p.zero_pad_to)) return;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias_s[c + j];
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + n * p.oN + y * p.oH + x * p.oW + c;
-          const float* r = p.res ? reinterpret_cast<const float*>(p.res) + n * p.rN + y * p.rH + x * p.rW + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (c + j < p.Cout) {
-              float val = f[j] + (r ? r[j] : 0.f);
-              o[j] = apply_act(val, p.act);
-            } else if (c + j < p.zero_pad_to) {
-              o[j] = 0.f;
-            }
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + n * p.oN + y * p.oH + x * p.oW + c;
-          const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + n * p.rN + y * p.rH + x * p.rW + c : nullptr;
+        for (int j = 0; j < 4; ++j) {
+          const float4 b = bias4[(c >> 2) + j];
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+        }
+        if (!p.out_f32) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
+          const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
           const bool full = (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
                             (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
           if (full) {
             if (r) {
-              uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+              const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
               const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -274,16 +289,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
               }
             }
+            switch (p.act) {            // one uniform branch per chunk, loops inside
+              case ACT_LEAKY:
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+                break;
+              case ACT_RELU:
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                break;
+              case ACT_ELU:
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+                break;
+              case ACT_SIGMOID:
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+                break;
+              default: break;
+            }
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
               w[j] = *reinterpret_cast<uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
-#pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (c + j < p.Cout) {
                 float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
@@ -293,8 +326,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
               }
             }
           }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + opix + c;
+          const float* r = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
+          for (int j = 0; j < 16; ++j) {
+            if (c + j < p.Cout) {
+              float val = f[j] + (r ? r[j] : 0.f);
+              o[j] = apply_act(val, p.act);
+            } else if (c + j < p.zero_pad_to) {
+              o[j] = 0.f;
+            }
+          }
         }
-        }
+      };
+
+      for (int ch = ch_begin; ch < ch_end; ch += 2) {
+        uint32_t v0[16], v1[16];
+        const bool two = ch + 1 < ch_end;
+        __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
+        tc_ld16_nowait(taddr0 + (uint32_t)(ch * 16), v0);
+        if (two) tc_ld16_nowait(taddr0 + (uint32_t)(ch * 16 + 16), v1);
+        tc_ld_wait16(v0);
+        if (two) tc_ld_wait16(v1);
+        process(v0, ch * 16);
+        if (two) process(v1, ch * 16 + 16);
       }
       tc_fence_before();
       __syncwarp();

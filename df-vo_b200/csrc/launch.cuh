@@ -7,4 +7,6 @@
 #include <cuda_runtime.h>
 #define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DFVO_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _dyn_smem_raw[]; \
+  type* name = reinterpret_cast<type*>(_dyn_smem_raw)
 #endif

@@ -96,5 +96,8 @@ int local_bestn(const float* diff, const float* depth_diff, int H, int W, int ro
 int bestn(const float* diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t ws_bytes,
           cudaStream_t s);
 size_t bestn_workspace_bytes(int H, int W);
+// idx: [ncells*n_best] slots (cell-major); cell_counts may be null (all slots valid, e.g. bestN with ncells=1)
+int gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int n_best, const float* flow_fwd, int H, int W,
+                     double* kp1, double* kp2, int32_t* n_out, cudaStream_t s);
 
 }  // namespace dfvo

@@ -1,0 +1,24 @@
+// Pose-solver launchers (ransac.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dfvo {
+
+// stage: M independent 5-point problems; x1/x2 [M][5][2] normalised; E [M][10][9], n [M]
+int five_point(const double* x1, const double* x2, int M, double* E, int32_t* n, cudaStream_t s);
+// stage: Sampson inlier counts of M models over N normalised correspondences (BASELINE config #4)
+int score_hypotheses(const double* E, int M, const double* x1, const double* x2, int N, double thr2, int32_t* counts,
+                     cudaStream_t s);
+size_t essential_workspace_bytes(int N, int R, int max_iters);
+// R repeats of cv2.findEssentialMat(p1[perm_r], p2[perm_r], focal=fx, pp=(cx,cy), RANSAC, prob, threshold) + GRIC-E.
+// perm [R][N] (may be null = identity), subsets [max_iters][5] = OpenCV's subset stream for this N.
+// outputs per repeat: E_out [R][9], mask_out [R][N] (ORIGINAL point order), info [R][4] = {inliers, iterations,
+// best iteration, best candidate}, gric [R].
+int essential_ransac(const double* p1, const double* p2, int N, const int32_t* perm, int R, const int32_t* subsets, int max_iters,
+                     double fx, double fy, double cx, double cy, double threshold, double prob, void* workspace, size_t ws_bytes,
+                     double* E_out, uint8_t* mask_out, int32_t* info, double* gric, cudaStream_t s);
+// cv2.recoverPose(E, p1, p2, focal, pp): Rt_out[12] = R (row-major) then t; mask [N]; info[5] = {count, c0..c3}
+int recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
+                 uint8_t* mask_out, int32_t* info, cudaStream_t s);
+
+}  // namespace dfvo

@@ -92,6 +92,49 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
                 int H, int W, int Cout, int kh, int kw, int stride, int pad_y, int pad_x, int reflect,
                 int act, int precision, void* stream);
 
+/* ---- correspondence selection (libs/matching) -----------------------------------------------------
+ * local_bestN, score_method 'flow' (kp_selection.py:74-200; KeypointSampler.kp_selection,
+ * keypoint_sampler.py:76-143).  flow_diff [H,W] fp32; depth_diff optional [H,W] (NULL = depth consistency
+ * off).  num_bestN = cfg.kp_selection.local_bestN.num_bestN (per-cell quota = floor(N/(rows*cols))).
+ * idx_out [rows*cols*quota] int32: per-cell slots, selected linear pixel indices (y*W+x) ascending, -1
+ * padded.  cell_counts [rows*cols].  status[0]=good_kp_found, [1]=#selected, [2]=#(diff<thre), [3]=#cells
+ * with >=1 keypoint.  The selected SET equals np.argpartition's; order is canonical. */
+int dfvo_local_bestn(const float* flow_diff, const float* depth_diff, int H, int W, int rows, int cols,
+                     int num_bestN, float thre, float depth_thre, int32_t* idx_out, int32_t* cell_counts,
+                     int32_t* status, void* stream);
+/* bestN_flow_kp (kp_selection.py:33-71): N smallest of the whole map, ascending linear index. */
+size_t dfvo_bestn_workspace_bytes(int H, int W);
+int dfvo_bestn(const float* flow_diff, int H, int W, int N, int32_t* idx_out, void* workspace,
+               size_t workspace_bytes, void* stream);
+/* kp1 = (x,y), kp2 = kp1 + flow_fwd[:,y,x] as float64 [n,2] (keypoint_sampler.py:101-104); compacts the
+ * slots of dfvo_local_bestn (cell_counts != NULL) or takes all ncells*quota entries (bestN: ncells=1). */
+int dfvo_gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int quota,
+                          const float* flow_fwd, int H, int W, double* kp1, double* kp2, int32_t* n_out,
+                          void* stream);
+
+/* ---- pose solvers (libs/tracker, FP64) ------------------------------------------------------------------
+ * 5-point minimal solver (inside cv2.findEssentialMat, E_tracker.py:231): M problems, x1/x2 [M][5][2]
+ * normalised image points -> E [M][10][9] (row-major, x2^T E x1 = 0, Frobenius-normalised), n [M]. */
+int dfvo_five_point(const double* x1, const double* x2, int M, double* E, int32_t* n, void* stream);
+/* Sampson inlier counts of M models over N normalised correspondences (BASELINE config #4). */
+int dfvo_score_hypotheses(const double* E, int M, const double* x1, const double* x2, int N, double thr2,
+                          int32_t* counts, void* stream);
+/* R repeats of cv2.findEssentialMat(p1[perm_r], p2[perm_r], focal=fx, pp=(cx,cy), RANSAC, prob, threshold)
+ * (E_tracker.py:223-286) + the GRIC-E score of each repeat's winner (gric.py).  p1 = kp_cur, p2 = kp_ref
+ * [N][2] pixels; perm [R][N] int32 = the host np.random.shuffle permutations (NULL: identity); subsets
+ * [max_iters][5] int32 = OpenCV's subset stream for this N (b200/cvrng.py).  Outputs per repeat: E_out
+ * [R][9], mask_out [R][N] uint8 in ORIGINAL point order, info [R][4] = {inliers, iterations run, winning
+ * iteration, winning candidate}, gric [R]. */
+size_t dfvo_essential_workspace_bytes(int N, int R, int max_iters);
+int dfvo_essential_ransac(const double* p1, const double* p2, int N, const int32_t* perm, int R,
+                          const int32_t* subsets, int max_iters, double fx, double fy, double cx, double cy,
+                          double threshold, double prob, void* workspace, size_t workspace_bytes,
+                          double* E_out, uint8_t* mask_out, int32_t* info, double* gric, void* stream);
+/* cv2.recoverPose(E, p1, p2, focal, pp) (E_tracker.py:292-295): Rt_out[12] = R row-major then t, mask [N],
+ * info[5] = {cheirality count, counts of the four (R,t) candidates}. */
+int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx,
+                      double cy, double* Rt_out, uint8_t* mask_out, int32_t* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

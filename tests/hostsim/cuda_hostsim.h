@@ -130,5 +130,7 @@ template <typename T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return 
 template <typename T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 inline void __threadfence() {}
 
+// dynamic shared memory: kernels declare it through DFVO_DYN_SMEM(type, name)
+#define DFVO_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(hostsim_dyn_smem)
 #define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
   hostsim::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
