@@ -44,6 +44,10 @@ SIGNATURES = {
     "dfvo_bestn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dfvo_gather_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "dfvo_monodepth2_build": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float]),
+    "dfvo_monodepth2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dfvo_depth_post": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p]),
     "dfvo_five_point": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dfvo_score_hypotheses": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "dfvo_essential_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -115,6 +119,12 @@ class Context:
 
     def liteflow_build(self, height, width, pairs=1, precision=PREC_BF16):
         self.lib.check(self.lib.dfvo_liteflow_build(self.h, height, width, pairs, precision))
+
+    def monodepth2_build(self, feed_h, feed_w, precision=PREC_BF16, min_depth=0.1, max_depth=100.0, baseline=5.4):
+        self.lib.check(self.lib.dfvo_monodepth2_build(self.h, feed_h, feed_w, precision, min_depth, max_depth, baseline))
+
+    def monodepth2_forward(self, img, depth_out, stream=0):
+        self.lib.check(self.lib.dfvo_monodepth2_forward(self.h, img, depth_out, stream))
 
     def liteflow_geometry(self):
         a, b, c = c_int(), c_int(), c_int()

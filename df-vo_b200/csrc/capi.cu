@@ -6,6 +6,7 @@
 #include <new>
 
 #include "liteflownet.h"
+#include "monodepth2.h"
 #include "net_common.h"
 #include "ransac.h"
 
@@ -17,6 +18,7 @@ struct dfvo_ctx {
   int device = 0;
   WeightStore weights[2];
   LiteFlowNetBase* lfn = nullptr;
+  Monodepth2Base* mono = nullptr;
 };
 
 #define API_BEGIN try {
@@ -129,6 +131,7 @@ int dfvo_destroy(dfvo_ctx* ctx) {
   API_BEGIN
   if (!ctx) return DFVO_OK;
   delete ctx->lfn;
+  delete ctx->mono;
   delete ctx;
   return DFVO_OK;
   API_END
@@ -221,6 +224,31 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
     return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
   DFVO_REQUIRE(stride == 1 && !reflect, DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1 and zero padding");
   return stage_conv<bf16>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, float min_depth, float max_depth, float baseline) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && (precision == 0 || precision == 1), DFVO_EINVAL, "dfvo_monodepth2_build args");
+  DFVO_CUDA(cudaSetDevice(ctx->device));
+  delete ctx->mono;
+  ctx->mono = nullptr;
+  return monodepth2_create(ctx->weights[DFVO_NET_MONODEPTH2], feed_h, feed_w, precision, min_depth, max_depth, baseline, &ctx->mono);
+  API_END
+}
+
+int dfvo_monodepth2_forward(dfvo_ctx* ctx, const float* img, float* depth_out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(ctx && ctx->mono && img && depth_out, DFVO_ESTATE, "dfvo_monodepth2_forward: call dfvo_monodepth2_build first");
+  return ctx->mono->run(img, depth_out, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1, float crop_x0, float crop_x1,
+                    float min_depth, float max_depth, float* raw_out, float* depth_out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(depth && depth_out && h > 0 && w > 0 && H > 0 && W > 0, DFVO_EINVAL, "dfvo_depth_post args");
+  return depth_post(depth, h, w, H, W, crop_y0, crop_y1, crop_x0, crop_x1, min_depth, max_depth, raw_out, depth_out, (cudaStream_t)stream);
   API_END
 }
 

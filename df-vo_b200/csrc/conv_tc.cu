@@ -452,7 +452,8 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   // tensor maps
   for (int s = 0; s < 3; ++s) {
     const ConvTcSource& src = c.src[s < c.nsrc ? s : 0];
-    cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+    const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
+    cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)inW, (cuuint64_t)inH, (cuuint64_t)c.N};
     cuuint64_t str[3] = {(cuuint64_t)src.sW * 2, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sN * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)k.tw, (cuuint32_t)k.th, 1};
     int rc = encode_map(&pl->tmA[s], src.p, 4, dims, str, box);
@@ -498,7 +499,8 @@ int conv_tc(const ConvTc& c, cudaStream_t) {
         for (int co = 0; co < c.Cout_pad; ++co) acc[co] = 0.f;
         for (int t = 0; t < c.ntaps; ++t) {
           int iy = y + c.dy[t], ix = x + c.dx[t];
-          if (iy < 0 || iy >= c.H || ix < 0 || ix >= c.W) continue;
+          const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
+          if (iy < 0 || iy >= inH || ix < 0 || ix >= inW) continue;
           int kofs = 0;
           for (int s = 0; s < c.nsrc; ++s) {
             const bf16* a = c.src[s].p + n * c.src[s].sN + iy * c.src[s].sH + ix * c.src[s].sW;

@@ -156,7 +156,9 @@ int run_conv<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<bf16> out, int ac
   DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc conv: input view has %d channels, layer expects %d", in.C, L.Ktot);
   ConvTc c;
   memset(&c, 0, sizeof(c));
-  c.N = in.N; c.H = in.H; c.W = in.W;
+  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W;
+  DFVO_REQUIRE(in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
+               "tc conv: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
   c.nsrc = 1;
   c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
   fill_taps(L, &c);

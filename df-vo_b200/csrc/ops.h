@@ -68,7 +68,9 @@ struct ConvTcSource {
   long long sN, sH, sW;   // strides in elements
 };
 struct ConvTc {
-  int N, H, W;            // output spatial size == input spatial size (stride 1)
+  int N, H, W;            // output spatial size (stride 1)
+  int inH, inW;           // input spatial size; 0 = same as output (zero padding through TMA OOB fill).  When
+                          // the input is pre-padded (reflection padding) use inH = H + kh - 1 and tap offsets >= 0
   int nsrc;               // 1..3 virtual-concat sources
   ConvTcSource src[3];
   int ntaps;              // kh*kw
@@ -88,6 +90,23 @@ struct ConvTc {
 int conv_tc(const ConvTc& c, cudaStream_t s);
 // tile shape chooser shared with tests
 void conv_tc_tile_shape(int H, int W, int* tw, int* th);
+
+// ---- monodepth2 helpers (depth_ops.cu) ----------------------------------------------------------------
+// NCHW float image -> NHWC T with (x - mean) / std  (resnet_encoder.py:89)
+template <typename T>
+int normalize_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float mean, float std, Ten<T> out, cudaStream_t s);
+// MaxPool2d(kernel 3, stride 2, padding 1)  (torchvision ResNet)
+template <typename T>
+int maxpool3x3s2(Ten<const T> in, Ten<T> out, cudaStream_t s);
+// out[(up*h + 2) x (up*w + 2)] = ReflectionPad2d(1)( cat( nearest_upsample(lo, up), skip ) )  (depth_decoder.py:54-60,
+// layers.py:121-136,347-350).  skip may be empty (p == nullptr).  up is 1 or 2.
+template <typename T>
+int upcat_reflect(Ten<const T> lo, int up, Ten<const T> skip, Ten<T> out, cudaStream_t s);
+// sigmoid disparity -> depth (layers.py:16-25, monodepth2.py:111-138): depth = baseline / (min_disp + (max_disp-min_disp)*disp)
+int disp_to_depth(const float* disp, int n, float min_depth, float max_depth, float baseline, float* depth, cudaStream_t s);
+// cv2.resize(INTER_NEAREST) to (W,H) + preprocess_depth (dfvo.py:314-319, utils.py:89-114)
+int depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1, float crop_x0, float crop_x1,
+               float min_depth, float max_depth, float* raw_out, float* depth_out, cudaStream_t s);
 
 // ---- keypoint selection (select.cu) -------------------------------------------------------------
 int local_bestn(const float* diff, const float* depth_diff, int H, int W, int rows, int cols, int n_best,

@@ -74,6 +74,20 @@ int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs_host_array, 
 int dfvo_liteflow_level_flow(dfvo_ctx* ctx, int level, float* out);
 int dfvo_liteflow_geometry(dfvo_ctx* ctx, int* net_h, int* net_w, int* batch);
 
+/* ---- monodepth2: DeepModel.forward_depth (deep_models.py:184-206) -------------------------------------
+ * feed size = checkpoint 'height'/'width' (monodepth2.py:70-71); (min_depth, max_depth, baseline) are the
+ * dataset constants of monodepth2.py:73-88 (kitti: 0.1, 100, 5.4). */
+int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, float min_depth,
+                          float max_depth, float baseline);
+/* img: float [1,3,feed_h,feed_w] in [0,1] (the PIL-LANCZOS-resized ToTensor image, deep_models.py:195-201);
+ * depth_out [feed_h,feed_w] fp32 = Monodepth2DepthNet.inference_depth (monodepth2.py:121-139). */
+int dfvo_monodepth2_forward(dfvo_ctx* ctx, const float* img, float* depth_out, void* stream);
+/* cv2.resize(raw_depth, (W,H), INTER_NEAREST) + utils.preprocess_depth (dfvo.py:314-319, utils.py:89-114):
+ * depth [h,w] -> raw_out [H,W] (may be NULL), depth_out [H,W]; crop = [[y0,y1],[x0,x1]] normalised. */
+int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1,
+                    float crop_x0, float crop_x1, float min_depth, float max_depth, float* raw_out,
+                    float* depth_out, void* stream);
+
 /* ---- stage-level entry points (parity tests; NCHW fp32 at the boundary like the reference) -----
  * FunctionCorrelation (correlation.py:400-402) [+ LeakyReLU if leaky]: first/second [B,C,H,W]
  * -> out [B,49,ceil(H/s),ceil(W/s)].  precision selects the fp32 or bf16 kernel. */
