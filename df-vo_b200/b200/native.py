@@ -54,6 +54,8 @@ SIGNATURES = {
     "dfvo_essential_ransac": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_double,
                                       c_double, c_double, c_double, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    "dfvo_cv_subset_stream_host": (c_int, [c_int, c_int, c_int, c_void_p]),
+    "dfvo_triangulate_depth": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dfvo_recover_pose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
 }

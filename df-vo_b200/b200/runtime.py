@@ -1,0 +1,108 @@
+"""Device memory / stream plumbing for the host side (PyTorch is used for exactly this: allocation,
+H2D/D2H copies, streams -- never for arithmetic on the hot path).
+
+``get()`` returns the process-wide runtime.  The product runtime is :class:`CudaRuntime`; it refuses
+to exist without a CUDA device.  The CPU test-suite injects the host-emulation runtime from
+``tests/hostsim`` with :func:`set_runtime` so the very same host logic (libs mirror, pipeline) can be
+exercised without a GPU -- that object lives in the test tree, not here.
+"""
+import ctypes
+
+import numpy as np
+
+from . import native
+
+
+class Buf:
+    """A typed device buffer: ``ptr`` (ctypes void*), ``shape``, ``dtype`` (numpy dtype)."""
+
+    __slots__ = ("t", "shape", "dtype", "rt")
+
+    def __init__(self, t, shape, dtype, rt):
+        self.t, self.shape, self.dtype, self.rt = t, tuple(shape), np.dtype(dtype), rt
+
+    @property
+    def ptr(self):
+        return self.rt.ptr_of(self.t)
+
+    def numpy(self):
+        """Blocking copy to a new host array."""
+        return self.rt.to_host(self)
+
+    def upload(self, arr):
+        self.rt.upload(self, arr)
+        return self
+
+
+_TORCH_DTYPES = None
+
+
+def _torch_dtype(dt):
+    global _TORCH_DTYPES
+    import torch
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                         np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+                         np.dtype(np.int64): torch.int64}
+    return _TORCH_DTYPES[np.dtype(dt)]
+
+
+class CudaRuntime:
+    """torch.cuda-backed runtime of the product."""
+
+    is_device = True
+
+    def __init__(self, device=0):
+        import torch
+        native.require_cuda()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.lib = native.load()
+        self.stream = None          # None -> torch's current stream (0 = legacy default is never used implicitly)
+
+    def stream_ptr(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype):
+        t = self.torch.empty(tuple(shape), dtype=_torch_dtype(dtype), device=self.device)
+        return Buf(t, shape, dtype, self)
+
+    def zeros(self, shape, dtype):
+        t = self.torch.zeros(tuple(shape), dtype=_torch_dtype(dtype), device=self.device)
+        return Buf(t, shape, dtype, self)
+
+    def from_host(self, arr):
+        arr = np.ascontiguousarray(arr)
+        t = self.torch.from_numpy(arr).to(self.device, non_blocking=False)
+        return Buf(t, arr.shape, arr.dtype, self)
+
+    def upload(self, buf, arr):
+        buf.t.copy_(self.torch.from_numpy(np.ascontiguousarray(arr, dtype=buf.dtype).reshape(buf.shape)))
+
+    def to_host(self, buf):
+        return buf.t.cpu().numpy()
+
+    def ptr_of(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def pinned(self, shape, dtype):
+        return self.torch.empty(tuple(shape), dtype=_torch_dtype(dtype)).pin_memory()
+
+
+_runtime = None
+
+
+def set_runtime(rt):
+    global _runtime
+    _runtime = rt
+
+
+def get():
+    global _runtime
+    if _runtime is None:
+        _runtime = CudaRuntime()
+    return _runtime

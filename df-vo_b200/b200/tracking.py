@@ -1,0 +1,214 @@
+"""Device-side building blocks of one DF-VO tracking step, shared by the reference-API mirror
+(``df-vo_b200/libs``) and the device-resident pipeline (``b200/pipeline.py``).
+
+Every numeric step is a call into the C ABI (``include/dfvo_b200.h``); this module only owns buffers,
+the order of calls and the few host-side decisions the reference makes on the host as well (RNG draws,
+majority vote, sentinels).  There is no CPU implementation of the kernels here.
+"""
+import ctypes
+
+import numpy as np
+
+from . import hostmath, native
+from . import runtime as rt_mod
+
+KITTI_DEPTH = dict(min_depth=0.1, max_depth=100.0, baseline=5.4)      # monodepth2.py:73-77
+TUM_DEPTH = dict(min_depth=0.1, max_depth=10.0, baseline=1.0)         # monodepth2.py:78-81
+
+
+def depth_constants(dataset):
+    return TUM_DEPTH if "tum" in dataset else KITTI_DEPTH
+
+
+class Engine:
+    """One ``dfvo_ctx`` + its buffers for a fixed image size."""
+
+    def __init__(self, height, width, runtime=None):
+        self.rt = runtime or rt_mod.get()
+        self.lib = self.rt.lib
+        self.ctx = native.Context(self.lib)
+        self.H, self.W = int(height), int(width)
+        self.flow_ready = False
+        self.depth_ready = False
+        self._subsets = {}          # N -> device table of OpenCV's 5-point subset stream
+        self._ess_ws = {}
+
+    # ------------------------------------------------------------------ networks
+    def build_flow(self, weights, pairs=1, precision=native.PREC_BF16):
+        self.ctx.load_weights(native.NET_LITEFLOWNET, weights)
+        self.ctx.liteflow_build(self.H, self.W, pairs, precision)
+        self.pairs = pairs
+        self.flow_fwd = self.rt.empty((pairs, 2, self.H, self.W), np.float32)
+        self.flow_bwd = self.rt.empty((pairs, 2, self.H, self.W), np.float32)
+        self.flow_diff = self.rt.empty((pairs, self.H, self.W), np.float32)
+        self.flow_ready = True
+
+    def build_depth(self, enc, dec, precision=native.PREC_BF16, dataset="kitti_odom"):
+        self.ctx.load_weights(native.NET_MONODEPTH2, enc)
+        self.ctx.load_weights(native.NET_MONODEPTH2, dec)
+        self.feed_h, self.feed_w = int(enc["height"]), int(enc["width"])
+        c = depth_constants(dataset)
+        self.ctx.monodepth2_build(self.feed_h, self.feed_w, precision, c["min_depth"], c["max_depth"], c["baseline"])
+        self.depth_feed = self.rt.empty((self.feed_h, self.feed_w), np.float32)
+        self.depth_ready = True
+
+    def flow(self, img_bufs):
+        """img_bufs: 2*pairs uint8 HWC device buffers [ref0, cur0, ...] -> (fwd, bwd, diff) buffers."""
+        assert self.flow_ready, "build_flow first"
+        ptrs = [b.ptr.value for b in img_bufs]
+        self.ctx.liteflow_forward(ptrs, self.flow_fwd.ptr, self.flow_bwd.ptr, self.flow_diff.ptr, self.rt.stream_ptr())
+        return self.flow_fwd, self.flow_bwd, self.flow_diff
+
+    def depth(self, feed_buf, out=None):
+        """feed_buf: float32 [1,3,feed_h,feed_w] device buffer -> depth [feed_h, feed_w]."""
+        assert self.depth_ready, "build_depth first"
+        out = out or self.depth_feed
+        self.ctx.monodepth2_forward(feed_buf.ptr, out.ptr, self.rt.stream_ptr())
+        return out
+
+    def depth_post(self, depth_buf, crop, min_depth, max_depth, raw_out=None, out=None):
+        raw_out = raw_out or self.rt.empty((self.H, self.W), np.float32)
+        out = out or self.rt.empty((self.H, self.W), np.float32)
+        h, w = depth_buf.shape[-2:]
+        self.lib.check(self.lib.dfvo_depth_post(depth_buf.ptr, h, w, self.H, self.W, crop[0][0], crop[0][1], crop[1][0],
+                                                crop[1][1], min_depth, max_depth, raw_out.ptr, out.ptr, self.rt.stream_ptr()))
+        return raw_out, out
+
+    # ------------------------------------------------------------------ selection
+    def select_local_bestn(self, diff_buf, flow_fwd_buf, rows, cols, num_bestN, thre, depth_diff_buf=None, depth_thre=0.05):
+        """local_bestN (kp_selection.py:74-200) + keypoint gather.  Returns (good, n, kp1, kp2, mask-less)
+        with kp buffers float64 [num_bestN, 2] (first n rows valid).  One small D2H (status)."""
+        quota = num_bestN // (rows * cols)
+        if not hasattr(self, "_sel"):
+            self._sel = dict(idx=self.rt.empty((rows * cols * quota,), np.int32), cc=self.rt.empty((rows * cols,), np.int32),
+                             st=self.rt.empty((4,), np.int32), kp1=self.rt.empty((rows * cols * quota, 2), np.float64),
+                             kp2=self.rt.empty((rows * cols * quota, 2), np.float64), n=self.rt.empty((1,), np.int32))
+        s = self._sel
+        st = self.rt.stream_ptr()
+        self.lib.check(self.lib.dfvo_local_bestn(diff_buf.ptr, depth_diff_buf.ptr if depth_diff_buf else None, self.H, self.W,
+                                                 rows, cols, num_bestN, thre, depth_thre, s["idx"].ptr, s["cc"].ptr, s["st"].ptr, st))
+        self.lib.check(self.lib.dfvo_gather_keypoints(s["idx"].ptr, s["cc"].ptr, rows * cols, quota, flow_fwd_buf.ptr, self.H,
+                                                      self.W, s["kp1"].ptr, s["kp2"].ptr, s["n"].ptr, st))
+        status = s["st"].numpy()
+        return bool(status[0]), int(status[1]), s["kp1"], s["kp2"]
+
+    def select_bestn(self, diff_buf, flow_fwd_buf, N):
+        """bestN_flow_kp (kp_selection.py:33-71)."""
+        if not hasattr(self, "_bsel"):
+            nb = int(self.lib.dfvo_bestn_workspace_bytes(self.H, self.W))
+            self._bsel = dict(idx=self.rt.empty((N,), np.int32), ws=self.rt.empty((nb,), np.uint8),
+                              kp1=self.rt.empty((N, 2), np.float64), kp2=self.rt.empty((N, 2), np.float64))
+        s = self._bsel
+        st = self.rt.stream_ptr()
+        self.lib.check(self.lib.dfvo_bestn(diff_buf.ptr, self.H, self.W, N, s["idx"].ptr, s["ws"].ptr, s["ws"].shape[0], st))
+        self.lib.check(self.lib.dfvo_gather_keypoints(s["idx"].ptr, None, 1, N, flow_fwd_buf.ptr, self.H, self.W, s["kp1"].ptr,
+                                                      s["kp2"].ptr, None, st))
+        return True, N, s["kp1"], s["kp2"]
+
+    # ------------------------------------------------------------------ pose
+    def _subset_table(self, n, max_iters=1000):
+        key = (n, max_iters)
+        if key not in self._subsets:
+            host = np.zeros((max_iters, 5), np.int32)
+            self.lib.check(self.lib.dfvo_cv_subset_stream_host(n, 5, max_iters, host.ctypes.data_as(ctypes.c_void_p)))
+            self._subsets[key] = self.rt.from_host(host)
+        return self._subsets[key]
+
+    def essential_launch(self, kp_cur_buf, kp_ref_buf, n, perms, K, threshold=0.2, prob=0.99, max_iters=1000):
+        """Enqueue R = len(perms) repeats of findEssentialMat(kp_cur[perm], kp_ref[perm]) + GRIC-E
+        (E_tracker.py:223-286).  Returns a handle for :meth:`essential_result`."""
+        cx, cy, fx, fy = K
+        R = len(perms)
+        key = (n, R, max_iters)
+        if key not in self._ess_ws:
+            nb = int(self.lib.dfvo_essential_workspace_bytes(n, R, max_iters))
+            self._ess_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), E=self.rt.empty((R, 9), np.float64),
+                                     mask=self.rt.empty((R, n), np.uint8), info=self.rt.empty((R, 4), np.int32),
+                                     gric=self.rt.empty((R,), np.float64), perm=self.rt.empty((R, n), np.int32),
+                                     Rt=self.rt.empty((12,), np.float64), pmask=self.rt.empty((n,), np.uint8),
+                                     pinfo=self.rt.empty((5,), np.int32))
+        w = self._ess_ws[key]
+        w["perm"].upload(np.asarray(perms, np.int32))
+        self.lib.check(self.lib.dfvo_essential_ransac(kp_cur_buf.ptr, kp_ref_buf.ptr, n, w["perm"].ptr, R,
+                                                      self._subset_table(n, max_iters).ptr, max_iters, fx, fy, cx, cy, threshold,
+                                                      prob, w["ws"].ptr, w["ws"].shape[0], w["E"].ptr, w["mask"].ptr,
+                                                      w["info"].ptr, w["gric"].ptr, self.rt.stream_ptr()))
+        return w
+
+    def recover_pose(self, w, best, kp_cur_buf, kp_ref_buf, n, K):
+        """cv2.recoverPose(best_E, kp_cur, kp_ref, focal=fx, pp) (E_tracker.py:292-295)."""
+        cx, cy, fx, fy = K
+        e_ptr = ctypes.c_void_p(w["E"].ptr.value + best * 9 * 8)
+        self.lib.check(self.lib.dfvo_recover_pose(e_ptr, kp_cur_buf.ptr, kp_ref_buf.ptr, n, fx, cx, cy, w["Rt"].ptr,
+                                                  w["pmask"].ptr, w["pinfo"].ptr, self.rt.stream_ptr()))
+        return w["Rt"].numpy(), int(w["pinfo"].numpy()[0])
+
+    def triangulate_depth(self, kp1n_buf, kp2n_buf, n, T21):
+        if not hasattr(self, "_tri") or self._tri["z"].shape[0] < n:
+            self._tri = dict(z=self.rt.empty((max(n, 2048),), np.float64), T=self.rt.empty((12,), np.float64))
+        t = self._tri
+        t["T"].upload(np.asarray(T21, np.float64)[:3].reshape(-1))
+        self.lib.check(self.lib.dfvo_triangulate_depth(kp1n_buf.ptr, kp2n_buf.ptr, n, t["T"].ptr, t["z"].ptr, self.rt.stream_ptr()))
+        return t["z"].numpy()[:n]
+
+
+# ---------------------------------------------------------------------------------------------
+# host-level orchestration of the E-tracker (E_tracker.py:154-307, validity.method == 'GRIC')
+# ---------------------------------------------------------------------------------------------
+def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=np.random, kp_ref_buf=None, kp_cur_buf=None):
+    """Same contract as ``EssTracker.compute_pose_2d2d`` with the default GRIC validity check.
+    kp_ref/kp_cur: float64 [N,2] host arrays (device copies optional).  The five RANSAC repeats, their
+    GRIC-E scores and recoverPose run on the device; cv2.findHomography + GRIC-H (the model-selection
+    counterpart) still run on the host and overlap with the device work.
+    Returns dict(R, t, inliers, valid, cheirality)."""
+    import cv2
+    n = kp_ref.shape[0]
+    R, t = np.eye(3), np.zeros((3, 1))
+    out = dict(R=R, t=t, inliers=np.ones(n, bool), valid=False, cheirality=0)
+    if n <= 10:                                                     # E_tracker.py:196,216-217
+        return out
+    # host RNG consumption identical to the reference: one shuffle per repeat (E_tracker.py:225-226)
+    perms = []
+    for _ in range(repeat):
+        order = np.arange(0, n, 1)
+        rng.shuffle(order)
+        perms.append(order)
+    rt = engine.rt
+    kp_cur_buf = kp_cur_buf or rt.from_host(kp_cur)
+    kp_ref_buf = kp_ref_buf or rt.from_host(kp_ref)
+    w = engine.essential_launch(kp_cur_buf, kp_ref_buf, n, perms, K, threshold=reproj_thre)
+    # ---- host, concurrently with the device RANSAC: homography model (E_tracker.py:199-215)
+    H, _ = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
+    H_gric = hostmath.calc_gric(hostmath.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
+    info = w["info"].numpy()
+    gric = w["gric"].numpy()
+    best, best_cnt, num_valid = -1, 0, 0
+    for r in range(repeat):
+        if info[r, 0] > best_cnt:                                   # strict '>' keeps the first maximum (:278-281)
+            best, best_cnt = r, int(info[r, 0])
+        num_valid += int(H_gric > gric[r])                          # :270,286
+    out["valid"] = num_valid > repeat / 2
+    out["H_gric"], out["E_gric"], out["ransac_info"] = H_gric, gric, info
+    if best >= 0:
+        out["inliers"] = w["mask"].numpy()[best].astype(bool)
+    if out["valid"] and best >= 0:
+        Rt, cheir = engine.recover_pose(w, best, kp_cur_buf, kp_ref_buf, n, K)
+        out["cheirality"] = cheir
+        if cheir > n * 0.1:                                         # :299-300
+            out["R"], out["t"] = Rt[:9].reshape(3, 3).copy(), Rt[9:].reshape(3, 1).copy()
+    return out
+
+
+def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1,
+                          rng=np.random):
+    """``EssTracker.find_scale_from_depth`` (E_tracker.py:571-643): triangulation on the device, the
+    (tiny, RNG-consuming) scale RANSAC on the host."""
+    cx, cy, fx, fy = K
+    n = kp1.shape[0]
+    k1 = (kp1 - np.array([cx, cy])) / np.array([fx, fy])
+    k2 = (kp2 - np.array([cx, cy])) / np.array([fx, fy])
+    z = engine.triangulate_depth(engine.rt.from_host(k1), engine.rt.from_host(k2), n, T_21)
+    ratio, nvalid = hostmath.last_writer_depth_ratio(kp2, z, depth2)
+    if nvalid > 10:
+        return hostmath.ransac_scale(ratio, min_samples, max_trials, stop_prob, thre, rng)
+    return -1

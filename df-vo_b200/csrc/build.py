@@ -11,6 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["capi.cu", "net_common.cu", "flow_ops.cu", "conv_direct.cu", "conv_tc.cu", "liteflownet.cu", "select.cu", "ransac.cu", "depth_ops.cu", "monodepth2.cu"]
+NO_FMA = {"ransac.cu"}
 OUT = os.path.join(HERE, "libdfvo_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -36,7 +37,9 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "_obj_" + src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", os.path.join(HERE, src), "-o", obj]
+        # the FP64 pose solvers make threshold decisions that were validated without FMA contraction
+        extra = ["-fmad=false"] if src in NO_FMA else []
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", os.path.join(HERE, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

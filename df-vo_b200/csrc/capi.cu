@@ -307,6 +307,32 @@ int dfvo_essential_ransac(const double* p1, const double* p2, int N, const int32
   API_END
 }
 
+int dfvo_cv_subset_stream_host(int count, int model_points, int n_subsets, int32_t* out) {
+  API_BEGIN
+  DFVO_REQUIRE(out && count >= model_points && model_points > 0 && model_points <= 16 && n_subsets > 0, DFVO_EINVAL, "dfvo_cv_subset_stream_host args");
+  uint64_t state = 0xFFFFFFFFFFFFFFFFull;                       // cv::RNG((uint64)-1)
+  for (int s = 0; s < n_subsets; ++s) {
+    int32_t* idx = out + (size_t)s * model_points;
+    for (int i = 0; i < model_points;) {
+      state = (uint64_t)(uint32_t)state * 4164903690u + (uint32_t)(state >> 32);   // cv::RNG::next
+      int v = (int)((uint32_t)state % (uint32_t)count);         // uniform(0, count)
+      bool dup = false;
+      for (int j = 0; j < i; ++j) dup = dup || idx[j] == v;
+      if (dup) continue;
+      idx[i++] = v;
+    }
+  }
+  return DFVO_OK;
+  API_END
+}
+
+int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(x1 && x2 && T21 && depth2 && N > 0, DFVO_EINVAL, "dfvo_triangulate_depth args");
+  return triangulate_depth(x1, x2, N, T21, depth2, (cudaStream_t)stream);
+  API_END
+}
+
 int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
                       uint8_t* mask_out, int32_t* info, void* stream) {
   API_BEGIN

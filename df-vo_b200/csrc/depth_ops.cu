@@ -108,12 +108,14 @@ int disp_to_depth(const float* disp, int n, float min_depth, float max_depth, fl
   return DFVO_OK;
 }
 
-// cv2.resize(..., INTER_NEAREST): sx = floor(dx * (w / W)) computed in double, clamped (OpenCV resizeNN)
+// cv2.resize(..., INTER_NEAREST) (OpenCV resizeNN): inv_scale = W / w, ifx = 1 / inv_scale,
+// sx = min(floor(dx * ifx), w - 1), all in double -- note 1/(W/w) is not bit-identical to w/W
 __global__ void k_depth_post(const float* __restrict__ depth, int h, int w, int H, int W, int y0, int y1, int x0, int x1,
                              float min_depth, float max_depth, float* __restrict__ raw_out, float* __restrict__ depth_out) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W) return;
-  int sy = (int)floor((double)y * ((double)h / (double)H)), sx = (int)floor((double)x * ((double)w / (double)W));
+  const double ify = 1.0 / ((double)H / (double)h), ifx = 1.0 / ((double)W / (double)w);
+  int sy = (int)floor((double)y * ify), sx = (int)floor((double)x * ifx);
   sy = sy < h - 1 ? sy : h - 1; sx = sx < w - 1 ? sx : w - 1;
   float d = depth[(size_t)sy * w + sx];
   if (raw_out) raw_out[(size_t)y * W + x] = d;

@@ -362,6 +362,24 @@ k_recover_pose(const double* __restrict__ Eptr, const double* __restrict__ p1, c
   for (int j = t; j < N; j += 256) mask_out[j] = (mask_out[j] >> b) & 1u;
 }
 
+__global__ void k_triangulate_depth(const double* __restrict__ x1, const double* __restrict__ x2, int N, const double* __restrict__ T21,
+                                    double* __restrict__ depth2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double P[3][4];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 4; ++b) P[a][b] = T21[4 * a + b];
+  double X[4];
+  triangulate_dlt(P, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], X);
+  const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];           // X /= X[3]  (ops_3d.py:64)
+  depth2[i] = P[2][0] * x + P[2][1] * y + P[2][2] * z + P[2][3];             // X2 = T_2w[:3] @ X
+}
+
+int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s) {
+  DFVO_LAUNCH(k_triangulate_depth, dim3(cdiv(N, 128)), dim3(128), 0, s, x1, x2, N, T21, depth2);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 int recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
                  uint8_t* mask_out, int32_t* info, cudaStream_t s) {
   DFVO_LAUNCH(k_recover_pose, dim3(1), dim3(256), 0, s, E, p1, p2, N, focal, cx, cy, 50.0, Rt_out, mask_out, info);

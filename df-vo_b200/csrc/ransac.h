@@ -21,4 +21,7 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
 int recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
                  uint8_t* mask_out, int32_t* info, cudaStream_t s);
 
+// ops_3d.triangulation(kp1n, kp2n, eye(4), T_21) -> z of X2 per point (ops_3d.py:44-67)
+int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s);
+
 }  // namespace dfvo

@@ -144,6 +144,13 @@ int dfvo_essential_ransac(const double* p1, const double* p2, int N, const int32
                           const int32_t* subsets, int max_iters, double fx, double fy, double cx, double cy,
                           double threshold, double prob, void* workspace, size_t workspace_bytes,
                           double* E_out, uint8_t* mask_out, int32_t* info, double* gric, void* stream);
+/* OpenCV's RANSAC subset stream (cv::RNG((uint64)-1) + getSubset, ptsetreg.cpp): the model_points-tuples
+ * findEssentialMat / solvePnPRansac draw for `count` correspondences depend only on `count`.  HOST function:
+ * out_host [n_subsets][model_points] int32. */
+int dfvo_cv_subset_stream_host(int count, int model_points, int n_subsets, int32_t* out_host);
+/* cv::triangulatePoints([I|0], T_21[:3], x1, x2) followed by X2 = T_21[:3] X / X_w (ops_3d.py:44-67): x1, x2
+ * [N][2] normalised (float64), T21 [12] row-major 3x4 -> depth2 [N] = z of the point in view 2. */
+int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, void* stream);
 /* cv2.recoverPose(E, p1, p2, focal, pp) (E_tracker.py:292-295): Rt_out[12] = R row-major then t, mask [N],
  * info[5] = {cheirality count, counts of the four (R,t) candidates}. */
 int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx,

@@ -17,11 +17,11 @@ import numpy as np
 # depth post-processing  (dfvo.py:314-319, utils.py:89-114)
 # ----------------------------------------------------------------------------------------
 def resize_nearest(depth, W, H):
-    """``cv2.resize(depth, (W, H), interpolation=cv2.INTER_NEAREST)``: src index =
-    floor(dst * in / out) (OpenCV's INTER_NEAREST uses ``floor(x * scale)`` with scale=in/out)."""
+    """``cv2.resize(depth, (W, H), interpolation=cv2.INTER_NEAREST)`` (OpenCV resizeNN): src index =
+    min(floor(dst * ifx), in - 1) with ``ifx = 1 / (out / in)`` in float64 (not bit-identical to in/out)."""
     h, w = depth.shape
-    ys = np.minimum((np.arange(H) * (h / H)).astype(np.int64), h - 1)
-    xs = np.minimum((np.arange(W) * (w / W)).astype(np.int64), w - 1)
+    ys = np.minimum(np.floor(np.arange(H) * (1.0 / (H / h))).astype(np.int64), h - 1)
+    xs = np.minimum(np.floor(np.arange(W) * (1.0 / (W / w))).astype(np.int64), w - 1)
     return depth[ys][:, xs]
 
 
