@@ -212,3 +212,47 @@ def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_
     if nvalid > 10:
         return hostmath.ransac_scale(ratio, min_samples, max_trials, stop_prob, thre, rng)
     return -1
+
+
+# ---------------------------------------------------------------------------------------------
+# process-wide default engine (the libs mirror's DeepModel / trackers share one dfvo_ctx)
+# ---------------------------------------------------------------------------------------------
+_default_engine = None
+
+
+def default_engine(height=None, width=None):
+    global _default_engine
+    if _default_engine is None or (height is not None and (_default_engine.H, _default_engine.W) != (height, width)):
+        if height is None:
+            raise native.DfvoError("no dfvo_b200 engine yet: construct libs.deep_models.DeepModel (or tracking.Engine) first")
+        _default_engine = Engine(height, width)
+    return _default_engine
+
+
+class DevArray:
+    """A device-resident array that behaves enough like ``numpy.ndarray`` for the reference driver
+    (``.copy()``, ``.shape``, indexing, ``np.asarray``) while the hot path keeps using ``.dev``.
+    Host materialisation happens lazily, once, and only if somebody (e.g. the visualiser) asks."""
+
+    def __init__(self, dev, shape=None, view=None):
+        self.dev = dev
+        self.shape = tuple(shape if shape is not None else dev.shape)
+        self.dtype = dev.dtype
+        self.ndim = len(self.shape)
+        self._view = view            # optional callable applied to the host copy (e.g. reshape)
+        self._host = None
+
+    def copy(self):
+        return self
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            h = self.dev.numpy()
+            self._host = (self._view(h) if self._view else h).reshape(self.shape)
+        return self._host if dtype is None else self._host.astype(dtype)
+
+    def __getitem__(self, k):
+        return np.asarray(self)[k]
+
+    def __len__(self):
+        return self.shape[0]

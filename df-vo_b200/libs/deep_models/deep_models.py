@@ -1,0 +1,110 @@
+"""``DeepModel`` facade with the reference's interface (libs/deep_models/deep_models.py:25-350), backed by
+the dfvo_b200 CUDA library: LiteFlowNet forward+backward flow with the forward-backward consistency map,
+and monodepth2 single-view depth.  Inference only -- the online-finetuning half of the reference class
+(``setup_train``, ``finetune``, ``save_model``) and the experimental PoseNet are outside the hot path
+ and raise ``NotImplementedError``.
+"""
+import os
+
+import numpy as np
+
+from b200 import native, runtime, tracking
+
+
+def _load_state_dict(path):
+    """Checkpoint IO (torch.load, lite_flow.py:45 / monodepth2.py:47-55) -> {key: float32 ndarray}."""
+    import torch
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    out = {}
+    for k, v in sd.items():
+        out[k] = v.detach().float().numpy() if hasattr(v, "detach") else v
+    return out
+
+
+class _FlowHandle:
+    """What the driver / tools read on ``deep_models.flow`` (SURVEY 8b 'attributes read on sub-objects')."""
+    flow_scales = [1]
+    enable_finetune = False
+    half_flow = False
+
+
+class _DepthHandle:
+    enable_finetune = False
+    depth_scales = [0]
+
+
+class DeepModel:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.finetune_cfg = cfg.online_finetune
+        self.precision = native.PREC_FP32 if os.environ.get("DFVO_B200_PRECISION", "bf16") == "fp32" else native.PREC_BF16
+        self.engine = tracking.default_engine(cfg.image.height, cfg.image.width)
+        self.rt = self.engine.rt
+
+    # ------------------------------------------------------------------ setup (deep_models.py:38-117)
+    def initialize_models(self):
+        assert not self.finetune_cfg.enable, "dfvo_b200 is inference-only (online_finetune.enable must be False)"
+        self.flow = self.initialize_deep_flow_model()
+        if self.cfg.depth.depth_src is None:
+            assert self.cfg.depth.deep_depth.pretrained_model is not None, "No precomputed depths nor pretrained depth model"
+            self.depth = self.initialize_deep_depth_model()
+        assert not self.cfg.deep_pose.enable, "deep_pose (PoseNet) is outside the dfvo_b200 hot path"
+
+    def initialize_deep_flow_model(self):
+        assert self.cfg.deep_flow.network == "liteflow", "Invalid flow network [{}] is provided.".format(self.cfg.deep_flow.network)
+        path = self.cfg.deep_flow.flow_net_weight
+        assert path is not None, "No LiteFlowNet pretrained model is provided."
+        print("==> Initialize LiteFlowNet with [{}]: ".format(path))
+        self.engine.build_flow(_load_state_dict(path), pairs=1, precision=self.precision)
+        return _FlowHandle()
+
+    def initialize_deep_depth_model(self):
+        assert self.cfg.depth.deep_depth.network == "monodepth2", "Invalid depth network"
+        wdir = self.cfg.depth.deep_depth.pretrained_model
+        print("==> Initialize Depth-CNN with [{}]".format(wdir))
+        enc = _load_state_dict(os.path.join(wdir, "encoder.pth"))
+        dec = _load_state_dict(os.path.join(wdir, "depth.pth"))
+        self.engine.build_depth(enc, dec, precision=self.precision, dataset=self.cfg.dataset)
+        h = _DepthHandle()
+        h.feed_height, h.feed_width = self.engine.feed_h, self.engine.feed_w          # monodepth2.py:70-71
+        c = tracking.depth_constants(self.cfg.dataset)
+        h.min_depth, h.max_depth, h.stereo_baseline_multiplier = c["min_depth"], c["max_depth"], c["baseline"]
+        return h
+
+    def setup_train(self):
+        raise NotImplementedError("online finetuning is outside the dfvo_b200 hot path (SURVEY.md section 8f rank 4)")
+
+    # ------------------------------------------------------------------ inference
+    def forward_flow(self, in_cur_data, in_ref_data, forward_backward):
+        """deep_models.py:144-182.  Values are device-backed arrays (``tracking.DevArray``): [2,H,W] flows
+        and the [H,W,1] inconsistency map; they convert to NumPy on demand."""
+        assert forward_backward, "dfvo_b200 always computes forward+backward flow (deep_flow.forward_backward: True)"
+        H, W = self.engine.H, self.engine.W
+        ref = self.rt.from_host(np.ascontiguousarray(in_ref_data["img"], np.uint8))
+        cur = self.rt.from_host(np.ascontiguousarray(in_cur_data["img"], np.uint8))
+        fwd, bwd, diff = self.engine.flow([ref, cur])
+        src_id, tgt_id = in_ref_data["id"], in_cur_data["id"]
+        return {
+            (src_id, tgt_id): tracking.DevArray(fwd, (2, H, W)),
+            (tgt_id, src_id): tracking.DevArray(bwd, (2, H, W)),
+            (src_id, tgt_id, "diff"): tracking.DevArray(diff, (H, W, 1)),
+        }
+
+    def forward_depth(self, imgs):
+        """deep_models.py:184-206: PIL LANCZOS resize to the feed size + ToTensor stay on the host (frame
+        ingest); the network runs on the device.  Returns float32 [feed_h, feed_w]."""
+        import PIL.Image as pil
+        img = pil.fromarray(imgs[0]).resize((self.engine.feed_w, self.engine.feed_h), pil.LANCZOS)
+        # transforms.ToTensor(): HWC uint8 -> CHW float32 / 255
+        feed = np.ascontiguousarray(np.transpose(np.asarray(img, np.uint8), (2, 0, 1))[None].astype(np.float32) / np.float32(255))
+        out = self.engine.depth(self.rt.from_host(feed))
+        return out.numpy()
+
+    def forward_pose(self, imgs):
+        raise NotImplementedError("deep_pose (PoseNet) is outside the dfvo_b200 hot path (SURVEY.md section 2 row 5)")
+
+    def finetune(self, *a, **k):
+        raise NotImplementedError("online finetuning is outside the dfvo_b200 hot path")
+
+    def save_model(self):
+        raise NotImplementedError("online finetuning is outside the dfvo_b200 hot path")

@@ -236,10 +236,32 @@ def gen_cv_solvers():
     save("cv_solvers", **out)
 
 
+def gen_dfvo_driver():
+    """The UNMODIFIED reference driver (libs/dfvo.py main loop) on a synthetic sequence with analytic
+    network outputs injected at DeepModel.forward_flow / forward_depth; trackers, selection, GRIC, scale
+    recovery and PnP fallback are the reference's own.  Poses are the golden for the drop-in test."""
+    from . import seqdata
+    h, w, n = 188, 620, 7
+    with tempfile.TemporaryDirectory() as tmp:
+        K = seqdata.write_sequence(os.path.join(tmp, "seqs"), n, h, w)
+        cfg = build_cfg(h, w, **{"directory.img_seq_dir": os.path.join(tmp, "seqs"), "directory.result_dir": os.path.join(tmp, "res"),
+                                 "image.ext": "png", "seq": "00"})
+        os.makedirs(cfg.directory.result_dir, exist_ok=True)
+        dm = shims.import_reference("libs.deep_models.deep_models")
+        seqdata.patch_deep_model(dm.DeepModel, h, w, K)
+        ks = shims.import_reference("libs.matching.keypoint_sampler")
+        seqdata.patch_canonical_kp_order(ks.KeypointSampler)        # order of an unordered set only (SURVEY H2)
+        dfvo = shims.import_reference("libs.dfvo")
+        np.random.seed(cfg.seed)                                    # apis/run.py:81-84
+        torch.manual_seed(cfg.seed)
+        poses = seqdata.run_driver(dfvo, cfg, n)
+    save("dfvo_driver_188x620", poses=poses, K=np.array(K), hw=np.array([h, w]))
+
+
 GENERATORS = {
     "correlation": gen_correlation, "warp_fb": gen_warp_fb, "liteflownet": gen_liteflownet,
     "deep_models": gen_deep_models, "selection": gen_selection, "trackers": gen_trackers,
-    "cv_solvers": gen_cv_solvers,
+    "cv_solvers": gen_cv_solvers, "dfvo_driver": gen_dfvo_driver,
 }
 
 if __name__ == "__main__":
