@@ -1,0 +1,37 @@
+"""Hot-path configuration keys with the reference's default values
+(options/examples/default_configuration.yml:7-168, SURVEY.md section 5 'Config / flags').  The libs
+mirror reads the caller's cfg object (the reference's EasyDict) directly; this dictionary is what the
+device pipeline / bench use when no DF-VO configuration file is around."""
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _wrap(d):
+    return AttrDict({k: _wrap(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+def default_cfg(height=376, width=1241):
+    return _wrap({
+        "dataset": "kitti_odom", "seed": 4869,
+        "image": {"height": height, "width": width},
+        "depth": {"max_depth": 50, "min_depth": 0},
+        "crop": {"depth_crop": [[0.3, 1], [0, 1]], "flow_crop": [[0, 1], [0, 1]]},
+        "kp_selection": {
+            "local_bestN": {"enable": True, "num_bestN": 2000, "num_row": 10, "num_col": 10, "score_method": "flow", "thre": 0.1},
+            "bestN": {"enable": False, "num_bestN": 2000},
+        },
+        "tracking_method": "hybrid",
+        "e_tracker": {"ransac": {"reproj_thre": 0.2, "repeat": 5}, "validity": {"method": "GRIC"}},
+        "scale_recovery": {"method": "simple",
+                           "ransac": {"method": "depth_ratio", "min_samples": 3, "max_trials": 100, "stop_prob": 0.99, "thre": 0.1}},
+        "pnp_tracker": {"ransac": {"iter": 100, "reproj_thre": 1, "repeat": 5}},
+    })

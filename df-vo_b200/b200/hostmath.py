@@ -138,6 +138,22 @@ def ransac_scale(x, min_samples=3, max_trials=100, stop_probability=0.99, residu
 # ---------------------------------------------------------------------------------------------
 # misc
 # ---------------------------------------------------------------------------------------------
+def last_writer_depth_ratio_sparse(kp2, z_tri, depth_at_kp, h, w):
+    """Same as :func:`last_writer_depth_ratio` when only the CNN depth at the keypoints' pixels is on the
+    host (``depth_at_kp[i] = depth2[int(kp2_y), int(kp2_x)]``, gathered on the device)."""
+    ki = kp2.astype(int)
+    ok = (ki[:, 0] >= 0) & (ki[:, 0] < w) & (ki[:, 1] >= 0) & (ki[:, 1] < h)
+    lin = ki[ok, 1].astype(np.int64) * w + ki[ok, 0]
+    z = np.asarray(z_tri, np.float64)[ok]
+    d = np.asarray(depth_at_kp, np.float64)[ok]
+    uniq, first = np.unique(lin[::-1], return_index=True)
+    zt = z[::-1][first]
+    zt = np.where(zt < 0, 0.0, zt)
+    dp = d[::-1][first]
+    valid = (dp > 0) & (zt > 0)
+    return zt[valid] / dp[valid], int(valid.sum())
+
+
 def last_writer_depth_ratio(kp2, z_tri, depth2):
     """The part of find_scale_from_depth between triangulation and RANSAC (E_tracker.py:598-616,
     ops_3d.py:15-41) without materialising the dense map: keypoints truncate toward zero to pixels,

@@ -27,6 +27,9 @@ SIGNATURES = {
     "dfvo_last_error": (c_char_p, []),
     "dfvo_version": (c_char_p, []),
     "dfvo_is_device_build": (c_int, []),
+    "dfvo_launch_count": (ctypes.c_longlong, []),
+    "dfvo_profile_enable": (None, [c_int]),
+    "dfvo_profile_read": (None, [ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_double)]),
     "dfvo_create": (c_int, [ctypes.POINTER(c_void_p), c_int]),
     "dfvo_destroy": (c_int, [c_void_p]),
     "dfvo_load_weight": (c_int, [c_void_p, c_int, c_char_p, c_void_p, ctypes.POINTER(ctypes.c_int64), c_int]),
@@ -48,6 +51,7 @@ SIGNATURES = {
     "dfvo_monodepth2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_depth_post": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
+    "dfvo_gather_depth": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dfvo_five_point": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dfvo_score_hypotheses": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "dfvo_essential_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

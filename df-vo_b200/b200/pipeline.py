@@ -1,0 +1,176 @@
+"""Device-resident DF-VO frame pipeline: uint8 frame in, 4x4 pose out.
+
+The same per-frame algorithm as the reference driver's ``deep_model_inference`` + ``tracking``
+(dfvo.py:121-262,299-345, hybrid tracking, default configuration) but organised for the B200:
+everything from the uploaded frame to the keypoints / RANSAC scores / triangulated depths stays in HBM;
+the host only draws the RNG-dependent permutations, takes the small decisions the reference takes on the
+host (GRIC vote, cheirality threshold, sentinels) and chains the pose.  Per frame the host receives a few
+kilobytes (keypoints, masks, scores) instead of the reference's ~9.8 MB of dense maps
+(deep_models.py:178-181,205).
+
+This is the object ``bench.py`` times; ``df-vo_b200/libs`` exposes the same kernels behind the reference's
+class API for the unmodified driver.
+"""
+import numpy as np
+
+from . import config as cfg_mod
+from . import hostmath, native, tracking
+from . import runtime as rt_mod
+
+
+class FrameState:
+    __slots__ = ("id", "img", "depth", "raw_depth")
+
+
+class FramePipeline:
+    def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random):
+        """K = [cx, cy, fx, fy]."""
+        self.cfg = cfg or cfg_mod.default_cfg(height, width)
+        self.K = [float(v) for v in K]
+        self.H, self.W = height, width
+        self.rt = runtime or rt_mod.get()
+        self.eng = tracking.Engine(height, width, self.rt)
+        self.precision = precision
+        self.rng = rng
+        self.ref = None
+        self.stage = 0
+        self.global_pose = np.eye(4)
+        self.motion = np.eye(4)
+        self.poses = {}
+        self.last = {}
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ setup
+    def load_weights(self, flow_weights, depth_enc, depth_dec):
+        self.eng.build_flow(flow_weights, pairs=1, precision=self.precision)
+        self.eng.build_depth(depth_enc, depth_dec, precision=self.precision, dataset=self.cfg.dataset)
+
+    def _buf(self, name, shape, dtype):
+        b = self._bufs.get(name)
+        if b is None or b.shape != tuple(shape):
+            b = self._bufs[name] = self.rt.empty(shape, dtype)
+        return b
+
+    # ------------------------------------------------------------------ per-frame stages
+    def depth_feed_host(self, img):
+        """deep_models.py:195-198: PIL LANCZOS to the feed size + ToTensor (host; frame ingest)."""
+        import PIL.Image as pil
+        im = pil.fromarray(img).resize((self.eng.feed_w, self.eng.feed_h), pil.LANCZOS)
+        return np.ascontiguousarray(np.transpose(np.asarray(im, np.uint8), (2, 0, 1))[None].astype(np.float32) / np.float32(255))
+
+    def infer(self, img, fid):
+        """Upload + both networks for one new frame; returns its FrameState (device buffers)."""
+        st = FrameState()
+        st.id = fid
+        # double-buffer images / depths so the previous frame's stay valid as 'ref'
+        slot = fid & 1
+        st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
+        feed = self._buf("feed", (1, 3, self.eng.feed_h, self.eng.feed_w), np.float32).upload(self.depth_feed_host(img))
+        d = self.eng.depth(feed)
+        st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
+        st.depth = self._buf("dep%d" % slot, (self.H, self.W), np.float32)
+        c = self.cfg
+        self.eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
+        if self.ref is not None:
+            self.eng.flow([self.ref.img, st.img])
+        return st
+
+    def track(self, cur):
+        """dfvo.py:121-262 (hybrid).  Returns the relative pose cur -> ref as a 4x4."""
+        c, eng, K = self.cfg, self.eng, self.K
+        b = c.kp_selection.local_bestN
+        if b.enable:
+            good, n, kp1_buf, kp2_buf = eng.select_local_bestn(eng.flow_diff, eng.flow_fwd, b.num_row, b.num_col, b.num_bestN, b.thre)
+        else:
+            good, n, kp1_buf, kp2_buf = eng.select_bestn(eng.flow_diff, eng.flow_fwd, c.kp_selection.bestN.num_bestN)
+        self.last = dict(good=good, n=n, mode="const")
+        if not good:
+            return self.motion.copy()                                     # constant motion (dfvo.py:157-161)
+        kp_ref = kp1_buf.numpy()[:n]
+        kp_cur = kp2_buf.numpy()[:n]
+        # ---- E-tracker (dfvo.py:165-193)
+        r = tracking.compute_pose_2d2d(eng, kp_ref, kp_cur, K, repeat=c.e_tracker.ransac.repeat,
+                                       reproj_thre=c.e_tracker.ransac.reproj_thre, rng=self.rng,
+                                       kp_ref_buf=kp1_buf, kp_cur_buf=kp2_buf)
+        E_pose = np.eye(4)
+        E_pose[:3, :3], E_pose[:3, 3:] = r["R"], r["t"]
+        hybrid = np.eye(4)
+        hybrid[:3, :3] = r["R"]
+        scale = None
+        self.last.update(valid=r["valid"], inliers=r["inliers"], mode="E")
+        if np.linalg.norm(E_pose[:3, 3]) != 0:
+            scale = self.scale_recovery(kp_ref, kp_cur, kp2_buf, np.linalg.inv(E_pose), cur.depth, n)
+            if scale != -1:
+                hybrid[:3, 3] = E_pose[:3, 3] * scale
+        self.last["scale"] = scale
+        # ---- PnP fallback (dfvo.py:225-250)
+        if np.linalg.norm(E_pose[:3, 3]) == 0 or scale == -1:
+            hybrid = self.pnp(kp_ref, kp_cur, kp1_buf, n)
+            self.last["mode"] = "PnP"
+        return hybrid
+
+    def scale_recovery(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
+        """E_tracker.py:476-507,571-643: device triangulation + device gather of the CNN depth at the
+        keypoints, host RANSAC (RNG-consuming, ~1 ms)."""
+        c = self.cfg.scale_recovery.ransac
+        cx, cy, fx, fy = self.K
+        k1 = self._buf("k1n", (n, 2), np.float64).upload((kp_ref - np.array([cx, cy])) / np.array([fx, fy]))
+        k2 = self._buf("k2n", (n, 2), np.float64).upload((kp_cur - np.array([cx, cy])) / np.array([fx, fy]))
+        z = self.eng.triangulate_depth(k1, k2, n, T_21)
+        dk = self._buf("dkp", (n,), np.float32)
+        self.rt.lib.check(self.rt.lib.dfvo_gather_depth(depth_buf.ptr, self.H, self.W, kp_cur_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
+        ratio, nvalid = hostmath.last_writer_depth_ratio_sparse(kp_cur, z, dk.numpy(), self.H, self.W)
+        if nvalid > 10:
+            return hostmath.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
+        return -1
+
+    def pnp(self, kp_ref, kp_cur, kp_ref_buf, n):
+        """pnp_tracker.py:45-125 -- host cv2.solvePnPRansac (the one SURVEY 8(a) row not yet on the device);
+        the reference depth at the keypoints is gathered on the device."""
+        import cv2
+        c = self.cfg
+        cx, cy, fx, fy = self.K
+        Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+        dk = self._buf("dkp", (n,), np.float32)
+        self.rt.lib.check(self.rt.lib.dfvo_gather_depth(self.ref.depth.ptr, self.H, self.W, kp_ref_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
+        d_all = dk.numpy().astype(np.float64)
+        keep = (kp_cur[:, 0] >= 0) & (kp_cur[:, 0] < self.W) & (kp_cur[:, 1] >= 0) & (kp_cur[:, 1] < self.H)
+        kp1, kp2, d = kp_ref[keep], kp_cur[keep], d_all[keep]
+        keep = (d != 0) & (d < c.depth.max_depth) & (d > c.depth.min_depth)
+        kp1, kp2, d = kp1[keep], kp2[keep], d[keep]
+        XYZ = (np.linalg.inv(Kmat) @ np.concatenate([kp1, np.ones((kp1.shape[0], 1))], 1).T).T * d[:, None]
+        best_rt, best_inl = [], 0
+        for _ in range(c.pnp_tracker.ransac.repeat):
+            order = np.arange(0, kp2.shape[0], 1)
+            self.rng.shuffle(order)
+            nX, n2 = XYZ.copy()[order], kp2.copy()[order]
+            if n2.shape[0] > 4:
+                flag, r, t, inl = cv2.solvePnPRansac(objectPoints=nX, imagePoints=n2, cameraMatrix=Kmat, distCoeffs=None,
+                                                     iterationsCount=c.pnp_tracker.ransac.iter,
+                                                     reprojectionError=c.pnp_tracker.ransac.reproj_thre)
+                if flag and inl.shape[0] > best_inl:
+                    best_rt, best_inl = [r, t], inl.shape[0]
+        pose = np.eye(4)
+        if len(best_rt) != 0:
+            pose[:3, :3] = cv2.Rodrigues(best_rt[0])[0]
+            pose[:3, 3:] = best_rt[1]
+        return np.linalg.inv(pose)
+
+    # ------------------------------------------------------------------ driver step
+    def step(self, img):
+        """One VO frame: returns the global pose (4x4) after this frame (dfvo.py:358-403 loop body)."""
+        fid = self.stage
+        cur = self.infer(img, fid)
+        if self.stage == 0:
+            self.global_pose = np.eye(4)
+            self.motion = np.eye(4)
+        else:
+            rel = self.track(cur)
+            self.motion = rel.copy()
+            # update_global_pose (dfvo.py:109-119): t_w += R_w t ; R_w = R_w R
+            self.global_pose[:3, 3:] = self.global_pose[:3, :3] @ rel[:3, 3:] + self.global_pose[:3, 3:]
+            self.global_pose[:3, :3] = self.global_pose[:3, :3] @ rel[:3, :3]
+        self.poses[fid] = self.global_pose.copy()
+        self.ref = cur
+        self.stage += 1
+        return self.poses[fid]

@@ -117,6 +117,10 @@ int dfvo_is_device_build(void) {
 #endif
 }
 
+long long dfvo_launch_count(void) { return dfvo::g_launch_count; }
+void dfvo_profile_enable(int on) { dfvo::conv_tc_profile_enable(on); }
+void dfvo_profile_read(double* tc_ms, long long* tc_launches, double* tc_flops) { dfvo::conv_tc_profile_read(tc_ms, tc_launches, tc_flops); }
+
 int dfvo_create(dfvo_ctx** out, int device) {
   API_BEGIN
   DFVO_REQUIRE(out != nullptr, DFVO_EINVAL, "dfvo_create: null out");
@@ -277,6 +281,13 @@ int dfvo_gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int nc
   API_BEGIN
   DFVO_REQUIRE(idx && flow_fwd && kp1 && kp2, DFVO_EINVAL, "dfvo_gather_keypoints args");
   return gather_keypoints(idx, cell_counts, ncells, quota, flow_fwd, H, W, kp1, kp2, n_out, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(depth && kp && out && n > 0, DFVO_EINVAL, "dfvo_gather_depth args");
+  return gather_depth(depth, H, W, kp, n, out, (cudaStream_t)stream);
   API_END
 }
 

@@ -20,6 +20,9 @@
 #endif
 #include <string.h>
 
+#include <utility>
+#include <vector>
+
 namespace dfvo {
 
 void conv_tc_tile_shape(int H, int W, int* tw, int* th) {
@@ -469,6 +472,30 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   return DFVO_OK;
 }
 
+long long g_launch_count = 0;
+static int g_prof_on = 0;
+static double g_prof_flops = 0.0;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+void conv_tc_profile_enable(int on) {
+  g_prof_on = on;
+  if (on) {
+    for (auto& e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    g_prof_events.clear();
+    g_prof_flops = 0.0;
+  }
+}
+
+void conv_tc_profile_read(double* ms, long long* launches, double* flops) {
+  double tot = 0.0;
+  for (auto& e : g_prof_events) {
+    cudaEventSynchronize(e.second);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) tot += t;
+  }
+  *ms = tot; *launches = (long long)g_prof_events.size(); *flops = g_prof_flops;
+}
+
 int conv_tc(const ConvTc& c, cudaStream_t s) {
   ConvTcPlanImpl pl;
   int rc = build_plan(c, &pl);
@@ -478,7 +505,11 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
     DFVO_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  ++g_launch_count;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
   k_conv_tc<<<pl.grid, TC_THREADS, pl.smem, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k);
+  if (g_prof_on) { cudaEventRecord(e1, s); g_prof_events.push_back({e0, e1}); g_prof_flops += c.flops; }
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }
@@ -488,6 +519,9 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
 // kernel and applies the same TMA semantics (zero fill outside the image / beyond a source's C,
 // virtual concat of sources, tap offsets), so the layer wiring and the weight packer can be
 // validated without a GPU.  Never compiled into the product library.
+long long g_launch_count = 0;
+void conv_tc_profile_enable(int) {}
+void conv_tc_profile_read(double* ms, long long* launches, double* flops) { *ms = 0; *launches = 0; *flops = 0; }
 int conv_tc(const ConvTc& c, cudaStream_t) {
   int ktot = 0;
   for (int s = 0; s < c.nsrc; ++s) ktot += c.src[s].C;

@@ -76,6 +76,39 @@ int resize_bilinear_f32(Ten<const float> in, Ten<float> out, int align_corners, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-unroll of the 3-channel input for the 7x7 stem (lite_flow_net.py:39-42): out[n,y,x, dx*3+c] =
+// img[n, y, x+dx-3, c] (zero outside), channels 21..31 zero.  The 7x7x3 convolution then is a 7x1
+// convolution over 32 channels, which the tcgen05 kernel can run (its K granularity is 16 channels).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_im2row7(Ten<const float> img, Ten<T> out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.W) return;
+  T* o = out.at(n, y, x);
+#pragma unroll
+  for (int dx = 0; dx < 7; ++dx) {
+    const int xx = x + dx - 3;
+    const bool in = xx >= 0 && xx < img.W;
+    const float* p = img.at(n, y, in ? xx : 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[dx * 3 + c] = from_f<T>(in ? p[c] : 0.f);
+  }
+  for (int c = 21; c < out.C; ++c) o[c] = from_f<T>(0.f);
+}
+
+template <typename T>
+int im2row7(Ten<const float> img, Ten<T> out, cudaStream_t s) {
+  DFVO_REQUIRE(out.C >= 21 && out.H == img.H && out.W == img.W, DFVO_ESHAPE, "im2row7 shapes");
+  auto k = k_im2row7<T>;
+  DFVO_LAUNCH(k, dim3(cdiv(out.W, 128), out.H, out.N), dim3(128), 0, s, img, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int im2row7<float>(Ten<const float>, Ten<float>, cudaStream_t);
+template int im2row7<bf16>(Ten<const float>, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
 // depthwise ConvTranspose2d(k=4, s=2, p=1, groups=C, bias=False)  (lite_flow_net.py:109,117)
 // out[oy] += in[iy] * w[ky] with oy = 2*iy - 1 + ky
 // ---------------------------------------------------------------------------------------------
@@ -167,8 +200,71 @@ __global__ void k_warp_bilinear(Ten<const T> in, Ten<const float> flow, float sc
   out.at(n, y, x)[c] = from_f<T>(v);
 }
 
+// vectorised variant: one thread per (pixel, 16-byte channel group); used when C and the strides allow it
+template <typename T>
+__global__ void k_warp_bilinear_vec(Ten<const T> in, Ten<const float> flow, float scale, int nxor, Ten<T> out) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int groups = out.C / VEC;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long npix = (long long)out.N * out.H * out.W;
+  if (gid >= npix * groups) return;
+  const int g = (int)(gid % groups);
+  long long p = gid / groups;
+  const int x = (int)(p % out.W), y = (int)((p / out.W) % out.H), n = (int)(p / ((long long)out.W * out.H));
+  const float* f = flow.at(n, y, x);
+  const float px = (float)x + f[0] * scale, py = (float)y + f[1] * scale;
+  const Bil b = bilinear_zeros(px, py, in.W, in.H);
+  const int ns = n ^ nxor;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const float wts[4] = {b.w00, b.w01, b.w10, b.w11};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (wts[k] == 0.f) continue;
+    const T* src = in.at(ns, b.y0 + (k >> 1), b.x0 + (k & 1)) + g * VEC;
+    const uint4 v = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    if (sizeof(T) == 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += __uint_as_float(w4[j]) * wts[k];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(w4[j] << 16) * wts[k];
+        acc[2 * j + 1] += __uint_as_float(w4[j] & 0xffff0000u) * wts[k];
+      }
+    }
+  }
+  uint32_t o4[4];
+  if (sizeof(T) == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o4[j] = __float_as_uint(acc[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = __float_as_uint(to_f(from_f<T>(acc[2 * j]))) >> 16;
+      const uint32_t hi = __float_as_uint(to_f(from_f<T>(acc[2 * j + 1]))) & 0xffff0000u;
+      o4[j] = lo | hi;
+    }
+  }
+  uint4 ov; ov.x = o4[0]; ov.y = o4[1]; ov.z = o4[2]; ov.w = o4[3];
+  *reinterpret_cast<uint4*>(out.at(n, y, x) + g * VEC) = ov;
+}
+
 template <typename T>
 int warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int in_nxor, Ten<T> out, cudaStream_t s) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = out.C % VEC == 0 && in.C >= out.C && in.sW % VEC == 0 && in.sH % VEC == 0 && in.sN % VEC == 0 &&
+                      out.sW % VEC == 0 && out.sH % VEC == 0 && out.sN % VEC == 0 &&
+                      (reinterpret_cast<uintptr_t>(in.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.p) & 15) == 0;
+  if (vec_ok) {
+    long long total = (long long)out.N * out.H * out.W * (out.C / VEC);
+    auto k = k_warp_bilinear_vec<T>;
+    DFVO_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, in, flow, scale, in_nxor, out);
+    DFVO_CHECK_LAUNCH();
+    return DFVO_OK;
+  }
   long long total = (long long)out.N * out.H * out.W * out.C;
   dim3 block(256), grid((unsigned)((total + 255) / 256));
   auto k = k_warp_bilinear<T>;
@@ -308,12 +404,13 @@ template int correlation49<bf16>(Ten<const bf16>, Ten<const bf16>, int, int, int
 // ---------------------------------------------------------------------------------------------
 // flow mean (lite_flow_net.py:257: tensorFlow.view(N,2,-1).mean(2))  -- one block per n
 // ---------------------------------------------------------------------------------------------
-__global__ void k_flow_mean(Ten<const float> flow, float* __restrict__ mean) {
+#define FM_BLOCKS 64
+__global__ void k_flow_mean_partial(Ten<const float> flow, double* __restrict__ partial) {
   __shared__ double sx[256], sy[256];
-  int n = blockIdx.x;
-  int npix = flow.H * flow.W;
+  const int n = blockIdx.y;
+  const int npix = flow.H * flow.W;
   double ax = 0.0, ay = 0.0;
-  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < npix; p += FM_BLOCKS * 256) {
     const float* f = flow.at(n, p / flow.W, p % flow.W);
     ax += (double)f[0]; ay += (double)f[1];
   }
@@ -323,14 +420,23 @@ __global__ void k_flow_mean(Ten<const float> flow, float* __restrict__ mean) {
     if ((int)threadIdx.x < off) { sx[threadIdx.x] += sx[threadIdx.x + off]; sy[threadIdx.x] += sy[threadIdx.x + off]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    mean[n * 2 + 0] = (float)(sx[0] / (double)npix);
-    mean[n * 2 + 1] = (float)(sy[0] / (double)npix);
+  if (threadIdx.x == 0) { partial[(n * FM_BLOCKS + blockIdx.x) * 2] = sx[0]; partial[(n * FM_BLOCKS + blockIdx.x) * 2 + 1] = sy[0]; }
+}
+
+__global__ void k_flow_mean_final(const double* __restrict__ partial, int npix, float* __restrict__ mean) {
+  const int n = blockIdx.x;
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int b = 0; b < FM_BLOCKS; ++b) a += partial[(n * FM_BLOCKS + b) * 2 + threadIdx.x];     // fixed order: deterministic
+    mean[n * 2 + threadIdx.x] = (float)(a / (double)npix);
   }
 }
 
 int flow_mean(Ten<const float> flow, float* mean, cudaStream_t s) {
-  DFVO_LAUNCH(k_flow_mean, dim3(flow.N), dim3(256), 0, s, flow, mean);
+  // the partial sums live behind the means: caller's buffer holds [N*2 floats | pad | N*FM_BLOCKS*2 doubles]
+  double* partial = reinterpret_cast<double*>(mean + ((flow.N * 2 + 3) & ~3));
+  DFVO_LAUNCH(k_flow_mean_partial, dim3(FM_BLOCKS, flow.N), dim3(256), 0, s, flow, partial);
+  DFVO_LAUNCH(k_flow_mean_final, dim3(flow.N), dim3(32), 0, s, (const double*)partial, flow.H * flow.W, mean);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }

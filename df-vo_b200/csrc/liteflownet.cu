@@ -60,7 +60,7 @@ struct LfnImpl : public LiteFlowNetBase {
   } lv[7];
   // buffers
   float* img[7];              // [B,h,w,4] fp32 pyramid (img[1] = network input)
-  T *f1buf, *t2a, *t2b, *feat2, *t3a, *t4a;
+  T *f1buf, *rowbuf, *t2a, *t2b, *feat2, *t3a, *t4a;
   T* subcat[7]; int subC[7];
   T *mfeat, *warpbuf, *corr, *corrU, *b128a, *b128b, *b64a, *b64b, *b32a, *b32b, *d0, *d1, *regcat;
   float *flow_up, *flow_m, *flow_s, *flow_r[7], *meanbuf;
@@ -107,7 +107,23 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 1; L <= 6; ++L) { lh[L] = th >> (L - 1); lw[L] = tw >> (L - 1); }
     // ---------------- weights ----------------
     const std::string F = "moduleFeatures.";
-    TRY(conv_layer(ws, F + "moduleOne.0", {{3, 3}}, 1, 3, 3, false, &fOne));
+    if (IsBf16<T>::v) {
+      // stem on tensor cores: 7x7x3 -> 7x1 over the row-unrolled 21 (padded 32) channels, w'[co][dx*3+c][ky] = w[co][c][ky][dx]
+      const HostTensor* w7 = find_weight(ws, F + "moduleOne.0.weight");
+      const HostTensor* b7 = find_weight(ws, F + "moduleOne.0.bias");
+      DFVO_REQUIRE(w7 && w7->shape.size() == 4 && w7->shape[1] == 3 && w7->shape[2] == 7 && w7->shape[3] == 7, DFVO_ESTATE, "moduleOne weight");
+      HostTensor wr;
+      wr.shape = {w7->shape[0], 21, 7, 1};
+      wr.data.assign((size_t)w7->shape[0] * 21 * 7, 0.f);
+      for (int co = 0; co < (int)w7->shape[0]; ++co)
+        for (int c = 0; c < 3; ++c)
+          for (int ky = 0; ky < 7; ++ky)
+            for (int dx = 0; dx < 7; ++dx)
+              wr.data[((size_t)co * 21 + dx * 3 + c) * 7 + ky] = w7->data[(((size_t)co * 3 + c) * 7 + ky) * 7 + dx];
+      TRY(build_conv_layer(arena, wr, b7, {{21, 32}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
+    } else {
+      TRY(conv_layer(ws, F + "moduleOne.0", {{3, 3}}, 1, 3, 3, false, &fOne));
+    }
     TRY(conv_layer(ws, F + "moduleTwo.0", {{32, 32}}, 2, 1, 1, false, &fTwo0));
     TRY(conv_layer(ws, F + "moduleTwo.2", {{32, 32}}, 1, 1, 1, true, &fTwo2));
     TRY(conv_layer(ws, F + "moduleTwo.4", {{32, 32}}, 1, 1, 1, true, &fTwo4));
@@ -165,6 +181,7 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 1; L <= 6; ++L) { img[L] = arena.alloc_t<float>(px(L) * 4); if (!img[L]) return DFVO_ENOMEM; }
 #define ALLOC(ptr, type, count) do { ptr = arena.alloc_t<type>(count); if (!ptr) return DFVO_ENOMEM; } while (0)
     ALLOC(f1buf, T, px(1) * 32);
+    ALLOC(rowbuf, T, IsBf16<T>::v ? px(1) * 32 : 64);
     ALLOC(t2a, T, px(2) * 32); ALLOC(t2b, T, px(2) * 32); ALLOC(feat2, T, px(2) * 32);
     ALLOC(t3a, T, px(3) * 64); ALLOC(t4a, T, px(4) * 96);
     subcat[1] = nullptr; subC[1] = 0;
@@ -196,7 +213,7 @@ struct LfnImpl : public LiteFlowNetBase {
     }
     ALLOC(flow_up, float, px(2) * 2); ALLOC(flow_m, float, px(2) * 2); ALLOC(flow_s, float, px(2) * 2);
     for (int L = 2; L <= 6; ++L) ALLOC(flow_r[L], float, px(L) * 2);
-    ALLOC(meanbuf, float, (size_t)B * 2);
+    ALLOC(meanbuf, float, flow_mean_buffer_floats(B));
     ALLOC(out_planar, float, (size_t)B * 2 * H0 * W0);
     return DFVO_OK;
   }
@@ -207,8 +224,11 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int b = 0; b < B; ++b) TRY(prep_image_u8(imgs_u8[b], H0, W0, i1, b, s));
     for (int L = 2; L <= 6; ++L) TRY(resize_bilinear_f32(cfview(img[L - 1], L - 1, 3, 4), fview(img[L], L, 4, 4), 0, s));
     Ten<const T> none; memset(&none, 0, sizeof(none));
-    // level 1: 7x7 3->32 on the fp32 image (CUDA-core kernel, reads float writes T)
-    {
+    // level 1: 7x7 3->32.  bf16: row-unroll + tcgen05 7x1 conv;  fp32: CUDA-core kernel on the float image
+    if (IsBf16<T>::v) {
+      TRY(im2row7<T>(cfview(img[1], 1, 3, 4), view(rowbuf, 1, 32, 32), s));
+      TRY(run_conv<T>(fOne, cview(rowbuf, 1, 32, 32), view(f1buf, 1, 32, 32), ACT_LEAKY, none, 0, s));
+    } else {
       ConvDirect d; d.Cin = 3; d.Cout = 32; d.kh = 7; d.kw = 7; d.stride = 1; d.pad_y = 3; d.pad_x = 3; d.reflect = 0;
       d.act = ACT_LEAKY; d.w = fOne.w_direct; d.w_pitch = fOne.w_pitch; d.bias = fOne.bias;
       DFVO_REQUIRE(fOne.w_direct, DFVO_ESTATE, "moduleOne weights");

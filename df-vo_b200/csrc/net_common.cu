@@ -166,6 +166,7 @@ int run_conv<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<bf16> out, int ac
   c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
   c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
   c.zero_pad_to = zero_pad_to;
+  c.flops = 2.0 * (double)in.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
   return conv_tc(c, s);
 }
 
@@ -190,6 +191,7 @@ int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out
   c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
   c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
   c.zero_pad_to = 0;
+  c.flops = 2.0 * (double)in.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
   return conv_tc(c, s);
 }
 

@@ -14,6 +14,9 @@ typedef __nv_bfloat16 bf16;
 int prep_image_u8(const uint8_t* img, int H0, int W0, Ten<float> out, int n, cudaStream_t s);
 // generic bilinear resize of float NHWC (C<=4), align_corners flag (lite_flow_net.py:307-309)
 int resize_bilinear_f32(Ten<const float> in, Ten<float> out, int align_corners, cudaStream_t s);
+// out[n,y,x,dx*3+c] = img[n,y,x+dx-3,c], zero padded, channels >= 21 zero (stem 7x7 -> 7x1 over 32 channels)
+template <typename T>
+int im2row7(Ten<const float> img, Ten<T> out, cudaStream_t s);
 // depthwise ConvTranspose2d k4 s2 p1, no bias (lite_flow_net.py:109,117); w = [C][4][4] float
 template <typename T>
 int deconv4x4s2_dw(Ten<const T> in, const float* w, Ten<T> out, cudaStream_t s);
@@ -24,8 +27,10 @@ int warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int in_nx
 // 49-channel correlation + fused LeakyReLU(0.1) (correlation.py:38-106, lite_flow_net.py:145-149)
 template <typename T>
 int correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out, cudaStream_t s);
-// per-(n,c) spatial mean of a 2-channel float field (lite_flow_net.py:257) -> mean[n*2+c]
+// per-(n,c) spatial mean of a 2-channel float field (lite_flow_net.py:257) -> mean[n*2+c].  `mean` must have
+// room for flow_mean_buffer_floats(N) floats (the means followed by the per-block partial sums).
 int flow_mean(Ten<const float> flow, float* mean, cudaStream_t s);
+inline size_t flow_mean_buffer_floats(int N) { return (size_t)((N * 2 + 3) & ~3) + (size_t)N * 64 * 2 * 2; }
 // Regularization input prep (lite_flow_net.py:244-257): out[...,0]=sqrt(sum((img1-warp(img2))^2)+1e-6),
 // out[...,1:3] = flow - mean, remaining channels of out (up to out.C) zero.
 template <typename T>
@@ -86,7 +91,11 @@ struct ConvTc {
   const void* residual;   // optional, same type/strides family as out
   long long rN, rH, rW;
   int zero_pad_to;        // if > Cout: also write zeros to channels [Cout, zero_pad_to)
+  double flops;           // algorithmic FLOPs of this launch (2*MAC, real channels), for the roofline report
 };
+// profiling hooks (bench.py roofline): CUDA-event timing of every conv_tc launch while enabled
+void conv_tc_profile_enable(int on);
+void conv_tc_profile_read(double* ms, long long* launches, double* flops);
 int conv_tc(const ConvTc& c, cudaStream_t s);
 // tile shape chooser shared with tests
 void conv_tc_tile_shape(int H, int W, int* tw, int* th);
@@ -115,6 +124,7 @@ int local_bestn(const float* diff, const float* depth_diff, int H, int W, int ro
 int bestn(const float* diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t ws_bytes,
           cudaStream_t s);
 size_t bestn_workspace_bytes(int H, int W);
+int gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, cudaStream_t s);
 // idx: [ncells*n_best] slots (cell-major); cell_counts may be null (all slots valid, e.g. bestN with ncells=1)
 int gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int n_best, const float* flow_fwd, int H, int W,
                      double* kp1, double* kp2, int32_t* n_out, cudaStream_t s);

@@ -314,6 +314,21 @@ __global__ void k_gather_keypoints(const int32_t* __restrict__ idx, const int32_
   }
 }
 
+// depth at int(kp) (truncation toward zero, like kp.astype(int) at ops_3d.py:29 / pnp_tracker.py:72); 0 if outside
+__global__ void k_gather_depth(const float* __restrict__ depth, int H, int W, const double* __restrict__ kp, int n,
+                               float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x = (int)kp[2 * i], y = (int)kp[2 * i + 1];
+  out[i] = (x >= 0 && x < W && y >= 0 && y < H) ? depth[(size_t)y * W + x] : 0.f;
+}
+
+int gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, cudaStream_t s) {
+  DFVO_LAUNCH(k_gather_depth, dim3(cdiv(n, 128)), dim3(128), 0, s, depth, H, W, kp, n, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 int gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int n_best, const float* flow, int H, int W,
                      double* kp1, double* kp2, int32_t* n_out, cudaStream_t s) {
   DFVO_REQUIRE(ncells > 0 && ncells <= 8192, DFVO_EINVAL, "gather_keypoints: ncells");

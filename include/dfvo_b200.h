@@ -50,6 +50,13 @@ const char* dfvo_version(void);
 /* 1 if this library was built by nvcc for sm_100a, 0 for the CPU test build (tests/hostsim). */
 int dfvo_is_device_build(void);
 
+/* instrumentation for bench.py: number of kernel launches issued by this library so far (process-wide), and
+ * CUDA-event timing of the tcgen05 conv launches while enabled (sum of durations in ms, launch count, and
+ * algorithmic FLOPs = 2*MAC over real channels). */
+long long dfvo_launch_count(void);
+void dfvo_profile_enable(int on);
+void dfvo_profile_read(double* tc_ms, long long* tc_launches, double* tc_flops);
+
 int dfvo_create(dfvo_ctx** out, int device);
 int dfvo_destroy(dfvo_ctx* ctx);
 
@@ -125,6 +132,9 @@ int dfvo_bestn(const float* flow_diff, int H, int W, int N, int32_t* idx_out, vo
 int dfvo_gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int quota,
                           const float* flow_fwd, int H, int W, double* kp1, double* kp2, int32_t* n_out,
                           void* stream);
+
+/* depth[int(kp_y), int(kp_x)] for n keypoints (ops_3d.py:29, pnp_tracker.py:72-73); 0 outside the image. */
+int dfvo_gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, void* stream);
 
 /* ---- pose solvers (libs/tracker, FP64) ------------------------------------------------------------------
  * 5-point minimal solver (inside cv2.findEssentialMat, E_tracker.py:231): M problems, x1/x2 [M][5][2]

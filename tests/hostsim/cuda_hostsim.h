@@ -40,6 +40,9 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct uint3_ { unsigned x, y, z; };
+struct uint4 { unsigned x, y, z, w; };
+struct float4 { float x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
 extern uint3_ threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 extern unsigned char* hostsim_dyn_smem;
@@ -132,5 +135,6 @@ inline void __threadfence() {}
 
 // dynamic shared memory: kernels declare it through DFVO_DYN_SMEM(type, name)
 #define DFVO_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(hostsim_dyn_smem)
+namespace dfvo { extern long long g_launch_count; }
 #define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
-  hostsim::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
+  do { ++dfvo::g_launch_count; hostsim::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)
