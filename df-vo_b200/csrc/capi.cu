@@ -226,7 +226,8 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
   if (bias_host) { b.shape = {Cout}; b.data.assign(bias_host, bias_host + Cout); }
   if (precision == DFVO_PREC_FP32)
     return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
-  DFVO_REQUIRE(stride == 1 && !reflect, DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1 and zero padding");
+  DFVO_REQUIRE((stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0 && kh % 2 == 1 && pad_y == kh / 2 && pad_x == kw / 2)) && !reflect,
+               DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1, or stride 2 on even sizes with 'same' padding; zero padding");
   return stage_conv<bf16>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
   API_END
 }

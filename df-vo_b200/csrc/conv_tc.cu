@@ -41,7 +41,9 @@ struct ConvTcK {
   int N, H, W, tw, th, tiles_x, tiles_y, n_blocks, ntiles;
   int nsrc, srcC[3];
   int ntaps;
-  int8_t dy[49], dx[49];
+  int8_t dy[49], dx[49];        // stride 1: input offsets; stride 2: offsets in units of double-pixels (floor((k-pad)/2))
+  int8_t py[49], px[49];        // stride 2: pixel phase of the tap inside the 2x2 cell
+  int stride, src_pitch;        // src_pitch (elements) = channel offset of the odd pixel inside a double-pixel
   int block_n, stages, acc_stride, tmem_cols;
   int Cout, Cout_pad, act, out_f32, zero_pad_to;
   const float* bias;
@@ -79,6 +81,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -195,7 +202,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_4d(sa, tm, full_bar(stage), c0, x0 + p.dx[tap], y0 + p.dy[tap], n);
+              if (p.stride == 2)
+                tma_load_5d(sa, tm, full_bar(stage), c0 + p.px[tap] * p.src_pitch, x0 + p.dx[tap], p.py[tap], y0 + p.dy[tap], n);
+              else
+                tma_load_4d(sa, tm, full_bar(stage), c0, x0 + p.dx[tap], y0 + p.dy[tap], n);
               tma_load_3d(sa + TC_A_BYTES, &tmB, full_bar(stage), kofs + c0, nb * p.block_n, tap);
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
@@ -393,6 +403,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
   PFN_encodeTiled enc = get_encode();
   DFVO_REQUIRE(enc != nullptr, DFVO_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  if (rank == 5 && dims[0] > 0) { /* last row of the last image: the odd pixel's view must stay inside the allocation */ }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -431,7 +442,21 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
                  DFVO_EINVAL, "conv_tc: source %d not 16-byte aligned/strided", s);
     k.srcC[s] = c.src[s].C; ktot += c.src[s].C;
   }
-  memcpy(k.dy, c.dy, sizeof(k.dy)); memcpy(k.dx, c.dx, sizeof(k.dx));
+  k.stride = c.stride == 2 ? 2 : 1;
+  if (k.stride == 2) {
+    const int inH = c.inH > 0 ? c.inH : 2 * c.H, inW = c.inW > 0 ? c.inW : 2 * c.W;
+    DFVO_REQUIRE(c.nsrc == 1 && inH % 2 == 0 && inW % 2 == 0 && inH == 2 * c.H && inW == 2 * c.W, DFVO_EINVAL,
+                 "conv_tc stride 2: needs one source and even input size = 2x output");
+    DFVO_REQUIRE(c.src[0].sH == (long long)inW * c.src[0].sW, DFVO_EINVAL, "conv_tc stride 2: rows must be contiguous");
+    k.src_pitch = (int)c.src[0].sW;
+    for (int t = 0; t < c.ntaps; ++t) {
+      const int oy = c.dy[t], ox = c.dx[t];                 // input-pixel offsets
+      k.py[t] = (int8_t)(((oy % 2) + 2) % 2); k.dy[t] = (int8_t)((oy - k.py[t]) / 2);
+      k.px[t] = (int8_t)(((ox % 2) + 2) % 2); k.dx[t] = (int8_t)((ox - k.px[t]) / 2);
+    }
+  } else {
+    memcpy(k.dy, c.dy, sizeof(k.dy)); memcpy(k.dx, c.dx, sizeof(k.dx));
+  }
   k.Cout = c.Cout; k.Cout_pad = c.Cout_pad; k.act = c.act; k.out_f32 = c.out_f32;
   k.zero_pad_to = c.zero_pad_to > c.Cout ? c.zero_pad_to : c.Cout;
   k.bias = c.bias; k.out = c.out; k.oN = c.oN; k.oH = c.oH; k.oW = c.oW;
@@ -455,6 +480,17 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   // tensor maps
   for (int s = 0; s < 3; ++s) {
     const ConvTcSource& src = c.src[s < c.nsrc ? s : 0];
+    if (k.stride == 2) {
+      // view [N][H/2][2][W/2][pitch+C]: a double-pixel holds the even pixel's channels at [0,C) and the odd pixel's
+      // at [pitch, pitch+C); (py, px) of a tap select the phase, the box walks W/2 x H/2 cells of the output tile
+      const int inW2 = c.W, inH2 = c.H;
+      cuuint64_t dims[5] = {(cuuint64_t)(src.sW + src.C), (cuuint64_t)inW2, 2, (cuuint64_t)inH2, (cuuint64_t)c.N};
+      cuuint64_t str[4] = {(cuuint64_t)src.sW * 4, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sH * 4, (cuuint64_t)src.sN * 2};
+      cuuint32_t box[5] = {64, (cuuint32_t)k.tw, 1, (cuuint32_t)k.th, 1};
+      int rc = encode_map(&pl->tmA[s], src.p, 5, dims, str, box);
+      if (rc) return rc;
+      continue;
+    }
     const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
     cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)inW, (cuuint64_t)inH, (cuuint64_t)c.N};
     cuuint64_t str[3] = {(cuuint64_t)src.sW * 2, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sN * 2};
@@ -532,8 +568,9 @@ int conv_tc(const ConvTc& c, cudaStream_t) {
       for (int x = 0; x < c.W; ++x) {
         for (int co = 0; co < c.Cout_pad; ++co) acc[co] = 0.f;
         for (int t = 0; t < c.ntaps; ++t) {
-          int iy = y + c.dy[t], ix = x + c.dx[t];
-          const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
+          const int st = c.stride == 2 ? 2 : 1;
+          int iy = y * st + c.dy[t], ix = x * st + c.dx[t];
+          const int inW = c.inW > 0 ? c.inW : c.W * st, inH = c.inH > 0 ? c.inH : c.H * st;
           if (iy < 0 || iy >= inH || ix < 0 || ix >= inW) continue;
           int kofs = 0;
           for (int s = 0; s < c.nsrc; ++s) {

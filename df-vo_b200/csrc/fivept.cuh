@@ -222,10 +222,12 @@ DFVO_HD int durand_kerner(const double* c, int n, double* re, double* im, int ma
       if (ad > max_diff) max_diff = ad;
     }
     // cv::solvePoly stops only at exact stagnation (max_diff <= 0), i.e. it normally runs all of its 1000
-    // iterations; the roots stop moving at round-off level long before, so stop there (same roots, same order).
+    // iterations.  The iteration converges quadratically (linearly with ratio 1/2 at double roots): once the
+    // largest correction is below 1e-13 of the root scale the roots are stationary at round-off level -- same
+    // roots, same index order -- and the real ones are Newton-polished below.
     double rmax = 0.0;
     for (int i = 0; i < n; ++i) { const double a = fabs(re[i]) + fabs(im[i]); if (a > rmax) rmax = a; }
-    if (max_diff <= 4e-16 * rmax) break;
+    if (max_diff <= 1e-13 * rmax) break;
     if (!(max_diff == max_diff)) break;           // NaN guard
   }
   return iter;
@@ -299,7 +301,7 @@ DFVO_HD int solve(const double* x1, const double* x2, double* E_out) {
   while (n > 0 && fabs(c[n]) <= 1e-14 * cmax) --n;
   if (n < 1) return 0;
   double re[10], im[10];
-  durand_kerner(c, n, re, im, 1000);
+  durand_kerner(c, n, re, im, 160);
   int count = 0;
   for (int i = 0; i < n; ++i) {
     if (!(fabs(im[i]) <= 1e-10) || !(re[i] == re[i])) continue;

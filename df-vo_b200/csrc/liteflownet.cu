@@ -124,15 +124,15 @@ struct LfnImpl : public LiteFlowNetBase {
     } else {
       TRY(conv_layer(ws, F + "moduleOne.0", {{3, 3}}, 1, 3, 3, false, &fOne));
     }
-    TRY(conv_layer(ws, F + "moduleTwo.0", {{32, 32}}, 2, 1, 1, false, &fTwo0));
+    TRY(conv_layer(ws, F + "moduleTwo.0", {{32, 32}}, 2, 1, 1, true, &fTwo0));
     TRY(conv_layer(ws, F + "moduleTwo.2", {{32, 32}}, 1, 1, 1, true, &fTwo2));
     TRY(conv_layer(ws, F + "moduleTwo.4", {{32, 32}}, 1, 1, 1, true, &fTwo4));
-    TRY(conv_layer(ws, F + "moduleThr.0", {{32, 32}}, 2, 1, 1, false, &fThr0));
+    TRY(conv_layer(ws, F + "moduleThr.0", {{32, 32}}, 2, 1, 1, true, &fThr0));
     TRY(conv_layer(ws, F + "moduleThr.2", {{64, 64}}, 1, 1, 1, true, &fThr2));
-    TRY(conv_layer(ws, F + "moduleFou.0", {{64, 64}}, 2, 1, 1, false, &fFou0));
+    TRY(conv_layer(ws, F + "moduleFou.0", {{64, 64}}, 2, 1, 1, true, &fFou0));
     TRY(conv_layer(ws, F + "moduleFou.2", {{96, 96}}, 1, 1, 1, true, &fFou2));
-    TRY(conv_layer(ws, F + "moduleFiv.0", {{96, 96}}, 2, 1, 1, false, &fFiv0));
-    TRY(conv_layer(ws, F + "moduleSix.0", {{128, 128}}, 2, 1, 1, false, &fSix0));
+    TRY(conv_layer(ws, F + "moduleFiv.0", {{96, 96}}, 2, 1, 1, true, &fFiv0));
+    TRY(conv_layer(ws, F + "moduleSix.0", {{128, 128}}, 2, 1, 1, true, &fSix0));
     for (int L = 2; L <= 6; ++L) {
       Lvl& v = lv[L];
       const int k = L - 2, kl = kKLast[L], C = (L == 2) ? 64 : kFeatC[L];

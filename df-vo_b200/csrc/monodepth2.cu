@@ -82,10 +82,10 @@ struct MonoImpl : public Monodepth2Base {
         Block& B = blk[li][b];
         B.stride = (li > 0 && b == 0) ? 2 : 1;
         const int ci = b == 0 ? cin : chans[li];
-        TRYM(bn_conv(ws, std::string(pre) + "conv1", std::string(pre) + "bn1", ci, B.stride, 1, B.stride == 1, &B.c1));
+        TRYM(bn_conv(ws, std::string(pre) + "conv1", std::string(pre) + "bn1", ci, B.stride, 1, true, &B.c1));
         TRYM(bn_conv(ws, std::string(pre) + "conv2", std::string(pre) + "bn2", chans[li], 1, 1, true, &B.c2));
         B.has_down = find_weight(ws, std::string(pre) + "downsample.0.weight") != nullptr;
-        if (B.has_down) TRYM(bn_conv(ws, std::string(pre) + "downsample.0", std::string(pre) + "downsample.1", ci, B.stride, 0, false, &B.down));
+        if (B.has_down) TRYM(bn_conv(ws, std::string(pre) + "downsample.0", std::string(pre) + "downsample.1", ci, B.stride, 0, true, &B.down));
       }
       cin = chans[li];
     }

@@ -104,7 +104,7 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
     DFVO_CUDA(cudaMemcpy(L->w_direct, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   }
   if (want_tc) {
-    DFVO_REQUIRE(stride == 1 && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1, zero pad, K %% 16 == 0");
+    DFVO_REQUIRE((stride == 1 || stride == 2) && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1|2, zero pad, K %% 16 == 0");
     std::vector<uint16_t> h((size_t)kh * kw * L->Cout_pad * ktot, 0);
     for (int ky = 0; ky < kh; ++ky)
       for (int kx = 0; kx < kw; ++kx)
@@ -156,9 +156,13 @@ int run_conv<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<bf16> out, int ac
   DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc conv: input view has %d channels, layer expects %d", in.C, L.Ktot);
   ConvTc c;
   memset(&c, 0, sizeof(c));
-  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W;
-  DFVO_REQUIRE(in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
-               "tc conv: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
+  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W; c.stride = L.stride;
+  if (L.stride == 2) {
+    DFVO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W, DFVO_ESHAPE, "tc conv stride 2: in %dx%d out %dx%d", in.H, in.W, out.H, out.W);
+  } else {
+    DFVO_REQUIRE(in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
+                 "tc conv: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
+  }
   c.nsrc = 1;
   c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
   fill_taps(L, &c);

@@ -78,8 +78,10 @@ struct ConvTc {
                           // the input is pre-padded (reflection padding) use inH = H + kh - 1 and tap offsets >= 0
   int nsrc;               // 1..3 virtual-concat sources
   ConvTcSource src[3];
+  int stride;             // 1, or 2 (then nsrc == 1, even input size; taps address the 2x2 pixel phases through a
+                          // 5-D tensor map (pitch+C, W/2, 2, H/2, N) -- see conv_tc.cu)
   int ntaps;              // kh*kw
-  int8_t dy[49], dx[49];  // tap offsets (already include -pad)
+  int8_t dy[49], dx[49];  // tap offsets in INPUT pixels (already include -pad): iy = oy*stride + dy
   const bf16* w;          // packed [ntaps][Cout_pad][Ktot] bf16, Ktot = sum(src[i].C)
   int Cout_pad;           // multiple of 16
   int Cout;               // real output channels written

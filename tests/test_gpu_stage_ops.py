@@ -137,6 +137,31 @@ TC_CASES = [
     (3, 16, 9, 130, 16, 3, 3, 1, 1, 3),        # odd sizes, elu, minimum channels
 ]
 
+TC_S2_CASES = [
+    # B, Cin, H, W, Cout, k, pad, act -- stride-2 convs (5-D tensor map over the 2x2 pixel phases)
+    (2, 32, 64, 96, 32, 3, 1, 1), (2, 64, 44, 152, 96, 3, 1, 1), (1, 128, 22, 76, 192, 3, 1, 1),
+    (1, 64, 48, 160, 128, 1, 0, 0), (1, 256, 12, 40, 512, 3, 1, 2), (2, 32, 352, 1216, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_S2_CASES)
+def test_conv2d_tcgen05_stride2(dev_lib, case):
+    B, Cin, H, W, Cout, k, pad, act = case
+    rs = np.random.RandomState(Cin + 7 * Cout + k)
+    x = bf16_round(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
+    w = bf16_round((rs.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32))
+    b = (rs.standard_normal(Cout) * 0.1).astype(np.float32)
+    y = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=pad)
+    y = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.1), 2: F.relu}[act](y).numpy()
+    dx = cu(x)
+    out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_conv2d(dptr(dx), w.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                      dptr(out), B, Cin, H, W, Cout, k, k, 2, pad, pad, 0, act, 1, None))
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - y)
+    assert (err <= 8e-3 * np.abs(y) + 4e-3).all(), err.max()
+
+
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv2d_tcgen05(dev_lib, case):

@@ -46,7 +46,8 @@ def test_warp_and_fb(hostsim_lib):
 
 @pytest.mark.parametrize("case", [(1, 3, 12, 20, 8, 7, 7, 1, 3, 3, 0, 1, 0), (1, 16, 9, 14, 24, 3, 3, 2, 1, 1, 0, 2, 0),
                                   (1, 16, 8, 12, 8, 3, 3, 1, 1, 1, 1, 3, 0), (1, 49, 7, 20, 20, 3, 3, 1, 1, 1, 0, 1, 1),
-                                  (1, 32, 6, 18, 2, 5, 5, 1, 2, 2, 0, 0, 1)])
+                                  (1, 32, 6, 18, 2, 5, 5, 1, 2, 2, 0, 0, 1), (2, 32, 8, 12, 48, 3, 3, 2, 1, 1, 0, 1, 1),
+                                  (1, 64, 6, 10, 32, 1, 1, 2, 0, 0, 0, 0, 1)])
 def test_conv2d(hostsim_lib, case):
     B, Cin, H, W, Cout, kh, kw, st, py, px, refl, act, prec = case
     rs = np.random.RandomState(Cin + Cout)
