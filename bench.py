@@ -219,7 +219,6 @@ def run_b200(args):
 
     # device-resident copies of everything a step consumes
     d_frames = [rt.from_host(f) for f in frames]
-    d_feeds = [rt.from_host(pipe.depth_feed_host(f)) for f in frames]
     d_fwd = [rt.from_host(a["fwd"][None]) for a in analytic]
     d_bwd = [rt.from_host(a["bwd"][None]) for a in analytic]
     d_diff = [rt.from_host(a["diff"][None, :, :, 0]) for a in analytic]
@@ -241,13 +240,12 @@ def run_b200(args):
         s2 = fid & 1
         if state["resident"]:
             st.img = d_frames[slot]
-            feed = d_feeds[slot]
+            feed = pipe.eng.depth_feed(st.img)
         else:
             st.img = pipe._buf("img%d" % s2, (H, W, 3), np.uint8)
             st.img.t.copy_(pinned[slot], non_blocking=True)                       # H2D from pinned memory
-            feed_h = pipe.depth_feed_host(frames[slot])                            # PIL LANCZOS on the host (frame ingest)
-            feed = pipe._buf("feed", (1, 3, FEED_H, FEED_W), np.float32).upload(feed_h)
-            state["h2d"] += frames[slot].nbytes + feed_h.nbytes
+            feed = pipe.eng.depth_feed(st.img)                                     # PIL-exact LANCZOS + ToTensor on the device
+            state["h2d"] += frames[slot].nbytes
         d = pipe.eng.depth(feed)
         st.raw_depth = pipe._buf("raw%d" % s2, (H, W), np.float32)
         st.depth = pipe._buf("dep%d" % s2, (H, W), np.float32)
@@ -335,7 +333,10 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_tc_traffic.json")))["dram_bytes_per_frame"]
     except Exception:
         pass
-    base, cpu_poses = cpu_baseline(args.cpu_frames, K, frames, analytic)
+    if args.cpu_frames > 0:
+        base, cpu_poses = cpu_baseline(args.cpu_frames, K, frames, analytic)
+    else:
+        base = None          # profiling runs only (ncu): the driver's runs always include the baseline
     value = world * args.steps / (ms / 1e3)
     line = dict(
         metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),

@@ -49,6 +49,8 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     "dfvo_monodepth2_build": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float]),
     "dfvo_monodepth2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dfvo_lanczos_resize_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_depth_post": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
     "dfvo_gather_depth": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -53,7 +53,8 @@ class FramePipeline:
 
     # ------------------------------------------------------------------ per-frame stages
     def depth_feed_host(self, img):
-        """deep_models.py:195-198: PIL LANCZOS to the feed size + ToTensor (host; frame ingest)."""
+        """deep_models.py:195-198 as the reference does it on the host (PIL LANCZOS + ToTensor).  The pipeline
+        uses the bit-identical device version (Engine.depth_feed); this one serves tests / comparisons."""
         import PIL.Image as pil
         im = pil.fromarray(img).resize((self.eng.feed_w, self.eng.feed_h), pil.LANCZOS)
         return np.ascontiguousarray(np.transpose(np.asarray(im, np.uint8), (2, 0, 1))[None].astype(np.float32) / np.float32(255))
@@ -65,8 +66,7 @@ class FramePipeline:
         # double-buffer images / depths so the previous frame's stay valid as 'ref'
         slot = fid & 1
         st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
-        feed = self._buf("feed", (1, 3, self.eng.feed_h, self.eng.feed_w), np.float32).upload(self.depth_feed_host(img))
-        d = self.eng.depth(feed)
+        d = self.eng.depth(self.eng.depth_feed(st.img))                  # LANCZOS resize + ToTensor on the device
         st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
         st.depth = self._buf("dep%d" % slot, (self.H, self.W), np.float32)
         c = self.cfg

@@ -59,6 +59,26 @@ class Engine:
         self.ctx.liteflow_forward(ptrs, self.flow_fwd.ptr, self.flow_bwd.ptr, self.flow_diff.ptr, self.rt.stream_ptr())
         return self.flow_fwd, self.flow_bwd, self.flow_diff
 
+    def depth_feed(self, img_buf, out=None):
+        """deep_models.py:195-198 on the device: PIL-exact LANCZOS resize of the uint8 HWC frame to the feed size +
+        ToTensor -> float32 [1,3,feed_h,feed_w] (csrc/depth_ops.cu, tables from b200/lanczos.py)."""
+        from . import lanczos
+        H, W = img_buf.shape[0], img_buf.shape[1]
+        key = (H, W, self.feed_h, self.feed_w)
+        if getattr(self, "_lz_key", None) != key:
+            bh, kh, ksh = lanczos.coeffs(W, self.feed_w)
+            bv, kv, ksv = lanczos.coeffs(H, self.feed_h)
+            self._lz = dict(bh=self.rt.from_host(bh), kh=self.rt.from_host(kh), ksh=ksh, bv=self.rt.from_host(bv),
+                            kv=self.rt.from_host(kv), ksv=ksv, tmp=self.rt.empty((H, self.feed_w, 3), np.uint8),
+                            feed=self.rt.empty((1, 3, self.feed_h, self.feed_w), np.float32))
+            self._lz_key = key
+        z = self._lz
+        out = out or z["feed"]
+        self.lib.check(self.lib.dfvo_lanczos_resize_u8(img_buf.ptr, H, W, z["bh"].ptr, z["kh"].ptr, z["ksh"], z["bv"].ptr, z["kv"].ptr,
+                                                       z["ksv"], self.feed_h, self.feed_w, z["tmp"].ptr, None, out.ptr,
+                                                       self.rt.stream_ptr()))
+        return out
+
     def depth(self, feed_buf, out=None):
         """feed_buf: float32 [1,3,feed_h,feed_w] device buffer -> depth [feed_h, feed_w]."""
         assert self.depth_ready, "build_depth first"

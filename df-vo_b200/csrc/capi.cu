@@ -257,6 +257,16 @@ int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y
   API_END
 }
 
+int dfvo_lanczos_resize_u8(const uint8_t* img, int H, int W, const int32_t* bounds_h, const int32_t* kk_h, int ksize_h,
+                           const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, int out_h, int out_w, uint8_t* tmp, uint8_t* out_u8,
+                           float* out_nchw, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(img && bounds_h && kk_h && bounds_v && kk_v && tmp && (out_u8 || out_nchw), DFVO_EINVAL, "dfvo_lanczos_resize_u8 args");
+  return lanczos_resize_u8(img, H, W, bounds_h, kk_h, ksize_h, bounds_v, kk_v, ksize_v, out_h, out_w, tmp, out_u8, out_nchw,
+                           (cudaStream_t)stream);
+  API_END
+}
+
 int dfvo_local_bestn(const float* flow_diff, const float* depth_diff, int H, int W, int rows, int cols, int num_bestN, float thre,
                      float depth_thre, int32_t* idx_out, int32_t* cell_counts, int32_t* status, void* stream) {
   API_BEGIN

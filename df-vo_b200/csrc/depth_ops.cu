@@ -134,4 +134,60 @@ int depth_post(const float* depth, int h, int w, int H, int W, float cy0, float 
   return DFVO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// PIL-exact antialiased resize of an 8-bit HWC image (Pillow libImaging/Resample.c, 8bpc path): horizontal
+// pass to a uint8 intermediate, vertical pass, both with 22-bit fixed-point coefficients and the same
+// rounding (start at 1 << 21, arithmetic shift, clamp).  The vertical pass also emits the network feed tensor
+// float32 NCHW = uint8 / 255 (transforms.ToTensor, deep_models.py:198).
+// ---------------------------------------------------------------------------------------------
+DFVO_D uint8_t clip8_fixed(int v) {
+  v >>= 22;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__global__ void k_resample_h_u8(const uint8_t* __restrict__ img, int H, int W, const int32_t* __restrict__ bounds,
+                                const int32_t* __restrict__ kk, int ksize, int out_w, uint8_t* __restrict__ tmp) {
+  int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (xx >= out_w) return;
+  const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+  int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+  const uint8_t* row = img + ((size_t)y * W + xmin) * 3;
+  const int32_t* k = kk + (size_t)xx * ksize;
+  for (int x = 0; x < n; ++x) {
+    const int c = k[x];
+    s0 += (int)row[3 * x] * c; s1 += (int)row[3 * x + 1] * c; s2 += (int)row[3 * x + 2] * c;
+  }
+  uint8_t* o = tmp + ((size_t)y * out_w + xx) * 3;
+  o[0] = clip8_fixed(s0); o[1] = clip8_fixed(s1); o[2] = clip8_fixed(s2);
+}
+
+__global__ void k_resample_v_u8(const uint8_t* __restrict__ tmp, int W, const int32_t* __restrict__ bounds,
+                                const int32_t* __restrict__ kk, int ksize, int out_h, uint8_t* __restrict__ out_u8,
+                                float* __restrict__ out_nchw) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
+  if (x >= W) return;
+  const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+  int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+  const int32_t* k = kk + (size_t)yy * ksize;
+  for (int y = 0; y < n; ++y) {
+    const uint8_t* p = tmp + ((size_t)(ymin + y) * W + x) * 3;
+    const int c = k[y];
+    s0 += (int)p[0] * c; s1 += (int)p[1] * c; s2 += (int)p[2] * c;
+  }
+  const uint8_t v[3] = {clip8_fixed(s0), clip8_fixed(s1), clip8_fixed(s2)};
+  if (out_u8) { uint8_t* o = out_u8 + ((size_t)yy * W + x) * 3; o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+  if (out_nchw)
+    for (int c = 0; c < 3; ++c) out_nchw[((size_t)c * out_h + yy) * W + x] = (float)v[c] / 255.0f;
+}
+
+int lanczos_resize_u8(const uint8_t* img, int H, int W, const int32_t* bounds_h, const int32_t* kk_h, int ksize_h,
+                      const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, int out_h, int out_w, uint8_t* tmp,
+                      uint8_t* out_u8, float* out_nchw, cudaStream_t s) {
+  DFVO_LAUNCH(k_resample_h_u8, dim3(cdiv(out_w, 128), H), dim3(128), 0, s, img, H, W, bounds_h, kk_h, ksize_h, out_w, tmp);
+  DFVO_LAUNCH(k_resample_v_u8, dim3(cdiv(out_w, 128), out_h), dim3(128), 0, s, (const uint8_t*)tmp, out_w, bounds_v, kk_v, ksize_v,
+              out_h, out_u8, out_nchw);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 }  // namespace dfvo

@@ -402,6 +402,85 @@ template int correlation49<float>(Ten<const float>, Ten<const float>, int, int, 
 template int correlation49<bf16>(Ten<const bf16>, Ten<const bf16>, int, int, int, Ten<bf16>, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
+// 2-channel flow head: 32x8 output pixels per 256-thread block; the (8+k-1)x(32+k-1) input patch (32 bf16
+// channels, 20-word pixel pitch = conflict-free 128-bit reads) and the k*k*32*2 fp32 weights live in shared memory.
+// ---------------------------------------------------------------------------------------------
+#define FH_TW 32
+#define FH_TH 8
+template <int K>
+__global__ void __launch_bounds__(FH_TW* FH_TH)
+k_flow_head(Ten<const bf16> in, const float* __restrict__ w, float b0, float b1, Ten<const float> res, int has_res, Ten<float> out) {
+  constexpr int PW = FH_TW + K - 1, PH = FH_TH + K - 1, R = K / 2;
+  DFVO_DYN_SMEM(uint32_t, smem);
+  uint32_t* patch = smem;                                   // [PH*PW][20] words
+  float* ws = reinterpret_cast<float*>(smem + PH * PW * 20);  // [K*K][32][2]
+  const int tx = threadIdx.x % FH_TW, ty = threadIdx.x / FH_TW;
+  const int x0 = blockIdx.x * FH_TW, y0 = blockIdx.y * FH_TH, n = blockIdx.z;
+  for (int i = threadIdx.x; i < K * K * 64; i += FH_TW * FH_TH) ws[i] = w[i];
+  for (int i = threadIdx.x; i < PH * PW * 4; i += FH_TW * FH_TH) {
+    const int q = i & 3, pp = i >> 2;
+    const int sx = x0 + pp % PW - R, sy = y0 + pp / PW - R;
+    uint4 v; v.x = v.y = v.z = v.w = 0u;
+    if (sx >= 0 && sx < in.W && sy >= 0 && sy < in.H) v = *reinterpret_cast<const uint4*>(in.at(n, sy, sx) + q * 8);
+    uint32_t* d = patch + pp * 20 + q * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int ox = x0 + tx, oy = y0 + ty;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const uint32_t* pw = patch + ((ty + ky) * PW + tx + kx) * 20;
+      const float* wt = ws + (ky * K + kx) * 64;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(pw + q * 4);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f0 = __uint_as_float(u[j] << 16), f1 = __uint_as_float(u[j] & 0xffff0000u);
+          const float4 wv = *reinterpret_cast<const float4*>(wt + (q * 8 + 2 * j) * 2);   // (c,0) (c,1) (c+1,0) (c+1,1)
+          a0 += f0 * wv.x + f1 * wv.z;
+          a1 += f0 * wv.y + f1 * wv.w;
+        }
+      }
+    }
+  }
+  if (ox >= out.W || oy >= out.H) return;
+  float* o = out.at(n, oy, ox);
+  float r0 = 0.f, r1 = 0.f;
+  if (has_res) { const float* r = res.at(n, oy, ox); r0 = r[0]; r1 = r[1]; }
+  o[0] = a0 + b0 + r0;
+  o[1] = a1 + b1 + r1;
+}
+
+int flow_head(Ten<const bf16> in, const float* w, float bias0, float bias1, int k, Ten<const float> residual, Ten<float> out,
+              cudaStream_t s) {
+  DFVO_REQUIRE(in.C == 32 && (k == 3 || k == 5 || k == 7) && in.H == out.H && in.W == out.W && in.sW % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(in.p) & 15) == 0, DFVO_ESHAPE, "flow_head shapes");
+  const float hb[2] = {bias0, bias1};
+  const int has_res = residual.p != nullptr;
+  dim3 grid(cdiv(out.W, FH_TW), cdiv(out.H, FH_TH), out.N), block(FH_TW * FH_TH);
+  const size_t smem = ((size_t)(FH_TH + k - 1) * (FH_TW + k - 1) * 20 + (size_t)k * k * 64) * 4;
+#ifndef DFVO_HOSTSIM
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_flow_head<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_flow_head<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_flow_head<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+#endif
+  if (k == 7) { auto kn = k_flow_head<7>; DFVO_LAUNCH(kn, grid, block, smem, s, in, w, hb[0], hb[1], residual, has_res, out); }
+  else if (k == 5) { auto kn = k_flow_head<5>; DFVO_LAUNCH(kn, grid, block, smem, s, in, w, hb[0], hb[1], residual, has_res, out); }
+  else { auto kn = k_flow_head<3>; DFVO_LAUNCH(kn, grid, block, smem, s, in, w, hb[0], hb[1], residual, has_res, out); }
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // flow mean (lite_flow_net.py:257: tensorFlow.view(N,2,-1).mean(2))  -- one block per n
 // ---------------------------------------------------------------------------------------------
 #define FM_BLOCKS 64

@@ -85,6 +85,7 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
       if (shift) v += shift[co];
       b[co] = v;
     }
+    for (int co = 0; co < 4 && co < Cout; ++co) L->bias_h[co] = b[co];
     L->bias = arena.alloc_t<float>(L->Cout_pad);
     if (!L->bias) return DFVO_ENOMEM;
     DFVO_CUDA(cudaMemcpy(L->bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
@@ -102,6 +103,17 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
     L->w_direct = arena.alloc_t<float>(h.size());
     if (!L->w_direct) return DFVO_ENOMEM;
     DFVO_CUDA(cudaMemcpy(L->w_direct, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (want_tc && Cout == 2 && stride == 1 && kh == kw && ktot == 32) {
+    std::vector<float> h((size_t)kh * kw * ktot * 2, 0.f);
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int k = 0; k < ktot; ++k)
+          if (kmap[k] >= 0)
+            for (int co = 0; co < 2; ++co) h[((((size_t)ky * kw + kx) * ktot) + k) * 2 + co] = W(co, kmap[k], ky, kx);
+    L->w_head = arena.alloc_t<float>(h.size());
+    if (!L->w_head) return DFVO_ENOMEM;
+    DFVO_CUDA(cudaMemcpy(L->w_head, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   }
   if (want_tc) {
     DFVO_REQUIRE((stride == 1 || stride == 2) && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1|2, zero pad, K %% 16 == 0");
@@ -184,6 +196,8 @@ template <>
 int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out, int act, Ten<const float> residual,
                           cudaStream_t s) {
   if (!L.tc) return conv_direct<bf16, float>(to_direct(L, act), in, out, residual, s);
+  if (L.w_head && act == ACT_NONE && in.C == 32 && (L.kh == 3 || L.kh == 5 || L.kh == 7) && L.pad_y == L.kh / 2 && L.pad_x == L.kw / 2)
+    return flow_head(in, L.w_head, L.bias_h[0], L.bias_h[1], L.kh, residual, out, s);
   DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc head: input view has %d channels, layer expects %d", in.C, L.Ktot);
   ConvTc c;
   memset(&c, 0, sizeof(c));

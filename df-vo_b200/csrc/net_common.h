@@ -40,7 +40,9 @@ struct ConvLayer {
   float* w_direct = nullptr;   // device [kh*kw*Ktot][w_pitch] fp32
   int w_pitch = 0;
   bf16* w_tc = nullptr;        // device [kh*kw][Cout_pad][Ktot] bf16 (only if tc requested)
+  float* w_head = nullptr;     // device [kh*kw][Ktot][2] fp32, only for 2-channel heads (flow_head kernel)
   float* bias = nullptr;       // device [Cout_pad] fp32 (zero padded; zeros if the conv has no bias)
+  float bias_h[4] = {0.f, 0.f, 0.f, 0.f};   // host copy of the first biases (kernel arguments of the head kernel)
   bool tc = false;
 };
 

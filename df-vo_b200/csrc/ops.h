@@ -66,6 +66,12 @@ template <typename TI, typename TO>
 int conv_direct(const ConvDirect& c, Ten<const TI> in, Ten<TO> out, Ten<const TO> residual,
                 cudaStream_t s);
 
+// 2-channel flow head (lite_flow_net.py:128,178): k x k conv (k = 3, 5, 7; 'same' zero padding) over 32 bf16 channels
+// -> 2 fp32 channels + bias + optional fp32 residual.  w = [k*k][32][2] fp32.  CUDA cores: with N = 2 the tensor-core
+// tile would be 87 % padding and its 49 taps make it L2-bound.
+int flow_head(Ten<const __nv_bfloat16> in, const float* w, float bias0, float bias1, int k, Ten<const float> residual,
+              Ten<float> out, cudaStream_t s);
+
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) -------------------------------------------
 struct ConvTcSource {
   const bf16* p;          // NHWC bf16 view (channel slice allowed)
@@ -118,6 +124,11 @@ int disp_to_depth(const float* disp, int n, float min_depth, float max_depth, fl
 // cv2.resize(INTER_NEAREST) to (W,H) + preprocess_depth (dfvo.py:314-319, utils.py:89-114)
 int depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1, float crop_x0, float crop_x1,
                float min_depth, float max_depth, float* raw_out, float* depth_out, cudaStream_t s);
+
+// PIL-exact LANCZOS resize of a uint8 HWC image (tables from b200/lanczos.py); tmp = uint8 [H][out_w][3]
+int lanczos_resize_u8(const uint8_t* img, int H, int W, const int32_t* bounds_h, const int32_t* kk_h, int ksize_h,
+                      const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, int out_h, int out_w, uint8_t* tmp,
+                      uint8_t* out_u8, float* out_nchw, cudaStream_t s);
 
 // ---- keypoint selection (select.cu) -------------------------------------------------------------
 int local_bestn(const float* diff, const float* depth_diff, int H, int W, int rows, int cols, int n_best,

@@ -91,13 +91,11 @@ class DeepModel:
         }
 
     def forward_depth(self, imgs):
-        """deep_models.py:184-206: PIL LANCZOS resize to the feed size + ToTensor stay on the host (frame
-        ingest); the network runs on the device.  Returns float32 [feed_h, feed_w]."""
-        import PIL.Image as pil
-        img = pil.fromarray(imgs[0]).resize((self.engine.feed_w, self.engine.feed_h), pil.LANCZOS)
-        # transforms.ToTensor(): HWC uint8 -> CHW float32 / 255
-        feed = np.ascontiguousarray(np.transpose(np.asarray(img, np.uint8), (2, 0, 1))[None].astype(np.float32) / np.float32(255))
-        out = self.engine.depth(self.rt.from_host(feed))
+        """deep_models.py:184-206.  The PIL LANCZOS resize to the feed size + ToTensor run on the device,
+        bit-identical to Pillow's 8-bit path (b200/lanczos.py, csrc/depth_ops.cu).  Returns float32
+        [feed_h, feed_w] on the host because the driver hands it to cv2.resize (dfvo.py:314-317)."""
+        img = self.rt.from_host(np.ascontiguousarray(imgs[0], np.uint8))
+        out = self.engine.depth(self.engine.depth_feed(img))
         return out.numpy()
 
     def forward_pose(self, imgs):

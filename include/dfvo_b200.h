@@ -89,6 +89,13 @@ int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, 
 /* img: float [1,3,feed_h,feed_w] in [0,1] (the PIL-LANCZOS-resized ToTensor image, deep_models.py:195-201);
  * depth_out [feed_h,feed_w] fp32 = Monodepth2DepthNet.inference_depth (monodepth2.py:121-139). */
 int dfvo_monodepth2_forward(dfvo_ctx* ctx, const float* img, float* depth_out, void* stream);
+/* PIL.Image.resize((out_w,out_h), LANCZOS) + transforms.ToTensor (deep_models.py:195-198) on the device,
+ * bit-exact with Pillow's 8-bit path.  img uint8 [H,W,3]; bounds_* [out][2] / kk_* [out][ksize] int32 are the
+ * fixed-point filter tables of b200/lanczos.py (device memory); tmp uint8 [H][out_w][3]; out_u8 [out_h][out_w][3]
+ * and/or out_nchw float32 [3][out_h][out_w] (= uint8/255). */
+int dfvo_lanczos_resize_u8(const uint8_t* img, int H, int W, const int32_t* bounds_h, const int32_t* kk_h,
+                           int ksize_h, const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, int out_h,
+                           int out_w, uint8_t* tmp, uint8_t* out_u8, float* out_nchw, void* stream);
 /* cv2.resize(raw_depth, (W,H), INTER_NEAREST) + utils.preprocess_depth (dfvo.py:314-319, utils.py:89-114):
  * depth [h,w] -> raw_out [H,W] (may be NULL), depth_out [H,W]; crop = [[y0,y1],[x0,x1]] normalised. */
 int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1,

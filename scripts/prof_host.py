@@ -14,7 +14,7 @@ pipe.load_weights(synth.liteflownet_weights(), enc, dec)
 H, W = 376, 1241
 d_fwd = [rt.from_host(a["fwd"][None]) for a in analytic]; d_bwd = [rt.from_host(a["bwd"][None]) for a in analytic]
 d_diff = [rt.from_host(a["diff"][None, :, :, 0]) for a in analytic]; d_depth = [rt.from_host(a["depth"]) for a in analytic]
-d_frames = [rt.from_host(f) for f in frames]; d_feeds = [rt.from_host(pipe.depth_feed_host(f)) for f in frames]
+d_frames = [rt.from_host(f) for f in frames]; d_feeds = [pipe.eng.depth_feed(f) for f in d_frames]
 T = {}
 def tic(): torch.cuda.synchronize(); return time.perf_counter()
 def add(k, t0): torch.cuda.synchronize(); T[k] = T.get(k, 0) + time.perf_counter() - t0

@@ -157,3 +157,22 @@ def test_score_hypotheses_config4(dev_lib):
     for i in idx:
         want = int((cvreplay.sampson_errors(E[i].reshape(3, 3), x1, x2) <= thr2).sum())
         assert int(got[i]) == want
+
+
+def test_lanczos_feed_bit_exact_with_pil(dev_lib):
+    import PIL.Image as pil
+    from b200 import lanczos
+    H, W, oh, ow = 376, 1241, 192, 640
+    img = synth.value_noise_image(H, W, 9)
+    ref = np.asarray(pil.fromarray(img).resize((ow, oh), pil.LANCZOS))
+    bh, kh, ksh = lanczos.coeffs(W, ow)
+    bv, kv, ksv = lanczos.coeffs(H, oh)
+    d = [cu(a) for a in (img, bh, kh, bv, kv)]
+    tmp = torch.zeros((H, ow, 3), dtype=torch.uint8, device="cuda")
+    out = torch.zeros((oh, ow, 3), dtype=torch.uint8, device="cuda")
+    f = torch.zeros((3, oh, ow), dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_lanczos_resize_u8(dptr(d[0]), H, W, dptr(d[1]), dptr(d[2]), ksh, dptr(d[3]), dptr(d[4]), ksv, oh, ow,
+                                                 dptr(tmp), dptr(out), dptr(f), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(f.cpu().numpy(), np.transpose(ref, (2, 0, 1)).astype(np.float32) / np.float32(255))

@@ -163,3 +163,21 @@ def test_tracker_orchestration_vs_reference_classes(hostsim_lib):
             dp = (depth * ((depth < 50) & (depth > 0))).astype(np.float64)
             s = tracking.find_scale_from_depth(eng, kp_ref, kp_cur, np.linalg.inv(pose), dp, K)
             assert abs(s - float(g[name + "_scale"])) < 1e-10
+
+
+def test_lanczos_feed_bit_exact_with_pil(hostsim_lib):
+    """deep_models.py:195-198: the device resize (run here in emulation) equals PIL.Image.resize(LANCZOS)
+    + ToTensor bit for bit."""
+    import PIL.Image as pil
+    from b200 import lanczos
+    for (H, W, oh, ow, seed) in [(376, 1241, 192, 640, 1), (70, 150, 64, 96, 2), (100, 300, 128, 416, 3)]:
+        rs = np.random.RandomState(seed)
+        img = synth.value_noise_image(H, W, seed) if seed != 2 else rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        ref = np.asarray(pil.fromarray(img).resize((ow, oh), pil.LANCZOS))
+        bh, kh, ksh = lanczos.coeffs(W, ow)
+        bv, kv, ksv = lanczos.coeffs(H, oh)
+        tmp, out, f = np.zeros((H, ow, 3), np.uint8), np.zeros((oh, ow, 3), np.uint8), np.zeros((3, oh, ow), np.float32)
+        hostsim_lib.check(hostsim_lib.dfvo_lanczos_resize_u8(hptr(img), H, W, hptr(bh), hptr(kh), ksh, hptr(bv), hptr(kv), ksv, oh, ow,
+                                                              hptr(tmp), hptr(out), hptr(f), None))
+        assert np.array_equal(out, ref)
+        assert np.array_equal(f, np.transpose(ref, (2, 0, 1)).astype(np.float32) / np.float32(255))
