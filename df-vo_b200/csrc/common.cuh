@@ -17,9 +17,11 @@
 #if defined(__CUDACC__)
 #define DFVO_HD __host__ __device__ __forceinline__
 #define DFVO_D __device__ __forceinline__
+#define DFVO_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define DFVO_HD inline
 #define DFVO_D inline
+#define DFVO_HD_NOINLINE inline
 #endif
 
 namespace dfvo {

@@ -187,14 +187,92 @@ DFVO_HD void build_poly(const double M[10][20], double bx[3][4], double by[3][4]
 }
 
 // Durand-Kerner (the iteration of cv::solvePoly): roots of c[0..n] (ascending).  re/im: [n].
+// cv::solvePoly stops only at exact stagnation (max_diff <= 0), i.e. it normally runs all of its 1000
+// iterations.  The iteration converges quadratically at simple roots (linearly, ratio 1/2, at double roots):
+// once the largest correction is below 1e-13 of the root scale -- or has stopped contracting at the
+// round-off floor (eps for simple roots, eps^(1/m) for an m-fold root) -- the roots are stationary at
+// round-off level: same roots, same index order; the real ones are Newton-polished by the caller.
+// N is a compile-time degree so that roots and coefficients live in registers on the device.
+struct DkStop {
+  double prev = 1e300;
+  int stall = 0;
+  DFVO_HD bool done(double max_diff, double rmax) {
+    if (max_diff <= 1e-13 * rmax) return true;
+    if (!(max_diff == max_diff)) return true;       // NaN guard
+    if (max_diff >= 0.25 * prev) {                  // no longer contracting quadratically
+      if (max_diff <= 1e-9 * rmax) return true;
+      if (max_diff <= 1e-4 * rmax && ++stall >= 8) return true;
+    } else {
+      stall = 0;
+    }
+    prev = max_diff;
+    return false;
+  }
+};
+
+template <int N>
+DFVO_HD_NOINLINE int durand_kerner_fixed(const double* c_in, double* re_out, double* im_out, int max_iters) {
+  double c[N + 1], re[N], im[N];
+#pragma unroll
+  for (int k = 0; k <= N; ++k) c[k] = c_in[k];
+  {
+    double pr = 1.0, pi = 0.0;                       // initial guesses p = (1,0) * (1,1)^i
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      re[i] = pr; im[i] = pi;
+      const double nr = pr - pi, ni = pr + pi;
+      pr = nr; pi = ni;
+    }
+  }
+  DkStop stop;
+  int iter = 0;
+  for (; iter < max_iters; ++iter) {
+    double max_diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double xr = re[i], xi = im[i];
+      double nr = c[N], ni = 0.0, dr = c[N], di = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double tr = nr * xr - ni * xi + c[N - j - 1], ti = nr * xi + ni * xr;   // num = num * p + c[n-j-1]
+        nr = tr; ni = ti;
+        if (j != i) {
+          const double er = xr - re[j], ei = xi - im[j];
+          const bool nz = (er != 0.0 || ei != 0.0);
+          const double ur = dr * er - di * ei, ui = dr * ei + di * er;
+          dr = nz ? ur : dr; di = nz ? ui : di;
+        }
+      }
+      const double den = dr * dr + di * di;
+      double qr = 0.0, qi = 0.0;
+      if (den > 0.0) { qr = (nr * dr + ni * di) / den; qi = (ni * dr - nr * di) / den; }   // num /= denom
+      re[i] = xr - qr; im[i] = xi - qi;
+      const double ad = sqrt(qr * qr + qi * qi);
+      if (ad > max_diff) max_diff = ad;
+    }
+    double rmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double a = fabs(re[i]) + fabs(im[i]); if (a > rmax) rmax = a; }
+    if (stop.done(max_diff, rmax)) break;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { re_out[i] = re[i]; im_out[i] = im[i]; }
+#ifdef DFVO_DK_STATS
+  DFVO_DK_STATS(iter);
+#endif
+  return iter;
+}
+
+// run-time degree (n < 10 only when the leading coefficients vanish)
 DFVO_HD int durand_kerner(const double* c, int n, double* re, double* im, int max_iters) {
-  // initial guesses p = (1,0) * (1,1)^i
+  if (n == 10) return durand_kerner_fixed<10>(c, re, im, max_iters);
   double pr = 1.0, pi = 0.0;
   for (int i = 0; i < n; ++i) {
     re[i] = pr; im[i] = pi;
-    const double nr = pr - pi, ni = pr + pi;       // (pr + i pi) * (1 + i)
+    const double nr = pr - pi, ni = pr + pi;
     pr = nr; pi = ni;
   }
+  DkStop stop;
   int iter = 0;
   for (; iter < max_iters; ++iter) {
     double max_diff = 0.0;
@@ -202,7 +280,6 @@ DFVO_HD int durand_kerner(const double* c, int n, double* re, double* im, int ma
       const double xr = re[i], xi = im[i];
       double nr = c[n], ni = 0.0, dr = c[n], di = 0.0;
       for (int j = 0; j < n; ++j) {
-        // num = num * p + c[n-j-1]
         const double tr = nr * xr - ni * xi + c[n - j - 1], ti = nr * xi + ni * xr;
         nr = tr; ni = ti;
         if (j != i) {
@@ -213,7 +290,6 @@ DFVO_HD int durand_kerner(const double* c, int n, double* re, double* im, int ma
           }
         }
       }
-      // num /= denom
       const double den = dr * dr + di * di;
       double qr = 0.0, qi = 0.0;
       if (den > 0.0) { qr = (nr * dr + ni * di) / den; qi = (ni * dr - nr * di) / den; }
@@ -221,14 +297,9 @@ DFVO_HD int durand_kerner(const double* c, int n, double* re, double* im, int ma
       const double ad = sqrt(qr * qr + qi * qi);
       if (ad > max_diff) max_diff = ad;
     }
-    // cv::solvePoly stops only at exact stagnation (max_diff <= 0), i.e. it normally runs all of its 1000
-    // iterations.  The iteration converges quadratically (linearly with ratio 1/2 at double roots): once the
-    // largest correction is below 1e-13 of the root scale the roots are stationary at round-off level -- same
-    // roots, same index order -- and the real ones are Newton-polished below.
     double rmax = 0.0;
     for (int i = 0; i < n; ++i) { const double a = fabs(re[i]) + fabs(im[i]); if (a > rmax) rmax = a; }
-    if (max_diff <= 1e-13 * rmax) break;
-    if (!(max_diff == max_diff)) break;           // NaN guard
+    if (stop.done(max_diff, rmax)) break;
   }
   return iter;
 }

@@ -9,7 +9,7 @@
 //      (strict >, first-found wins) and adaptive iteration count, i.e. finds the candidate OpenCV
 //      would return and where it would stop;
 //   5. k_finalize: inlier mask + GRIC-E residual sum (gric.py:14-37,94-132) of each repeat's winner;
-//   6. k_recover_pose: decomposeEssentialMat + 4 x triangulation + cheirality vote.
+//   6. k_recover_pose_vote / _pick: decomposeEssentialMat + 4 x triangulation + cheirality vote.
 // All arithmetic is FP64 (inlier decisions are threshold tests).
 #include "fivept.cuh"
 #include "ops.h"
@@ -274,9 +274,9 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
 
 // ---------------------------------------------------------------------------------------------
 // cv2.recoverPose(E, points1, points2, focal, pp)  (E_tracker.py:292-295; five-point.cpp)
-// One 256-thread block: decomposeEssentialMat, then every point is triangulated (4x4 DLT, smallest
-// singular vector as in cv::triangulatePoints) against the four (R,t) candidates; cheirality masks in
-// OpenCV's order; first maximum wins.  out: Rt[12] (R row-major then t), info[5] = {best count, c0..c3}.
+// decomposeEssentialMat, then every point is triangulated (4x4 DLT, smallest singular vector as in
+// cv::triangulatePoints) against the four (R,t) candidates; cheirality masks in OpenCV's order; first
+// maximum wins.  out: Rt[12] (R row-major then t), info[5] = {best count, c0..c3}.
 // ---------------------------------------------------------------------------------------------
 DFVO_D void triangulate_dlt(const double P1[3][4], double u0, double v0, double u1, double v1, double X[4]) {
   // rows of A (cvTriangulatePoints): x*P[2] - P[0], y*P[2] - P[1] for view 0 = [I|0] and view 1 = P1
@@ -291,75 +291,84 @@ DFVO_D void triangulate_dlt(const double P1[3][4], double u0, double v0, double 
   for (int i = 0; i < 4; ++i) X[i] = V[i][m];
 }
 
-__global__ void __launch_bounds__(256)
-k_recover_pose(const double* __restrict__ Eptr, const double* __restrict__ p1, const double* __restrict__ p2, int N, double focal,
-               double cx, double cy, double dist, double* __restrict__ Rt_out, uint8_t* __restrict__ mask_out,
-               int32_t* __restrict__ info) {
-  __shared__ double sR[2][3][3], st[3];
-  __shared__ int cnt[4][256];
-  __shared__ int best_c;
-  const int t = threadIdx.x;
-  if (t == 0) {
-    double E[3][3], U[3][3], s[3], Vt[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) E[i][j] = Eptr[3 * i + j];
-    sm::svd3_rank2(E, U, s, Vt);
-    if (sm::det3(U) < 0) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) U[i][j] = -U[i][j];
-    if (sm::det3(Vt) < 0) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Vt[i][j] = -Vt[i][j];
-    const double W[3][3] = {{0, 1, 0}, {-1, 0, 0}, {0, 0, 1}};
-    for (int which = 0; which < 2; ++which) {
-      double T[3][3];
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double a = 0;
-        for (int k = 0; k < 3; ++k) a += U[i][k] * (which == 0 ? W[k][j] : W[j][k]);
-        T[i][j] = a;
-      }
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double a = 0;
-        for (int k = 0; k < 3; ++k) a += T[i][k] * Vt[k][j];
-        sR[which][i][j] = a;
-      }
+// decomposeEssentialMat: R candidates U W Vt / U W^T Vt and t = U[:,2]
+DFVO_D void decompose_essential(const double* __restrict__ Eptr, double R[2][3][3], double tv[3]) {
+  double E[3][3], U[3][3], s[3], Vt[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) E[i][j] = Eptr[3 * i + j];
+  sm::svd3_rank2(E, U, s, Vt);
+  if (sm::det3(U) < 0) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) U[i][j] = -U[i][j];
+  if (sm::det3(Vt) < 0) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Vt[i][j] = -Vt[i][j];
+  const double W[3][3] = {{0, 1, 0}, {-1, 0, 0}, {0, 0, 1}};
+  for (int which = 0; which < 2; ++which) {
+    double T[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+      double a = 0;
+      for (int k = 0; k < 3; ++k) a += U[i][k] * (which == 0 ? W[k][j] : W[j][k]);
+      T[i][j] = a;
     }
-    for (int i = 0; i < 3; ++i) st[i] = U[i][2];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+      double a = 0;
+      for (int k = 0; k < 3; ++k) a += T[i][k] * Vt[k][j];
+      R[which][i][j] = a;
+    }
   }
+  for (int i = 0; i < 3; ++i) tv[i] = U[i][2];
+}
+
+// Pass 1: one thread per (point, candidate) -- the 4 candidates of a point sit in adjacent lanes.  Every block
+// repeats the (tiny) decomposition instead of waiting for a producer kernel.  mask_out[j] receives the 4-bit
+// candidate field, info[1+k] the cheirality count of candidate k (atomics; info zeroed by the caller).
+__global__ void __launch_bounds__(256)
+k_recover_pose_vote(const double* __restrict__ Eptr, const double* __restrict__ p1, const double* __restrict__ p2, int N, double focal,
+                    double cx, double cy, double dist, uint8_t* __restrict__ mask_out, int32_t* __restrict__ info) {
+  __shared__ double sR[2][3][3], st[3];
+  __shared__ int cnt[4];
+  const int t = threadIdx.x;
+  if (t == 0) decompose_essential(Eptr, sR, st);
+  if (t < 4) cnt[t] = 0;
   __syncthreads();
-  int c[4] = {0, 0, 0, 0};
-  for (int j = t; j < N; j += 256) {
+  const int g = blockIdx.x * 256 + t, j = g >> 2, k = g & 3;
+  bool m = false;
+  if (j < N) {
     const double u0 = (p1[2 * j] - cx) / focal, v0 = (p1[2 * j + 1] - cy) / focal;
     const double u1 = (p2[2 * j] - cx) / focal, v1 = (p2[2 * j + 1] - cy) / focal;
-    uint8_t bits = 0;
-    for (int k = 0; k < 4; ++k) {
-      double P[3][4];
-      const double sg = k < 2 ? 1.0 : -1.0;
-      for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) P[a][b] = sR[k & 1][a][b]; P[a][3] = sg * st[a]; }
-      double X[4];
-      triangulate_dlt(P, u0, v0, u1, v1, X);
-      bool m = (X[2] * X[3]) > 0;
-      const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
-      m = m && (z < dist);
-      const double z2 = P[2][0] * x + P[2][1] * y + P[2][2] * z + P[2][3];
-      m = m && (z2 > 0) && (z2 < dist);
-      if (m) { bits |= (uint8_t)(1u << k); ++c[k]; }
-    }
-    mask_out[j] = bits;                 // candidate bit-field; resolved below
+    double P[3][4];
+    const double sg = k < 2 ? 1.0 : -1.0;
+    for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) P[a][b] = sR[k & 1][a][b]; P[a][3] = sg * st[a]; }
+    double X[4];
+    triangulate_dlt(P, u0, v0, u1, v1, X);
+    m = (X[2] * X[3]) > 0;
+    const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
+    m = m && (z < dist);
+    const double z2 = P[2][0] * x + P[2][1] * y + P[2][2] * z + P[2][3];
+    m = m && (z2 > 0) && (z2 < dist);
   }
-  for (int k = 0; k < 4; ++k) cnt[k][t] = c[k];
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (t < off) for (int k = 0; k < 4; ++k) cnt[k][t] += cnt[k][t + off];
-    __syncthreads();
-  }
-  if (t == 0) {
-    int b = 0;
-    for (int k = 1; k < 4; ++k) if (cnt[k][0] > cnt[b][0]) b = k;      // first maximum wins
-    best_c = b;
-    for (int a = 0; a < 3; ++a) for (int q = 0; q < 3; ++q) Rt_out[3 * a + q] = sR[b & 1][a][q];
-    for (int a = 0; a < 3; ++a) Rt_out[9 + a] = (b < 2 ? 1.0 : -1.0) * st[a];
-    info[0] = cnt[b][0];
-    for (int k = 0; k < 4; ++k) info[1 + k] = cnt[k][0];
+  const unsigned ballot = __ballot_sync(0xffffffffu, m);
+  const int lane = t & 31;
+  if (j < N && k == 0) mask_out[j] = (uint8_t)((ballot >> lane) & 0xfu);
+  if (lane < 4) {                                  // lane k sums candidate k over the warp's 8 points
+    const int c = __popc(ballot & (0x11111111u << lane));
+    if (c) atomicAdd(&cnt[lane], c);
   }
   __syncthreads();
-  const int b = best_c;
-  for (int j = t; j < N; j += 256) mask_out[j] = (mask_out[j] >> b) & 1u;
+  if (t < 4 && cnt[t]) atomicAdd(&info[1 + t], cnt[t]);
+}
+
+// Pass 2: first maximum wins (OpenCV's order); resolve the bit-field to the winner's mask; block 0 writes R|t.
+__global__ void __launch_bounds__(256)
+k_recover_pose_pick(const double* __restrict__ Eptr, int N, double* __restrict__ Rt_out, uint8_t* __restrict__ mask_out,
+                    int32_t* __restrict__ info) {
+  int b = 0;
+  for (int k = 1; k < 4; ++k) if (info[1 + k] > info[1 + b]) b = k;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j < N) mask_out[j] = (mask_out[j] >> b) & 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double R[2][3][3], tv[3];
+    decompose_essential(Eptr, R, tv);
+    for (int a = 0; a < 3; ++a) for (int q = 0; q < 3; ++q) Rt_out[3 * a + q] = R[b & 1][a][q];
+    for (int a = 0; a < 3; ++a) Rt_out[9 + a] = (b < 2 ? 1.0 : -1.0) * tv[a];
+    info[0] = info[1 + b];
+  }
 }
 
 __global__ void k_triangulate_depth(const double* __restrict__ x1, const double* __restrict__ x2, int N, const double* __restrict__ T21,
@@ -382,7 +391,9 @@ int triangulate_depth(const double* x1, const double* x2, int N, const double* T
 
 int recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
                  uint8_t* mask_out, int32_t* info, cudaStream_t s) {
-  DFVO_LAUNCH(k_recover_pose, dim3(1), dim3(256), 0, s, E, p1, p2, N, focal, cx, cy, 50.0, Rt_out, mask_out, info);
+  DFVO_CUDA(cudaMemsetAsync(info, 0, 5 * sizeof(int32_t), s));
+  DFVO_LAUNCH(k_recover_pose_vote, dim3(cdiv(4 * N, 256)), dim3(256), 0, s, E, p1, p2, N, focal, cx, cy, 50.0, mask_out, info);
+  DFVO_LAUNCH(k_recover_pose_pick, dim3(cdiv(N, 256)), dim3(256), 0, s, E, N, Rt_out, mask_out, info);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }
