@@ -57,15 +57,15 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic inputs (oracle.synth is the shared seeded generator; it contains no arithmetic of the path)
+# synthetic inputs (synthdata.py: seeded generators only, no arithmetic of the path)
 # ------------------------------------------------------------------------------------------------
 def make_inputs(seed):
-    from oracle import seqdata, synth
+    import synthdata as synth
     K = synth.kitti_intrinsics(H, W)
     frames = [synth.value_noise_image(H, W, seed * 100 + i) for i in range(N_DISTINCT)]
     modes = ["normal"] * N_DISTINCT
     modes[5] = "still"             # one PnP-fallback frame per cycle (GRIC prefers the homography)
-    analytic = [seqdata.frame_inputs(i, H, W, K, modes[i]) for i in range(N_DISTINCT)]
+    analytic = [synth.frame_inputs(i, H, W, K, modes[i]) for i in range(N_DISTINCT)]
     return K, frames, analytic
 
 
@@ -186,7 +186,7 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from b200 import native, pipeline, runtime as rt_mod
-    from oracle import synth
+    import synthdata as synth
     rt = rt_mod.CudaRuntime(local_rank)
     rt_mod.set_runtime(rt)
     lib = rt.lib
@@ -195,22 +195,8 @@ def run_b200(args):
     enc, dec = synth.monodepth2_weights(4869, FEED_H, FEED_W)
     flow_w = synth.liteflownet_weights()
     if world > 1:
-        import torch.distributed as dist
-        blobs = []
-        for d in (flow_w, enc, dec):
-            for k in sorted(d):
-                if hasattr(d[k], "shape"):
-                    blobs.append((d, k))
-        flat = torch.cat([torch.from_numpy(np.ascontiguousarray(d[k], np.float32).reshape(-1)) for d, k in blobs]).cuda()
-        if rank != 0:
-            flat.zero_()
-        dist.broadcast(flat, src=0)
-        host = flat.cpu().numpy()
-        off = 0
-        for d, k in blobs:
-            n = d[k].size
-            d[k] = host[off:off + n].reshape(d[k].shape).copy()
-            off += n
+        from b200 import multi
+        flow_w, enc, dec = multi.broadcast_weights([flow_w, enc, dec], src=0, device=torch.device("cuda", local_rank))
 
     K, frames, analytic = make_inputs(rank)
     np.random.seed(4869 + rank)
@@ -288,10 +274,8 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            from b200 import multi
+            ms = multi.max_over_ranks(ms, device=torch.device("cuda", local_rank))
         return ms, lib.dfvo_launch_count() - l0
 
     pipe.step(None)                                   # frame 0 (no flow yet)

@@ -25,22 +25,8 @@ def write_sequence(root, n_frames, h, w, seq="00"):
     return [cx / 1226.0 * w, cy / 370.0 * h, fx / 1226.0 * w, fy / 370.0 * h]
 
 
-def frame_inputs(t, h, w, K, mode="normal"):
-    """Analytic network outputs for the pair (t-1, t): forward/backward flow [2,h,w] f32, inconsistency
-    [h,w,1] f32 and the CNN depth [h,w] f32 of frame t.  mode 'still' has zero translation (forces the
-    GRIC check to prefer the homography -> PnP fallback); 'blind' has no consistent flow at all."""
-    rs = np.random.RandomState(1000 + t)
-    depth = synth.scene_depth(h, w, K, 7).astype(np.float32) * np.float32(1.0 + 0.05 * np.sin(t))
-    rvec, tr = synth.default_motion(rs)
-    if mode == "still":
-        tr = tr * 0.0
-    flow = synth.rigid_flow(depth.astype(np.float64), K, synth.rodrigues(rvec), tr) + rs.standard_normal((2, h, w)) * 0.05
-    diff = np.abs(rs.standard_normal((h, w)) * (0.08 if mode != "blind" else 50.0))
-    return dict(fwd=flow.astype(np.float32), bwd=(-flow).astype(np.float32), diff=diff.astype(np.float32)[..., None],
-                depth=depth, rvec=rvec, t=tr)
-
-
-MODES = ["normal", "normal", "normal", "still", "normal", "blind", "normal"]      # frame t uses MODES[t]
+frame_inputs = synth.frame_inputs
+MODES = synth.SEQUENCE_MODES
 
 
 def patch_deep_model(DeepModel, h, w, K):
