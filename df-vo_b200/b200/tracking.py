@@ -49,7 +49,7 @@ class Engine:
         self.feed_h, self.feed_w = int(enc["height"]), int(enc["width"])
         c = depth_constants(dataset)
         self.ctx.monodepth2_build(self.feed_h, self.feed_w, precision, c["min_depth"], c["max_depth"], c["baseline"])
-        self.depth_feed = self.rt.empty((self.feed_h, self.feed_w), np.float32)
+        self.depth_out = self.rt.empty((self.feed_h, self.feed_w), np.float32)
         self.depth_ready = True
 
     def flow(self, img_bufs):
@@ -82,7 +82,7 @@ class Engine:
     def depth(self, feed_buf, out=None):
         """feed_buf: float32 [1,3,feed_h,feed_w] device buffer -> depth [feed_h, feed_w]."""
         assert self.depth_ready, "build_depth first"
-        out = out or self.depth_feed
+        out = out or self.depth_out
         self.ctx.monodepth2_forward(feed_buf.ptr, out.ptr, self.rt.stream_ptr())
         return out
 

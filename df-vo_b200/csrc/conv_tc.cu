@@ -18,8 +18,11 @@
 #ifndef DFVO_HOSTSIM
 #include <cuda.h>
 #endif
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -512,22 +515,27 @@ long long g_launch_count = 0;
 static int g_prof_on = 0;
 static double g_prof_flops = 0.0;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<std::string> g_prof_desc;      // per-launch layer description (DFVO_TC_TRACE=1 prints them with their times)
 
 void conv_tc_profile_enable(int on) {
   g_prof_on = on;
   if (on) {
     for (auto& e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     g_prof_events.clear();
+    g_prof_desc.clear();
     g_prof_flops = 0.0;
   }
 }
 
 void conv_tc_profile_read(double* ms, long long* launches, double* flops) {
   double tot = 0.0;
-  for (auto& e : g_prof_events) {
+  const bool trace = getenv("DFVO_TC_TRACE") != nullptr;
+  for (size_t i = 0; i < g_prof_events.size(); ++i) {
+    auto& e = g_prof_events[i];
     cudaEventSynchronize(e.second);
     float t = 0.f;
     if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) tot += t;
+    if (trace && i < g_prof_desc.size()) fprintf(stderr, "conv_tc %4zu %8.2f us  %s\n", i, t * 1e3, g_prof_desc[i].c_str());
   }
   *ms = tot; *launches = (long long)g_prof_events.size(); *flops = g_prof_flops;
 }
@@ -545,7 +553,16 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
   k_conv_tc<<<pl.grid, TC_THREADS, pl.smem, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k);
-  if (g_prof_on) { cudaEventRecord(e1, s); g_prof_events.push_back({e0, e1}); g_prof_flops += c.flops; }
+  if (g_prof_on) {
+    cudaEventRecord(e1, s);
+    g_prof_events.push_back({e0, e1});
+    g_prof_flops += c.flops;
+    char d[256];
+    snprintf(d, sizeof(d), "N%d %dx%d s%d taps%d src[%d,%d,%d] cout%d/%d bn%d tile%dx%d stages%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,
+             pl.k.stride, c.ntaps, c.src[0].C, c.nsrc > 1 ? c.src[1].C : 0, c.nsrc > 2 ? c.src[2].C : 0, c.Cout, c.Cout_pad, pl.k.block_n,
+             pl.k.tw, pl.k.th, pl.k.stages, pl.grid, pl.k.ntiles, c.flops * 1e-9);
+    g_prof_desc.push_back(d);
+  }
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }

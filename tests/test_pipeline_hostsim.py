@@ -50,3 +50,33 @@ def test_pipeline_matches_reference_driver(hostsim_lib):
         dt = np.linalg.norm(pose[:3, 3] - g["poses"][t][:3, 3])
         assert ang < 1e-6 and dt < 1e-6 * max(1.0, np.linalg.norm(g["poses"][t][:3, 3])), (t, ang, dt)
     assert "PnP" in modes and "const" in modes and "E" in modes      # all three branches of dfvo.py:121-262 exercised
+
+
+def test_pipeline_real_infer_plumbing(hostsim_lib):
+    """The un-injected FramePipeline.infer/step (upload -> device LANCZOS feed -> depth net -> depth post ->
+    flow net -> tracking) runs end to end on a small frame pair; the depth it produces equals the stage-level
+    path (Engine.depth on the PIL feed), i.e. the wiring bench.py times is the tested one."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    from runtime import HostsimRuntime
+    import synthdata
+    from b200 import native, pipeline, runtime as rt_mod
+    rt = HostsimRuntime(hostsim_lib)
+    rt_mod.set_runtime(rt)
+    h, w = 64, 96
+    K = synthdata.kitti_intrinsics(h, w)
+    enc, dec = synthdata.monodepth2_weights(4869, 32, 64)
+    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_FP32, runtime=rt)
+    p.load_weights(synthdata.liteflownet_weights(), enc, dec)
+    frames = [synthdata.value_noise_image(h, w, 11), synthdata.value_noise_image(h, w, 12)]
+    np.random.seed(1)
+    for f in frames:
+        pose = p.step(f)
+        assert pose.shape == (4, 4) and np.all(np.isfinite(pose))
+    assert p.eng.flow_ready and np.all(np.isfinite(p.eng.flow_fwd.numpy())) and np.all(np.isfinite(p.eng.flow_diff.numpy()))
+    # depth of the last frame through the host (PIL) feed == through the device feed
+    feed_host = rt.from_host(p.depth_feed_host(frames[1]))
+    d_host = p.eng.depth(feed_host, out=rt.empty((p.eng.feed_h, p.eng.feed_w), np.float32)).numpy()
+    d_dev = p.eng.depth(p.eng.depth_feed(rt.from_host(frames[1]))).numpy()
+    assert np.array_equal(d_host, d_dev)
+    raw = p.ref.raw_depth.numpy()
+    assert raw.shape == (h, w) and np.all(np.isfinite(raw)) and raw.max() > 0
