@@ -19,12 +19,24 @@ from . import runtime as rt_mod
 
 
 class FrameState:
-    __slots__ = ("id", "img", "depth", "raw_depth")
+    """Device buffers of one frame: image, depths and (for every frame but the first) the flows of the pair
+    (previous frame -> this frame).  `ready` = event recorded after the frame's networks (two-stream mode)."""
+    __slots__ = ("id", "img", "depth", "raw_depth", "fwd", "bwd", "diff", "ready")
+
+    def __init__(self):
+        self.fwd = self.bwd = self.diff = self.ready = None
 
 
 class FramePipeline:
-    def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random):
-        """K = [cx, cy, fx, fy]."""
+    def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
+                 overlap=False):
+        """K = [cx, cy, fx, fy].
+
+        overlap=False: ``step(img)`` returns the pose of ``img`` (one stream, in order).
+        overlap=True : two CUDA streams; ``step(img)`` enqueues the networks of ``img`` and then tracks the
+        PREVIOUS frame while the GPU runs them, returning the previous frame's pose (``None`` on the first
+        call); ``flush()`` tracks the last frame.  Same arithmetic, same RNG order, same poses -- frames only
+        depend on each other through the reference image / depth, which are triple-buffered here."""
         self.cfg = cfg or cfg_mod.default_cfg(height, width)
         self.K = [float(v) for v in K]
         self.H, self.W = height, width
@@ -39,11 +51,22 @@ class FramePipeline:
         self.poses = {}
         self.last = {}
         self._bufs = {}
+        self.overlap = bool(overlap)
+        self.nslots = 3 if self.overlap else 2
+        self.pending = None          # overlap mode: frame whose networks are enqueued but which is not tracked yet
+        self.trk_ref = None          # overlap mode: the tracker's reference frame (self.ref is the networks')
+        if self.overlap:
+            self.s_net = self.rt.new_stream()
+            self.s_trk = self.rt.new_stream(high_priority=True)
 
     # ------------------------------------------------------------------ setup
     def load_weights(self, flow_weights, depth_enc, depth_dec):
         self.eng.build_flow(flow_weights, pairs=1, precision=self.precision)
         self.eng.build_depth(depth_enc, depth_dec, precision=self.precision, dataset=self.cfg.dataset)
+
+    def slot(self, fid):
+        """Buffer slot of frame `fid` (images / depths / flows are multi-buffered so a reference frame stays valid)."""
+        return fid % self.nslots
 
     def _buf(self, name, shape, dtype):
         b = self._bufs.get(name)
@@ -63,8 +86,8 @@ class FramePipeline:
         """Upload + both networks for one new frame; returns its FrameState (device buffers)."""
         st = FrameState()
         st.id = fid
-        # double-buffer images / depths so the previous frame's stay valid as 'ref'
-        slot = fid & 1
+        # multi-buffer images / depths / flows so the previous frame's stay valid as 'ref'
+        slot = self.slot(fid)
         st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
         d = self.eng.depth(self.eng.depth_feed(st.img))                  # LANCZOS resize + ToTensor on the device
         st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
@@ -72,17 +95,27 @@ class FramePipeline:
         c = self.cfg
         self.eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
         if self.ref is not None:
-            self.eng.flow([self.ref.img, st.img])
+            st.fwd, st.bwd, st.diff = self.flow_slot(slot)
+            self.eng.flow([self.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
         return st
 
-    def track(self, cur):
+    def flow_slot(self, slot):
+        """The (fwd, bwd, diff) output buffers of buffer slot `slot`."""
+        e = self.eng
+        return (self._buf("ffwd%d" % slot, e.flow_fwd.shape, np.float32), self._buf("fbwd%d" % slot, e.flow_bwd.shape, np.float32),
+                self._buf("fdif%d" % slot, e.flow_diff.shape, np.float32))
+
+    def track(self, cur, ref=None):
         """dfvo.py:121-262 (hybrid).  Returns the relative pose cur -> ref as a 4x4."""
         c, eng, K = self.cfg, self.eng, self.K
+        ref = ref or self.ref
+        fwd = cur.fwd if cur.fwd is not None else eng.flow_fwd          # (subclasses may leave the flows in the engine's buffers)
+        diff = cur.diff if cur.diff is not None else eng.flow_diff
         b = c.kp_selection.local_bestN
         if b.enable:
-            good, n, kp1_buf, kp2_buf = eng.select_local_bestn(eng.flow_diff, eng.flow_fwd, b.num_row, b.num_col, b.num_bestN, b.thre)
+            good, n, kp1_buf, kp2_buf = eng.select_local_bestn(diff, fwd, b.num_row, b.num_col, b.num_bestN, b.thre)
         else:
-            good, n, kp1_buf, kp2_buf = eng.select_bestn(eng.flow_diff, eng.flow_fwd, c.kp_selection.bestN.num_bestN)
+            good, n, kp1_buf, kp2_buf = eng.select_bestn(diff, fwd, c.kp_selection.bestN.num_bestN)
         self.last = dict(good=good, n=n, mode="const")
         if not good:
             return self.motion.copy()                                     # constant motion (dfvo.py:157-161)
@@ -105,7 +138,7 @@ class FramePipeline:
         self.last["scale"] = scale
         # ---- PnP fallback (dfvo.py:225-250)
         if np.linalg.norm(E_pose[:3, 3]) == 0 or scale == -1:
-            hybrid = self.pnp(kp_ref, kp_cur, kp1_buf, n)
+            hybrid = self.pnp(kp_ref, kp_cur, kp1_buf, n, ref)
             self.last["mode"] = "PnP"
         return hybrid
 
@@ -124,15 +157,16 @@ class FramePipeline:
             return hostmath.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
         return -1
 
-    def pnp(self, kp_ref, kp_cur, kp_ref_buf, n):
+    def pnp(self, kp_ref, kp_cur, kp_ref_buf, n, ref=None):
         """pnp_tracker.py:45-125 -- host cv2.solvePnPRansac (the one SURVEY 8(a) row not yet on the device);
         the reference depth at the keypoints is gathered on the device."""
         import cv2
         c = self.cfg
         cx, cy, fx, fy = self.K
         Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+        ref = ref or self.ref
         dk = self._buf("dkp", (n,), np.float32)
-        self.rt.lib.check(self.rt.lib.dfvo_gather_depth(self.ref.depth.ptr, self.H, self.W, kp_ref_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
+        self.rt.lib.check(self.rt.lib.dfvo_gather_depth(ref.depth.ptr, self.H, self.W, kp_ref_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
         d_all = dk.numpy().astype(np.float64)
         keep = (kp_cur[:, 0] >= 0) & (kp_cur[:, 0] < self.W) & (kp_cur[:, 1] >= 0) & (kp_cur[:, 1] < self.H)
         kp1, kp2, d = kp_ref[keep], kp_cur[keep], d_all[keep]
@@ -157,20 +191,49 @@ class FramePipeline:
         return np.linalg.inv(pose)
 
     # ------------------------------------------------------------------ driver step
-    def step(self, img):
-        """One VO frame: returns the global pose (4x4) after this frame (dfvo.py:358-403 loop body)."""
-        fid = self.stage
-        cur = self.infer(img, fid)
-        if self.stage == 0:
+    def _advance(self, cur, ref):
+        """Track `cur` against `ref` and chain the global pose (dfvo.py:358-403 loop body)."""
+        fid = cur.id
+        if ref is None:
             self.global_pose = np.eye(4)
             self.motion = np.eye(4)
         else:
-            rel = self.track(cur)
+            rel = self.track(cur, ref)
             self.motion = rel.copy()
             # update_global_pose (dfvo.py:109-119): t_w += R_w t ; R_w = R_w R
             self.global_pose[:3, 3:] = self.global_pose[:3, :3] @ rel[:3, 3:] + self.global_pose[:3, 3:]
             self.global_pose[:3, :3] = self.global_pose[:3, :3] @ rel[:3, :3]
         self.poses[fid] = self.global_pose.copy()
-        self.ref = cur
-        self.stage += 1
         return self.poses[fid]
+
+    def step(self, img):
+        """One VO frame.  In-order mode: returns the global pose (4x4) after this frame.  Overlap mode: returns the
+        pose of the previous frame (None on the first call); see __init__."""
+        fid = self.stage
+        self.stage += 1
+        if not self.overlap:
+            cur = self.infer(img, fid)
+            pose = self._advance(cur, self.ref)
+            self.ref = cur
+            return pose
+        with self.rt.on_stream(self.s_net):
+            cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
+            cur.ready = self.rt.record_event()
+        self.ref = cur
+        pose = self._track_pending()
+        self.pending = cur
+        return pose
+
+    def _track_pending(self):
+        if self.pending is None:
+            return None
+        with self.rt.on_stream(self.s_trk):
+            self.rt.wait_event(self.pending.ready)
+            pose = self._advance(self.pending, self.trk_ref)
+        self.trk_ref = self.pending
+        self.pending = None
+        return pose
+
+    def flush(self):
+        """Overlap mode: track the frame whose networks are still in flight; returns its pose (None if none)."""
+        return self._track_pending() if self.overlap else None

@@ -89,6 +89,22 @@ class CudaRuntime:
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
 
+    # ---- streams / events (the two-stream frame pipeline: networks of frame t+1 overlap the tracker of frame t)
+    def new_stream(self, high_priority=False):
+        return self.torch.cuda.Stream(device=self.device, priority=-1 if high_priority else 0)
+
+    def on_stream(self, stream):
+        """Context manager: every launch / copy inside is enqueued on `stream`."""
+        return self.torch.cuda.stream(stream)
+
+    def record_event(self):
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
+    def wait_event(self, ev):
+        self.torch.cuda.current_stream(self.device).wait_event(ev)
+
     def pinned(self, shape, dtype):
         return self.torch.empty(tuple(shape), dtype=_torch_dtype(dtype)).pin_memory()
 

@@ -52,12 +52,14 @@ class Engine:
         self.depth_out = self.rt.empty((self.feed_h, self.feed_w), np.float32)
         self.depth_ready = True
 
-    def flow(self, img_bufs):
-        """img_bufs: 2*pairs uint8 HWC device buffers [ref0, cur0, ...] -> (fwd, bwd, diff) buffers."""
+    def flow(self, img_bufs, out=None):
+        """img_bufs: 2*pairs uint8 HWC device buffers [ref0, cur0, ...] -> (fwd, bwd, diff) buffers
+        (`out` or the engine's own)."""
         assert self.flow_ready, "build_flow first"
         ptrs = [b.ptr.value for b in img_bufs]
-        self.ctx.liteflow_forward(ptrs, self.flow_fwd.ptr, self.flow_bwd.ptr, self.flow_diff.ptr, self.rt.stream_ptr())
-        return self.flow_fwd, self.flow_bwd, self.flow_diff
+        fwd, bwd, diff = out or (self.flow_fwd, self.flow_bwd, self.flow_diff)
+        self.ctx.liteflow_forward(ptrs, fwd.ptr, bwd.ptr, diff.ptr, self.rt.stream_ptr())
+        return fwd, bwd, diff
 
     def depth_feed(self, img_buf, out=None):
         """deep_models.py:195-198 on the device: PIL-exact LANCZOS resize of the uint8 HWC frame to the feed size +

@@ -13,7 +13,7 @@
 //   * persistent CTAs, static round-robin tile schedule, mbarrier full/empty smem ring.
 // Restates torch.nn.Conv2d(stride=1) + LeakyReLU/ELU/ReLU as used at lite_flow_net.py:98-240 and
 // depth_decoder.py / torchvision BasicBlock (BN folded by the weight packer).
-#include "ops.h"
+#include "tc_ptx.cuh"
 
 #ifndef DFVO_HOSTSIM
 #include <cuda.h>
@@ -58,92 +58,6 @@ struct ConvTcK {
 // =============================================================================================
 //                                       device side
 // =============================================================================================
-namespace tc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// wait for outstanding tcgen05.ld; the registers are in/out operands so no use can be hoisted above it
-__device__ __forceinline__ void tc_ld_wait16(uint32_t* v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :: "memory");
-}
-__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// K-major, 128-byte-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-}  // namespace tc
-
 #define TC_THREADS 320
 #define TC_A_BYTES 16384
 
@@ -189,20 +103,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        int t = tile;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int n = t % p.N; const int nb = t / p.N;
-        const int x0 = tx * p.tw, y0 = ty * p.th;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          int kofs = 0;
-          for (int s = 0; s < p.nsrc; ++s) {
-            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
-            for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+    // whole warp walks the loop, one elected lane issues (see tc_ptx.cuh::elect_one)
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int n = t % p.N; const int nb = t / p.N;
+      const int x0 = tx * p.tw, y0 = ty * p.th;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        int kofs = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+          for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (elect_one()) {
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               mbar_expect_tx(full_bar(stage), stage_bytes);
               if (p.stride == 2)
@@ -210,48 +125,56 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
               else
                 tma_load_4d(sa, tm, full_bar(stage), c0, x0 + p.dx[tap], y0 + p.dy[tap], n);
               tma_load_3d(sa + TC_A_BYTES, &tmB, full_bar(stage), kofs + c0, nb * p.block_n, tap);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            kofs += p.srcC[s];
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          kofs += p.srcC[s];
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
-    if (lane == 0) {
-      // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
-        uint32_t accumulate = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          for (int s = 0; s < p.nsrc; ++s) {
-            for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
-              mbar_wait(full_bar(stage), phase);
-              tc_fence_after();
+    // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+      uint32_t fresh = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int s = 0; s < p.nsrc; ++s) {
+          for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (elect_one()) {
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-              const uint64_t adesc = make_desc_sw128(sa);
-              const uint64_t bdesc = make_desc_sw128(sa + TC_A_BYTES);
-              int rem = p.srcC[s] - c0;
+              const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = (((sa + TC_A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+              const int rem = p.srcC[s] - c0;
               const int nks = (rem >= 64 ? 64 : rem) >> 4;       // K=16 steps with real channels
-              for (int ks = 0; ks < nks; ++ks) {
-                // advance 32 B (= 16 bf16) inside the 128-B swizzle atom: +2 in 16-byte units
-                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, accumulate);
-                accumulate = 1;
+              if (nks == 4) {
+                tc_mma_bf16_lohi(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, fresh);
+                tc_mma_bf16_lohi(tmem_d, a_lo + 2u, d_hi, b_lo + 2u, d_hi, idesc, 1u);   // +32 B inside the 128-B swizzle atom
+                tc_mma_bf16_lohi(tmem_d, a_lo + 4u, d_hi, b_lo + 4u, d_hi, idesc, 1u);
+                tc_mma_bf16_lohi(tmem_d, a_lo + 6u, d_hi, b_lo + 6u, d_hi, idesc, 1u);
+              } else {
+                for (int ks = 0; ks < nks; ++ks)
+                  tc_mma_bf16_lohi(tmem_d, a_lo + 2u * ks, d_hi, b_lo + 2u * ks, d_hi, idesc, ks == 0 ? fresh : 1u);
               }
               tc_commit(empty_bar(stage));
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            __syncwarp();
+            fresh = 1u;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        tc_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (elect_one()) tc_commit(tfull_bar(acc));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ===================================== epilogue warps ====================================
@@ -278,82 +201,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
 
+      TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.out = p.out; ep.res = p.res;
       auto process = [&](const uint32_t* v, int col) {
         const int c = cbase + col;
-        if (!(inb && c < p.zero_pad_to)) return;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b = bias4[(c >> 2) + j];
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-        }
-        if (!p.out_f32) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
-          const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
-          const bool full = (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
-                            (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
-          if (full) {
-            if (r) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[2 * j] += __uint_as_float(rw[j] << 16);
-                f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-              }
-            }
-            switch (p.act) {            // one uniform branch per chunk, loops inside
-              case ACT_LEAKY:
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
-                break;
-              case ACT_RELU:
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                break;
-              case ACT_ELU:
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
-                break;
-              case ACT_SIGMOID:
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
-                break;
-              default: break;
-            }
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              w[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else {
-            for (int j = 0; j < 16; ++j) {
-              if (c + j < p.Cout) {
-                float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
-                o[j] = __float2bfloat16_rn(apply_act(val, p.act));
-              } else if (c + j < p.zero_pad_to) {
-                o[j] = __float2bfloat16_rn(0.f);
-              }
-            }
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + opix + c;
-          const float* r = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
-          for (int j = 0; j < 16; ++j) {
-            if (c + j < p.Cout) {
-              float val = f[j] + (r ? r[j] : 0.f);
-              o[j] = apply_act(val, p.act);
-            } else if (c + j < p.zero_pad_to) {
-              o[j] = 0.f;
-            }
-          }
-        }
+        if (inb && c < p.zero_pad_to) tc_epilogue16(ep, v, bias4, c, opix, rpix);
       };
 
       for (int ch = ch_begin; ch < ch_end; ch += 2) {
@@ -401,12 +252,15 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims_, const unsigned long long* strides_, const unsigned* box_) {
+  cuuint64_t dims[5], str[5];
+  cuuint32_t box[5];
+  for (int i = 0; i < rank; ++i) { dims[i] = dims_[i]; box[i] = box_[i]; if (i < rank - 1) str[i] = strides_[i]; }
+  CUtensorMap* m = reinterpret_cast<CUtensorMap*>(map);
+  const cuuint64_t* strides_bytes = str;
   PFN_encodeTiled enc = get_encode();
   DFVO_REQUIRE(enc != nullptr, DFVO_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  if (rank == 5 && dims[0] > 0) { /* last row of the last image: the odd pixel's view must stay inside the allocation */ }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -423,6 +277,19 @@ struct ConvTcPlanImpl {
 };
 
 static int g_num_sms = 0;
+int tc_num_sms() {
+  if (!g_num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  unsigned long long d[5], st[5]; unsigned b[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i < rank - 1) st[i] = strides_bytes[i]; }
+  return tc_encode_map(m, ptr, rank, d, st, b);
+}
 
 static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   DFVO_REQUIRE(c.nsrc >= 1 && c.nsrc <= 3 && c.ntaps >= 1 && c.ntaps <= 49, DFVO_EINVAL, "conv_tc: nsrc/ntaps");
@@ -474,12 +341,7 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   DFVO_REQUIRE(stages >= 2, DFVO_EINVAL, "conv_tc: tile does not fit in shared memory");
   k.stages = stages;
   pl->smem = fixed + (size_t)stages * stage_bytes;
-  if (!g_num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  pl->grid = k.ntiles < g_num_sms ? k.ntiles : g_num_sms;
+  pl->grid = k.ntiles < tc_num_sms() ? k.ntiles : tc_num_sms();
   // tensor maps
   for (int s = 0; s < 3; ++s) {
     const ConvTcSource& src = c.src[s < c.nsrc ? s : 0];
@@ -540,7 +402,20 @@ void conv_tc_profile_read(double* ms, long long* launches, double* flops) {
   *ms = tot; *launches = (long long)g_prof_events.size(); *flops = g_prof_flops;
 }
 
+bool tc_prof_begin(cudaStream_t s, TcProf* p) {
+  if (!g_prof_on) return false;
+  cudaEventCreate(&p->e0); cudaEventCreate(&p->e1); cudaEventRecord(p->e0, s);
+  return true;
+}
+void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc) {
+  cudaEventRecord(p.e1, s);
+  g_prof_events.push_back({p.e0, p.e1});
+  g_prof_flops += flops;
+  g_prof_desc.push_back(desc);
+}
+
 int conv_tc(const ConvTc& c, cudaStream_t s) {
+  if (conv_halo_supported(c)) return conv_halo(c, s);
   ConvTcPlanImpl pl;
   int rc = build_plan(c, &pl);
   if (rc) return rc;
@@ -550,18 +425,15 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
     attr_set = true;
   }
   ++g_launch_count;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+  TcProf pr;
+  const bool prof = tc_prof_begin(s, &pr);
   k_conv_tc<<<pl.grid, TC_THREADS, pl.smem, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k);
-  if (g_prof_on) {
-    cudaEventRecord(e1, s);
-    g_prof_events.push_back({e0, e1});
-    g_prof_flops += c.flops;
+  if (prof) {
     char d[256];
-    snprintf(d, sizeof(d), "N%d %dx%d s%d taps%d src[%d,%d,%d] cout%d/%d bn%d tile%dx%d stages%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,
+    snprintf(d, sizeof(d), "tap  N%d %dx%d s%d taps%d src[%d,%d,%d] cout%d/%d bn%d tile%dx%d stages%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,
              pl.k.stride, c.ntaps, c.src[0].C, c.nsrc > 1 ? c.src[1].C : 0, c.nsrc > 2 ? c.src[2].C : 0, c.Cout, c.Cout_pad, pl.k.block_n,
              pl.k.tw, pl.k.th, pl.k.stages, pl.grid, pl.k.ntiles, c.flops * 1e-9);
-    g_prof_desc.push_back(d);
+    tc_prof_end(s, pr, c.flops, d);
   }
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;

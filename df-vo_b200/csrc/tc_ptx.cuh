@@ -1,0 +1,215 @@
+// tcgen05 / TMA / mbarrier PTX wrappers and the fused conv epilogue shared by the two tensor-core convolution
+// kernels (conv_tc.cu: per-tap operand loads, stride 1|2;  conv_halo.cu: halo-resident operand, stride 1).
+#pragma once
+#include "ops.h"
+
+namespace dfvo {
+
+// what the epilogue needs to turn 16 accumulator columns of one output pixel into stored channels
+struct TcEpi {
+  int Cout, zero_pad_to, act, out_f32;
+  void* out;
+  const void* res;
+};
+
+#ifndef DFVO_HOSTSIM
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MMA with the two 64-bit shared-memory descriptors given as (lo, hi) words: the hi words (SBO / version / swizzle) are
+// loop invariants, only the 14-bit start-address field in lo changes between issues
+__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one elected lane of a fully active warp (cute::elect_one_sync): ptxas keeps tcgen05 / TMA issues under this
+// predicate on the uniform datapath without the per-instruction ELECT loop it emits under `if (lane == 0)`
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+// wait for outstanding tcgen05.ld; the registers are in/out operands so no use can be hoisted above it
+__device__ __forceinline__ void tc_ld_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+}  // namespace tc
+
+// bias + optional residual + activation + store of 16 consecutive output channels [c, c+16) of one pixel.
+// v = 16 fp32 accumulator words (tcgen05.ld), bias4 = shared-memory bias, opix/rpix = element offsets of the pixel.
+__device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v, const float4* bias4, int c, long long opix, long long rpix) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b = bias4[(c >> 2) + j];
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+  }
+  if (!p.out_f32) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
+    const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
+    const bool full = (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
+                      (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
+    if (full) {
+      if (r) {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] += __uint_as_float(rw[j] << 16);
+          f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+        }
+      }
+      switch (p.act) {            // one uniform branch per chunk, loops inside
+        case ACT_LEAKY:
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+          break;
+        case ACT_RELU:
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          break;
+        case ACT_ELU:
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+          break;
+        case ACT_SIGMOID:
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+          break;
+        default: break;
+      }
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      for (int j = 0; j < 16; ++j) {
+        if (c + j < p.Cout) {
+          float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
+          o[j] = __float2bfloat16_rn(apply_act(val, p.act));
+        } else if (c + j < p.zero_pad_to) {
+          o[j] = __float2bfloat16_rn(0.f);
+        }
+      }
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + opix + c;
+    const float* r = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
+    for (int j = 0; j < 16; ++j) {
+      if (c + j < p.Cout) {
+        float val = f[j] + (r ? r[j] : 0.f);
+        o[j] = apply_act(val, p.act);
+      } else if (c + j < p.zero_pad_to) {
+        o[j] = 0.f;
+      }
+    }
+  }
+}
+#endif  // !DFVO_HOSTSIM
+
+// internal: the halo-resident kernel (conv_halo.cu); conv_tc() dispatches to it for stride-1 rectangular tap sets
+int conv_halo(const ConvTc& c, cudaStream_t s);
+bool conv_halo_supported(const ConvTc& c);
+// per-launch CUDA-event timing shared by both kernels (bench.py roofline; DFVO_TC_TRACE=1 prints every launch)
+struct TcProf { cudaEvent_t e0, e1; };
+bool tc_prof_begin(cudaStream_t s, TcProf* p);                       // false (and no events) when profiling is off
+void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc);
+int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                  const unsigned* box);                              // bf16, SWIZZLE_128B, zero OOB fill
+int tc_num_sms();
+
+}  // namespace dfvo

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "rc=$? ($name)"; tail -n 3 gpurun_out/$name.log | cut -c1-300; }
+run ncu_halo ncu --set full --import-source on --clock-control none -k regex:k_conv_halo --launch-skip 410 --launch-count 17 -f -o gpurun_out/prof_halo_L2 python scripts/trace_tc.py

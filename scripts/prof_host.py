@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "df-vo_b200"))
 import numpy as np, torch
 import bench
 from b200 import native, pipeline, tracking, runtime as rt_mod
-from oracle import synth
+import synthdata as synth
 rt = rt_mod.CudaRuntime(0); rt_mod.set_runtime(rt)
 K, frames, analytic = bench.make_inputs(0)
 enc, dec = synth.monodepth2_weights(4869, 192, 640)

@@ -37,3 +37,17 @@ class HostsimRuntime:
 
     def sync(self):
         pass
+
+    # streams / events: the emulation is synchronous, so these are no-ops with the CudaRuntime signatures
+    def new_stream(self, high_priority=False):
+        return None
+
+    def on_stream(self, stream):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def record_event(self):
+        return None
+
+    def wait_event(self, ev):
+        pass

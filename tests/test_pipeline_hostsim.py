@@ -5,13 +5,15 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 from oracle import seqdata
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def test_pipeline_matches_reference_driver(hostsim_lib):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_pipeline_matches_reference_driver(hostsim_lib, overlap):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     from runtime import HostsimRuntime
     from b200 import pipeline, runtime as rt_mod
@@ -26,7 +28,7 @@ def test_pipeline_matches_reference_driver(hostsim_lib):
             f = seqdata.frame_inputs(fid, h, w, K, seqdata.MODES[fid % len(seqdata.MODES)])
             st = pipeline.FrameState()
             st.id = fid
-            slot = fid & 1
+            slot = self.slot(fid)
             st.raw_depth = self._buf("raw%d" % slot, (h, w), np.float32)
             st.depth = self._buf("dep%d" % slot, (h, w), np.float32)
             d = self._buf("dsrc", (h, w), np.float32).upload(f["depth"])
@@ -36,14 +38,17 @@ def test_pipeline_matches_reference_driver(hostsim_lib):
                 self.eng.flow_bwd = self.rt.empty((1, 2, h, w), np.float32)
                 self.eng.flow_diff = self.rt.empty((1, h, w), np.float32)
                 self.eng.flow_ready = True
-            self.eng.flow_fwd.upload(f["fwd"][None]); self.eng.flow_bwd.upload(f["bwd"][None]); self.eng.flow_diff.upload(f["diff"][None, :, :, 0])
+            st.fwd, st.bwd, st.diff = self.flow_slot(slot)
+            st.fwd.upload(f["fwd"][None]); st.bwd.upload(f["bwd"][None]); st.diff.upload(f["diff"][None, :, :, 0])
             return st
 
     np.random.seed(4869)
-    p = Injected(K, h, w)
+    p = Injected(K, h, w, overlap=overlap)
     modes = []
+    if overlap:                          # two-stream mode: step(t) returns the pose of frame t-1, flush() the last one
+        assert p.step(None) is None
     for t in range(n):
-        pose = p.step(None)
+        pose = (p.step(None) if t + 1 < n else p.flush()) if overlap else p.step(None)
         modes.append(p.last.get("mode"))
         dR = pose[:3, :3].T @ g["poses"][t][:3, :3]
         ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
@@ -72,7 +77,8 @@ def test_pipeline_real_infer_plumbing(hostsim_lib):
     for f in frames:
         pose = p.step(f)
         assert pose.shape == (4, 4) and np.all(np.isfinite(pose))
-    assert p.eng.flow_ready and np.all(np.isfinite(p.eng.flow_fwd.numpy())) and np.all(np.isfinite(p.eng.flow_diff.numpy()))
+    assert p.eng.flow_ready and np.all(np.isfinite(p.ref.fwd.numpy())) and np.all(np.isfinite(p.ref.diff.numpy()))
+    assert np.abs(p.ref.fwd.numpy()).max() > 0
     # depth of the last frame through the host (PIL) feed == through the device feed
     feed_host = rt.from_host(p.depth_feed_host(frames[1]))
     d_host = p.eng.depth(feed_host, out=rt.empty((p.eng.feed_h, p.eng.feed_w), np.float32)).numpy()
