@@ -121,10 +121,17 @@ class FramePipeline:
             return self.motion.copy()                                     # constant motion (dfvo.py:157-161)
         kp_ref = kp1_buf.numpy()[:n]
         kp_cur = kp2_buf.numpy()[:n]
-        # ---- E-tracker (dfvo.py:165-193)
+        # ---- E-tracker (dfvo.py:165-193).  The homography vote runs on a host worker thread; the pose-dependent device
+        # work of the scale recovery (triangulation, depth gather) is issued before the vote is joined.
         r = tracking.compute_pose_2d2d(eng, kp_ref, kp_cur, K, repeat=c.e_tracker.ransac.repeat,
                                        reproj_thre=c.e_tracker.ransac.reproj_thre, rng=self.rng,
-                                       kp_ref_buf=kp1_buf, kp_cur_buf=kp2_buf)
+                                       kp_ref_buf=kp1_buf, kp_cur_buf=kp2_buf, defer_validity=True)
+        prep = None
+        if np.linalg.norm(r["t"]) != 0:
+            E_spec = np.eye(4)
+            E_spec[:3, :3], E_spec[:3, 3:] = r["R"], r["t"]
+            prep = self.scale_prepare(kp_ref, kp_cur, kp2_buf, np.linalg.inv(E_spec), cur.depth, n)
+        tracking.resolve_validity(r)
         E_pose = np.eye(4)
         E_pose[:3, :3], E_pose[:3, 3:] = r["R"], r["t"]
         hybrid = np.eye(4)
@@ -132,7 +139,7 @@ class FramePipeline:
         scale = None
         self.last.update(valid=r["valid"], inliers=r["inliers"], mode="E")
         if np.linalg.norm(E_pose[:3, 3]) != 0:
-            scale = self.scale_recovery(kp_ref, kp_cur, kp2_buf, np.linalg.inv(E_pose), cur.depth, n)
+            scale = self.scale_finish(prep)
             if scale != -1:
                 hybrid[:3, 3] = E_pose[:3, 3] * scale
         self.last["scale"] = scale
@@ -142,20 +149,28 @@ class FramePipeline:
             self.last["mode"] = "PnP"
         return hybrid
 
-    def scale_recovery(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
-        """E_tracker.py:476-507,571-643: device triangulation + device gather of the CNN depth at the
-        keypoints, host RANSAC (RNG-consuming, ~1 ms)."""
-        c = self.cfg.scale_recovery.ransac
+    def scale_prepare(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
+        """E_tracker.py:476-507,571-616: device triangulation + device gather of the CNN depth at the keypoints ->
+        (depth ratios, number of valid ones).  Consumes no host RNG."""
         cx, cy, fx, fy = self.K
         k1 = self._buf("k1n", (n, 2), np.float64).upload((kp_ref - np.array([cx, cy])) / np.array([fx, fy]))
         k2 = self._buf("k2n", (n, 2), np.float64).upload((kp_cur - np.array([cx, cy])) / np.array([fx, fy]))
         z = self.eng.triangulate_depth(k1, k2, n, T_21)
         dk = self._buf("dkp", (n,), np.float32)
         self.rt.lib.check(self.rt.lib.dfvo_gather_depth(depth_buf.ptr, self.H, self.W, kp_cur_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
-        ratio, nvalid = hostmath.last_writer_depth_ratio_sparse(kp_cur, z, dk.numpy(), self.H, self.W)
+        return hostmath.last_writer_depth_ratio_sparse(kp_cur, z, dk.numpy(), self.H, self.W)
+
+    def scale_finish(self, prep):
+        """E_tracker.py:617-643: the RNG-consuming 1-parameter RANSAC on the host (~0.5 ms)."""
+        c = self.cfg.scale_recovery.ransac
+        ratio, nvalid = prep
         if nvalid > 10:
             return hostmath.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
         return -1
+
+    def scale_recovery(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
+        """E_tracker.py:476-507,571-643 in one call (scale_prepare + scale_finish)."""
+        return self.scale_finish(self.scale_prepare(kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n))
 
     def pnp(self, kp_ref, kp_cur, kp_ref_buf, n, ref=None):
         """pnp_tracker.py:45-125 -- host cv2.solvePnPRansac (the one SURVEY 8(a) row not yet on the device);

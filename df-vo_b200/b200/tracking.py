@@ -177,13 +177,30 @@ class Engine:
 # ---------------------------------------------------------------------------------------------
 # host-level orchestration of the E-tracker (E_tracker.py:154-307, validity.method == 'GRIC')
 # ---------------------------------------------------------------------------------------------
-def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=np.random, kp_ref_buf=None, kp_cur_buf=None):
+_h_pool = None
+
+
+def _homography_gric(kp_cur, kp_ref, n):
+    """E_tracker.py:199-215: cv2.findHomography (RANSAC, 1 px) + GRIC-H.  Runs in a worker thread: OpenCV releases the
+    GIL, so it overlaps the host's waits on the device RANSAC / pose recovery / triangulation."""
+    import cv2
+    H, _ = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
+    return hostmath.calc_gric(hostmath.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
+
+
+def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=np.random, kp_ref_buf=None, kp_cur_buf=None,
+                      defer_validity=False):
     """Same contract as ``EssTracker.compute_pose_2d2d`` with the default GRIC validity check.
     kp_ref/kp_cur: float64 [N,2] host arrays (device copies optional).  The five RANSAC repeats, their
     GRIC-E scores and recoverPose run on the device; cv2.findHomography + GRIC-H (the model-selection
-    counterpart) still run on the host and overlap with the device work.
-    Returns dict(R, t, inliers, valid, cheirality)."""
-    import cv2
+    counterpart) run on a host worker thread concurrently.
+    Returns dict(R, t, inliers, valid, cheirality).
+
+    defer_validity=True: the homography vote is not joined here.  R, t are the pose *as if* the E-model is valid and the
+    caller must call :func:`resolve_validity` (which resets them to identity / zero when GRIC prefers the homography)
+    before using them for a decision -- this lets device work that only depends on the pose (triangulation for the
+    scale) run while the homography is still being estimated.  Results are identical either way."""
+    global _h_pool
     n = kp_ref.shape[0]
     R, t = np.eye(3), np.zeros((3, 1))
     out = dict(R=R, t=t, inliers=np.ones(n, bool), valid=False, cheirality=0)
@@ -195,29 +212,46 @@ def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=
         order = np.arange(0, n, 1)
         rng.shuffle(order)
         perms.append(order)
+    if _h_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _h_pool = ThreadPoolExecutor(max_workers=1)
+    fut = _h_pool.submit(_homography_gric, kp_cur, kp_ref, n)       # homography model (E_tracker.py:199-215)
     rt = engine.rt
     kp_cur_buf = kp_cur_buf or rt.from_host(kp_cur)
     kp_ref_buf = kp_ref_buf or rt.from_host(kp_ref)
     w = engine.essential_launch(kp_cur_buf, kp_ref_buf, n, perms, K, threshold=reproj_thre)
-    # ---- host, concurrently with the device RANSAC: homography model (E_tracker.py:199-215)
-    H, _ = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
-    H_gric = hostmath.calc_gric(hostmath.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
     info = w["info"].numpy()
     gric = w["gric"].numpy()
-    best, best_cnt, num_valid = -1, 0, 0
+    best, best_cnt = -1, 0
     for r in range(repeat):
         if info[r, 0] > best_cnt:                                   # strict '>' keeps the first maximum (:278-281)
             best, best_cnt = r, int(info[r, 0])
-        num_valid += int(H_gric > gric[r])                          # :270,286
-    out["valid"] = num_valid > repeat / 2
-    out["H_gric"], out["E_gric"], out["ransac_info"] = H_gric, gric, info
+    out["E_gric"], out["ransac_info"] = gric, info
     if best >= 0:
         out["inliers"] = w["mask"].numpy()[best].astype(bool)
-    if out["valid"] and best >= 0:
+        # recoverPose before the validity vote is known (a wasted ~30 us of device time when the vote fails)
         Rt, cheir = engine.recover_pose(w, best, kp_cur_buf, kp_ref_buf, n, K)
         out["cheirality"] = cheir
         if cheir > n * 0.1:                                         # :299-300
             out["R"], out["t"] = Rt[:9].reshape(3, 3).copy(), Rt[9:].reshape(3, 1).copy()
+    out["_vote"] = (fut, gric, repeat, best)
+    if not defer_validity:
+        resolve_validity(out)
+    return out
+
+
+def resolve_validity(out):
+    """Join the homography worker and apply the majority vote H_gric > E_gric (E_tracker.py:270,286-290)."""
+    vote = out.pop("_vote", None)
+    if vote is None:
+        return out
+    fut, gric, repeat, best = vote
+    H_gric = fut.result()
+    num_valid = sum(int(H_gric > gric[r]) for r in range(repeat))
+    out["valid"] = num_valid > repeat / 2
+    out["H_gric"] = H_gric
+    if not (out["valid"] and best >= 0):
+        out["R"], out["t"], out["cheirality"] = np.eye(3), np.zeros((3, 1)), 0
     return out
 
 

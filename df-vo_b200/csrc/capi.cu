@@ -1,9 +1,12 @@
 // C-ABI glue (include/dfvo_b200.h).  No torch types, no exceptions across the boundary.
 #include "../../include/dfvo_b200.h"
 
+#include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <new>
+#include <vector>
 
 #include "liteflownet.h"
 #include "monodepth2.h"
@@ -14,11 +17,70 @@ namespace dfvo { const char* last_error(); }
 
 using namespace dfvo;
 
+// ---- CUDA-graph replay of a network forward ------------------------------------------------------------------
+// A forward pass is a fixed sequence of ~100-200 small launches whose arguments depend only on the caller's buffer
+// pointers.  The first call with a given pointer set runs eagerly (lazy module loading, function attributes), the
+// second is stream-captured and instantiated, later ones are one cudaGraphLaunch: the host enqueue cost drops from
+// ~0.5 ms to tens of microseconds and the launch gaps between dependent kernels shrink.  Only on a capturable stream
+// (not the legacy default stream) and never while the per-launch profiler is on.  DFVO_GRAPHS=0 disables.
+#ifndef DFVO_HOSTSIM
+namespace dfvo { extern int g_tc_prof_on; }
+struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+struct GraphCache {
+  std::map<std::vector<uintptr_t>, GraphEntry> m;
+  ~GraphCache() { for (auto& kv : m) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); }
+  void clear() { for (auto& kv : m) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); m.clear(); }
+};
+
+template <typename F>
+static int run_graphed(GraphCache& gc, const std::vector<uintptr_t>& key, cudaStream_t s, F body) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DFVO_GRAPHS"); enabled = !(e && atoi(e) == 0); }
+  if (!enabled || dfvo::g_tc_prof_on || s == nullptr || s == cudaStreamLegacy) return body();
+  auto it = gc.m.find(key);
+  if (it == gc.m.end()) {
+    if (gc.m.size() >= 64) return body();                 // bounded cache: unusual callers stay eager
+    it = gc.m.emplace(key, GraphEntry()).first;
+  }
+  GraphEntry& e = it->second;
+  if (e.exec) {
+    DFVO_CUDA(cudaGraphLaunch(e.exec, s));
+    dfvo::g_launch_count += e.launches;
+    return DFVO_OK;
+  }
+  if (e.seen < 0 || e.seen++ == 0) return body();
+  const long long l0 = dfvo::g_launch_count;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e.seen = -1; return body(); }
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(s, &g);
+  if (rc != DFVO_OK || ce != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    e.seen = -1;                                           // not capturable: stay eager for this pointer set
+    dfvo::g_launch_count = l0;
+    return body();
+  }
+  e.launches = dfvo::g_launch_count - l0;
+  const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ie != cudaSuccess) { cudaGetLastError(); e.exec = nullptr; e.seen = -1; dfvo::g_launch_count = l0; return body(); }
+  DFVO_CUDA(cudaGraphLaunch(e.exec, s));
+  return DFVO_OK;
+}
+
+#else   // CPU test build: no graphs, every forward runs eagerly
+struct GraphCache { void clear() {} };
+template <typename F>
+static int run_graphed(GraphCache&, const std::vector<uintptr_t>&, cudaStream_t, F body) { return body(); }
+#endif
+
 struct dfvo_ctx {
   int device = 0;
   WeightStore weights[2];
   LiteFlowNetBase* lfn = nullptr;
   Monodepth2Base* mono = nullptr;
+  GraphCache flow_graphs, depth_graphs;
 };
 
 #define API_BEGIN try {
@@ -159,6 +221,7 @@ int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int pre
   DFVO_CUDA(cudaSetDevice(ctx->device));
   delete ctx->lfn;
   ctx->lfn = nullptr;
+  ctx->flow_graphs.clear();
   return liteflownet_create(ctx->weights[DFVO_NET_LITEFLOWNET], height, width, pairs, precision, &ctx->lfn);
   API_END
 }
@@ -167,7 +230,15 @@ int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs, float* flow
                           void* stream) {
   API_BEGIN
   DFVO_REQUIRE(ctx && ctx->lfn && imgs, DFVO_ESTATE, "dfvo_liteflow_forward: call dfvo_liteflow_build first");
-  return ctx->lfn->run(imgs, flow_fwd, flow_bwd, flow_diff, (cudaStream_t)stream);
+  int th, tw, B;
+  ctx->lfn->geometry(&th, &tw, &B);
+  std::vector<uintptr_t> key;
+  for (int b = 0; b < B; ++b) key.push_back((uintptr_t)imgs[b]);
+  key.push_back((uintptr_t)flow_fwd); key.push_back((uintptr_t)flow_bwd); key.push_back((uintptr_t)flow_diff);
+  // the image pointer array is read while the launches are recorded, so capture by value
+  std::vector<const uint8_t*> im(imgs, imgs + B);
+  return run_graphed(ctx->flow_graphs, key, (cudaStream_t)stream,
+                     [&]() { return ctx->lfn->run(im.data(), flow_fwd, flow_bwd, flow_diff, (cudaStream_t)stream); });
   API_END
 }
 
@@ -238,6 +309,7 @@ int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, 
   DFVO_CUDA(cudaSetDevice(ctx->device));
   delete ctx->mono;
   ctx->mono = nullptr;
+  ctx->depth_graphs.clear();
   return monodepth2_create(ctx->weights[DFVO_NET_MONODEPTH2], feed_h, feed_w, precision, min_depth, max_depth, baseline, &ctx->mono);
   API_END
 }
@@ -245,7 +317,8 @@ int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, 
 int dfvo_monodepth2_forward(dfvo_ctx* ctx, const float* img, float* depth_out, void* stream) {
   API_BEGIN
   DFVO_REQUIRE(ctx && ctx->mono && img && depth_out, DFVO_ESTATE, "dfvo_monodepth2_forward: call dfvo_monodepth2_build first");
-  return ctx->mono->run(img, depth_out, (cudaStream_t)stream);
+  std::vector<uintptr_t> key = {(uintptr_t)img, (uintptr_t)depth_out};
+  return run_graphed(ctx->depth_graphs, key, (cudaStream_t)stream, [&]() { return ctx->mono->run(img, depth_out, (cudaStream_t)stream); });
   API_END
 }
 

@@ -374,13 +374,13 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
 }
 
 long long g_launch_count = 0;
-static int g_prof_on = 0;
+int g_tc_prof_on = 0;
 static double g_prof_flops = 0.0;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static std::vector<std::string> g_prof_desc;      // per-launch layer description (DFVO_TC_TRACE=1 prints them with their times)
 
 void conv_tc_profile_enable(int on) {
-  g_prof_on = on;
+  g_tc_prof_on = on;
   if (on) {
     for (auto& e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     g_prof_events.clear();
@@ -403,7 +403,7 @@ void conv_tc_profile_read(double* ms, long long* launches, double* flops) {
 }
 
 bool tc_prof_begin(cudaStream_t s, TcProf* p) {
-  if (!g_prof_on) return false;
+  if (!g_tc_prof_on) return false;
   cudaEventCreate(&p->e0); cudaEventCreate(&p->e1); cudaEventRecord(p->e0, s);
   return true;
 }
