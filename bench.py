@@ -45,8 +45,8 @@ N_DISTINCT = 8                     # distinct synthetic frames cycled through th
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU baseline sample")
     return ap.parse_args()
@@ -213,38 +213,42 @@ def run_b200(args):
     pinned = [torch.from_numpy(f).pin_memory() for f in frames]
     state = dict(resident=True, i=0, h2d=0, d2h=0)
 
-    def inject(slot, st):
+    def inject(pipe, slot, st):
         # analytic flow / depth over the (random-weight) network outputs: D2D, inside the timed region
         if st.fwd is not None:
             st.fwd.t.copy_(d_fwd[slot].t); st.bwd.t.copy_(d_bwd[slot].t); st.diff.t.copy_(d_diff[slot].t)
-        tmp = pipe._buf("dsrc", (H, W), np.float32)
-        tmp.t.copy_(d_depth[slot].t)
-        pipe.eng.depth_post(tmp, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
+        with pipe.depth_stream():                       # ordered after the depth network's own post-processing
+            tmp = pipe._buf("dsrc", (H, W), np.float32)
+            tmp.t.copy_(d_depth[slot].t)
+            pipe.eng.depth_post(tmp, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
 
-    def infer(img, fid):
-        slot = fid % N_DISTINCT
-        st = pipeline.FrameState()
-        st.id = fid
-        s2 = pipe.slot(fid)
-        if state["resident"]:
-            st.img = d_frames[slot]
-            feed = pipe.eng.depth_feed(st.img)
-        else:
-            st.img = pipe._buf("img%d" % s2, (H, W, 3), np.uint8)
-            st.img.t.copy_(pinned[slot], non_blocking=True)                       # H2D from pinned memory
-            feed = pipe.eng.depth_feed(st.img)                                     # PIL-exact LANCZOS + ToTensor on the device
-            state["h2d"] += frames[slot].nbytes
-        d = pipe.eng.depth(feed)
-        st.raw_depth = pipe._buf("raw%d" % s2, (H, W), np.float32)
-        st.depth = pipe._buf("dep%d" % s2, (H, W), np.float32)
-        pipe.eng.depth_post(d, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
-        if pipe.ref is not None:
-            st.fwd, st.bwd, st.diff = pipe.flow_slot(s2)
-            pipe.eng.flow([pipe.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
-        inject(slot, st)
-        return st
+    def make_infer(pipe):
+        def infer(img, fid):
+            slot = fid % N_DISTINCT
+            st = pipeline.FrameState()
+            st.id = fid
+            s2 = pipe.slot(fid)
+            if state["resident"]:
+                st.img = d_frames[slot]
+                feed = pipe.eng.depth_feed(st.img)
+            else:
+                st.img = pipe._buf("img%d" % s2, (H, W, 3), np.uint8)
+                st.img.t.copy_(pinned[slot], non_blocking=True)                       # H2D from pinned memory
+                feed = pipe.eng.depth_feed(st.img)                                     # PIL-exact LANCZOS + ToTensor on the device
+                state["h2d"] += frames[slot].nbytes
+            st.raw_depth = pipe._buf("raw%d" % s2, (H, W), np.float32)
+            st.depth = pipe._buf("dep%d" % s2, (H, W), np.float32)
+            with pipe.depth_stream():                       # monodepth2 on its side stream (overlap mode), as FramePipeline.infer does
+                d = pipe.eng.depth(feed)
+                pipe.eng.depth_post(d, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
+            if pipe.ref is not None:
+                st.fwd, st.bwd, st.diff = pipe.flow_slot(s2)
+                pipe.eng.flow([pipe.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
+            inject(pipe, slot, st)
+            return st
+        return infer
 
-    pipe.infer = infer
+    pipe.infer = make_infer(pipe)
     # count the bytes the host side moves per step
     up0, dn0 = rt_mod.Buf.upload, rt_mod.Buf.numpy
 
@@ -296,12 +300,21 @@ def run_b200(args):
     ms_e2e, _ = timed(args.steps, False)
     h2d, d2h = state["h2d"] / args.steps, state["d2h"] / args.steps
 
-    # ---- roofline of the dominant kernel (tcgen05 conv): CUDA-event timing of every launch over a few steps
-    lib.dfvo_profile_enable(1)
+    # ---- roofline of the dominant kernels (tcgen05 convs): CUDA-event timing of every launch over a few steps, on an
+    # in-order single-stream pipeline sharing the built networks (in the two-stream pipeline the tracker's and the depth
+    # network's kernels run beside the convolutions, which would be charged to whichever launch they overlap)
+    pipe.flush()
+    torch.cuda.synchronize()
+    prof = pipeline.FramePipeline(K, H, W, precision=native.PREC_BF16, runtime=rt, overlap=False, engine=pipe.eng)
+    prof.infer = make_infer(prof)
     state["resident"] = True
+    prof.step(None)
+    prof.step(None)
+    torch.cuda.synchronize()
+    lib.dfvo_profile_enable(1)
     prof_steps = 5
     for _ in range(prof_steps):
-        pipe.step(None)
+        prof.step(None)
     torch.cuda.synchronize()
     import ctypes
     tc_ms, tc_n, tc_fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()

@@ -14,6 +14,17 @@ import math
 import numpy as np
 
 
+def rodrigues(rvec):
+    """cv2.Rodrigues(rvec)[0]: rotation vector -> matrix."""
+    r = np.asarray(rvec, np.float64).reshape(3)
+    th = float(np.linalg.norm(r))
+    if th < 2.220446049250313e-16:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return math.cos(th) * np.eye(3) + (1 - math.cos(th)) * np.outer(k, k) + math.sin(th) * Kx
+
+
 # ---------------------------------------------------------------------------------------------
 # GRIC (gric.py)
 # ---------------------------------------------------------------------------------------------

@@ -27,9 +27,27 @@ class FrameState:
         self.fwd = self.bwd = self.diff = self.ready = None
 
 
+class _ForkJoin:
+    """`with` block whose launches go to `side`, ordered after everything already on the current stream; the join event
+    is left in ``owner._depth_done`` for the step to wait on."""
+
+    def __init__(self, rt, side, owner):
+        self.rt, self.side, self.owner = rt, side, owner
+
+    def __enter__(self):
+        fork = self.rt.record_event()
+        self.ctx = self.rt.on_stream(self.side)
+        self.ctx.__enter__()
+        self.rt.wait_event(fork)
+
+    def __exit__(self, *a):
+        self.owner._depth_done = self.rt.record_event()
+        return self.ctx.__exit__(*a)
+
+
 class FramePipeline:
     def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
-                 overlap=False):
+                 overlap=False, engine=None):
         """K = [cx, cy, fx, fy].
 
         overlap=False: ``step(img)`` returns the pose of ``img`` (one stream, in order).
@@ -41,7 +59,7 @@ class FramePipeline:
         self.K = [float(v) for v in K]
         self.H, self.W = height, width
         self.rt = runtime or rt_mod.get()
-        self.eng = tracking.Engine(height, width, self.rt)
+        self.eng = engine or tracking.Engine(height, width, self.rt)      # `engine`: share built networks with another pipeline
         self.precision = precision
         self.rng = rng
         self.ref = None
@@ -56,8 +74,9 @@ class FramePipeline:
         self.pending = None          # overlap mode: frame whose networks are enqueued but which is not tracked yet
         self.trk_ref = None          # overlap mode: the tracker's reference frame (self.ref is the networks')
         if self.overlap:
-            self.s_net = self.rt.new_stream()
-            self.s_trk = self.rt.new_stream(high_priority=True)
+            self.s_net = self.rt.new_stream()                      # LiteFlowNet
+            self.s_depth = self.rt.new_stream()                    # monodepth2: independent of the flow network, its small
+            self.s_trk = self.rt.new_stream(high_priority=True)    # launches fill the SMs LiteFlowNet's coarse levels leave idle
 
     # ------------------------------------------------------------------ setup
     def load_weights(self, flow_weights, depth_enc, depth_dec):
@@ -89,15 +108,25 @@ class FramePipeline:
         # multi-buffer images / depths / flows so the previous frame's stay valid as 'ref'
         slot = self.slot(fid)
         st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
-        d = self.eng.depth(self.eng.depth_feed(st.img))                  # LANCZOS resize + ToTensor on the device
         st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
         st.depth = self._buf("dep%d" % slot, (self.H, self.W), np.float32)
-        c = self.cfg
-        self.eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
+        with self.depth_stream():
+            d = self.eng.depth(self.eng.depth_feed(st.img))              # LANCZOS resize + ToTensor on the device
+            c = self.cfg
+            self.eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
         if self.ref is not None:
             st.fwd, st.bwd, st.diff = self.flow_slot(slot)
             self.eng.flow([self.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
         return st
+
+    def depth_stream(self):
+        """Context for the depth network of the frame being inferred: in overlap mode a side stream forked from the
+        network stream (after the image upload) and joined back into it by ``step`` -- monodepth2 and LiteFlowNet share
+        only the input image; in-order mode: the current stream."""
+        import contextlib
+        if not self.overlap:
+            return contextlib.nullcontext()
+        return _ForkJoin(self.rt, self.s_depth, self)
 
     def flow_slot(self, slot):
         """The (fwd, bwd, diff) output buffers of buffer slot `slot`."""
@@ -173,12 +202,9 @@ class FramePipeline:
         return self.scale_finish(self.scale_prepare(kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n))
 
     def pnp(self, kp_ref, kp_cur, kp_ref_buf, n, ref=None):
-        """pnp_tracker.py:45-125 -- host cv2.solvePnPRansac (the one SURVEY 8(a) row not yet on the device);
-        the reference depth at the keypoints is gathered on the device."""
-        import cv2
+        """pnp_tracker.py:45-125: keypoint filtering on the host arrays the tracker already holds, the reference depth
+        at the keypoints gathered on the device, the five solvePnPRansac repeats + refits on the device (csrc/pnp.cu)."""
         c = self.cfg
-        cx, cy, fx, fy = self.K
-        Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
         ref = ref or self.ref
         dk = self._buf("dkp", (n,), np.float32)
         self.rt.lib.check(self.rt.lib.dfvo_gather_depth(ref.depth.ptr, self.H, self.W, kp_ref_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
@@ -187,23 +213,10 @@ class FramePipeline:
         kp1, kp2, d = kp_ref[keep], kp_cur[keep], d_all[keep]
         keep = (d != 0) & (d < c.depth.max_depth) & (d > c.depth.min_depth)
         kp1, kp2, d = kp1[keep], kp2[keep], d[keep]
-        XYZ = (np.linalg.inv(Kmat) @ np.concatenate([kp1, np.ones((kp1.shape[0], 1))], 1).T).T * d[:, None]
-        best_rt, best_inl = [], 0
-        for _ in range(c.pnp_tracker.ransac.repeat):
-            order = np.arange(0, kp2.shape[0], 1)
-            self.rng.shuffle(order)
-            nX, n2 = XYZ.copy()[order], kp2.copy()[order]
-            if n2.shape[0] > 4:
-                flag, r, t, inl = cv2.solvePnPRansac(objectPoints=nX, imagePoints=n2, cameraMatrix=Kmat, distCoeffs=None,
-                                                     iterationsCount=c.pnp_tracker.ransac.iter,
-                                                     reprojectionError=c.pnp_tracker.ransac.reproj_thre)
-                if flag and inl.shape[0] > best_inl:
-                    best_rt, best_inl = [r, t], inl.shape[0]
-        pose = np.eye(4)
-        if len(best_rt) != 0:
-            pose[:3, :3] = cv2.Rodrigues(best_rt[0])[0]
-            pose[:3, 3:] = best_rt[1]
-        return np.linalg.inv(pose)
+        pose, _ = tracking.compute_pose_3d2d(self.eng, kp1, kp2, d, self.K, repeat=c.pnp_tracker.ransac.repeat,
+                                             iters=c.pnp_tracker.ransac.iter, reproj_thre=c.pnp_tracker.ransac.reproj_thre,
+                                             rng=self.rng)
+        return pose
 
     # ------------------------------------------------------------------ driver step
     def _advance(self, cur, ref):
@@ -232,7 +245,10 @@ class FramePipeline:
             self.ref = cur
             return pose
         with self.rt.on_stream(self.s_net):
+            self._depth_done = None
             cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
+            if self._depth_done is not None:                # join the depth side stream
+                self.rt.wait_event(self._depth_done)
             cur.ready = self.rt.record_event()
         self.ref = cur
         pose = self._track_pending()

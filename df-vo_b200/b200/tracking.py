@@ -165,6 +165,27 @@ class Engine:
                                                   w["pmask"].ptr, w["pinfo"].ptr, self.rt.stream_ptr()))
         return w["Rt"].numpy(), int(w["pinfo"].numpy()[0])
 
+    def pnp_ransac(self, XYZ, kp2, perms, K, iters=100, reproj_thre=1.0, prob=0.99):
+        """len(perms) repeats of cv2.solvePnPRansac(XYZ[perm], kp2[perm], K, None, iterationsCount=iters,
+        reprojectionError=reproj_thre) on the device (pnp_tracker.py:86-112; csrc/pnp.cu).  XYZ [n,3], kp2 [n,2] float64
+        host arrays.  Returns (rt [R,6] = rvec|tvec, info [R,4] = found, inliers, iterations, winning iteration)."""
+        cx, cy, fx, fy = K
+        n, R = XYZ.shape[0], len(perms)
+        key = (n, R, iters)
+        if not hasattr(self, "_pnp_ws"):
+            self._pnp_ws = {}
+        if key not in self._pnp_ws:
+            nb = int(self.lib.dfvo_pnp_workspace_bytes(n, R, iters))
+            self._pnp_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), obj=self.rt.empty((n, 3), np.float64),
+                                     img=self.rt.empty((n, 2), np.float64), perm=self.rt.empty((R, n), np.int32),
+                                     rt=self.rt.empty((R, 6), np.float64), info=self.rt.empty((R, 4), np.int32))
+        w = self._pnp_ws[key]
+        w["obj"].upload(XYZ); w["img"].upload(kp2); w["perm"].upload(np.asarray(perms, np.int32))
+        self.lib.check(self.lib.dfvo_pnp_ransac(w["obj"].ptr, w["img"].ptr, n, w["perm"].ptr, R, self._subset_table(n, iters).ptr,
+                                                iters, fx, fy, cx, cy, float(reproj_thre), prob, w["ws"].ptr, w["ws"].shape[0],
+                                                w["rt"].ptr, w["info"].ptr, self.rt.stream_ptr()))
+        return w["rt"].numpy(), w["info"].numpy()
+
     def triangulate_depth(self, kp1n_buf, kp2n_buf, n, T21):
         if not hasattr(self, "_tri") or self._tri["z"].shape[0] < n:
             self._tri = dict(z=self.rt.empty((max(n, 2048),), np.float64), T=self.rt.empty((12,), np.float64))
@@ -253,6 +274,35 @@ def resolve_validity(out):
     if not (out["valid"] and best >= 0):
         out["R"], out["t"], out["cheirality"] = np.eye(3), np.zeros((3, 1)), 0
     return out
+
+
+def compute_pose_3d2d(engine, kp1, kp2, d, K, repeat=5, iters=100, reproj_thre=1.0, rng=np.random):
+    """The solver part of ``PnpTracker.compute_pose_3d2d`` (pnp_tracker.py:80-118) for keypoints already filtered by the
+    caller: kp1 [n,2] reference pixels with depths d [n], kp2 [n,2] current pixels.  Unprojection (ops_3d.py:70-94),
+    one host shuffle per repeat (same RNG consumption as the reference), the RANSACs + refits on the device, best
+    repeat by inlier count (strict '>', first maximum).  Returns the 4x4 pose current -> reference (the inverse of
+    solvePnP's, pnp_tracker.py:113-118) and the winning inlier count."""
+    cx, cy, fx, fy = K
+    n = kp1.shape[0]
+    Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    XYZ = (np.linalg.inv(Kmat) @ np.concatenate([kp1, np.ones((n, 1))], 1).T).T * np.asarray(d, np.float64)[:, None]
+    perms = []
+    for _ in range(repeat):
+        order = np.arange(0, n, 1)
+        rng.shuffle(order)
+        perms.append(order)
+    pose = np.eye(4)
+    best_inl = 0
+    if n > 4:                                                       # pnp_tracker.py:97
+        rt, info = engine.pnp_ransac(XYZ, np.ascontiguousarray(kp2, np.float64), perms, K, iters, reproj_thre)
+        best = -1
+        for r in range(repeat):
+            if info[r, 0] and info[r, 1] > best_inl:
+                best, best_inl = r, int(info[r, 1])
+        if best >= 0:
+            pose[:3, :3] = hostmath.rodrigues(rt[best, :3])
+            pose[:3, 3] = rt[best, 3:]
+    return np.linalg.inv(pose), best_inl
 
 
 def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1,

@@ -230,15 +230,14 @@ int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs, float* flow
                           void* stream) {
   API_BEGIN
   DFVO_REQUIRE(ctx && ctx->lfn && imgs, DFVO_ESTATE, "dfvo_liteflow_forward: call dfvo_liteflow_build first");
-  int th, tw, B;
-  ctx->lfn->geometry(&th, &tw, &B);
-  std::vector<uintptr_t> key;
-  for (int b = 0; b < B; ++b) key.push_back((uintptr_t)imgs[b]);
-  key.push_back((uintptr_t)flow_fwd); key.push_back((uintptr_t)flow_bwd); key.push_back((uintptr_t)flow_diff);
-  // the image pointer array is read while the launches are recorded, so capture by value
-  std::vector<const uint8_t*> im(imgs, imgs + B);
-  return run_graphed(ctx->flow_graphs, key, (cudaStream_t)stream,
-                     [&]() { return ctx->lfn->run(im.data(), flow_fwd, flow_bwd, flow_diff, (cudaStream_t)stream); });
+  // only the body -- the part that touches nothing but the runner's own buffers -- is replayed as a graph, so there is
+  // one graph per network no matter which frame / output buffers the caller cycles through
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ctx->lfn->ingest(imgs, st);
+  if (rc) return rc;
+  rc = run_graphed(ctx->flow_graphs, std::vector<uintptr_t>(), st, [&]() { return ctx->lfn->body(st); });
+  if (rc) return rc;
+  return ctx->lfn->emit(flow_fwd, flow_bwd, flow_diff, st);
   API_END
 }
 
@@ -433,6 +432,18 @@ int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N
   API_BEGIN
   DFVO_REQUIRE(E && p1 && p2 && Rt_out && mask_out && info && N > 0, DFVO_EINVAL, "dfvo_recover_pose args");
   return recover_pose(E, p1, p2, N, focal, cx, cy, Rt_out, mask_out, info, (cudaStream_t)stream);
+  API_END
+}
+
+size_t dfvo_pnp_workspace_bytes(int N, int R, int iters) { return pnp_workspace_bytes(N, R, iters); }
+
+int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm, int R, const int32_t* subsets, int iters,
+                    double fx, double fy, double cx, double cy, double threshold, double prob, void* workspace,
+                    size_t workspace_bytes, double* rt_out, int32_t* info, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(workspace != nullptr, DFVO_EINVAL, "dfvo_pnp_ransac: null workspace");
+  return pnp_ransac(obj, img, N, perm, R, subsets, iters, fx, fy, cx, cy, threshold, prob, workspace, workspace_bytes, rt_out, info,
+                    (cudaStream_t)stream);
   API_END
 }
 

@@ -70,9 +70,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.Cout_pad; i += HALO_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  pdl_trigger();
+  for (int i = threadIdx.x; i < p.Cout_pad; i += HALO_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;     // constant weights
 
   if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmB);
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
@@ -87,6 +89,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ntaps = p.kh * p.kw;
+  pdl_wait();                                  // from here on: activations of the previous kernel / our output buffers
 
   if (warp == 0) {
     // ===================================== A producer: one halo box per (tile, source, 64-channel chunk)
@@ -419,9 +422,11 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
   ++g_launch_count;
   TcProf pr;
   const bool prof = tc_prof_begin(s, &pr);
-  if (k.S == 1) k_conv_halo<1><<<grid, HALO_THREADS, h.smem, s>>>(tmA[0], tmA[1], tmA[2], tmB, k);
-  else if (k.S == 2) k_conv_halo<2><<<grid, HALO_THREADS, h.smem, s>>>(tmA[0], tmA[1], tmA[2], tmB, k);
-  else k_conv_halo<4><<<grid, HALO_THREADS, h.smem, s>>>(tmA[0], tmA[1], tmA[2], tmB, k);
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
+  tc_launch_config(&cfg, &attr, grid, HALO_THREADS, h.smem, s);
+  if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1>, tmA[0], tmA[1], tmA[2], tmB, k));
+  else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2>, tmA[0], tmA[1], tmA[2], tmB, k));
+  else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4>, tmA[0], tmA[1], tmA[2], tmB, k));
   if (prof) {
     char d[256];
     snprintf(d, sizeof(d), "halo N%d %dx%d k%dx%d src[%d,%d,%d] cout%d/%d bn%d S%d stages%d/%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,

@@ -82,9 +82,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.Cout_pad; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  pdl_trigger();
+  for (int i = threadIdx.x; i < p.Cout_pad; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;     // constant weights
 
   if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -97,6 +99,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                  // from here on: activations of the previous kernel / our output buffers
 
   int chunks_total = 0;
   for (int s = 0; s < p.nsrc; ++s) chunks_total += (p.srcC[s] + 63) >> 6;
@@ -277,6 +280,15 @@ struct ConvTcPlanImpl {
 };
 
 static int g_num_sms = 0;
+void tc_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int block, size_t smem, cudaStream_t s) {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("DFVO_PDL"); pdl = !(e && atoi(e) == 0); }
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = dim3(grid); cfg->blockDim = dim3(block); cfg->dynamicSmemBytes = smem; cfg->stream = s;
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  cfg->attrs = attr; cfg->numAttrs = pdl ? 1 : 0;
+}
 int tc_num_sms() {
   if (!g_num_sms) {
     int dev = 0; cudaGetDevice(&dev);
@@ -427,7 +439,9 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
   ++g_launch_count;
   TcProf pr;
   const bool prof = tc_prof_begin(s, &pr);
-  k_conv_tc<<<pl.grid, TC_THREADS, pl.smem, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k);
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
+  tc_launch_config(&cfg, &attr, pl.grid, TC_THREADS, pl.smem, s);
+  DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc, pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k));
   if (prof) {
     char d[256];
     snprintf(d, sizeof(d), "tap  N%d %dx%d s%d taps%d src[%d,%d,%d] cout%d/%d bn%d tile%dx%d stages%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,

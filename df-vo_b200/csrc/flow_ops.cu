@@ -109,6 +109,34 @@ template int im2row7<float>(Ten<const float>, Ten<float>, cudaStream_t);
 template int im2row7<bf16>(Ten<const float>, Ten<bf16>, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
+// Column-padded 8-channel copy of the 3-channel input for the 7x7 stem: out[n, y, x + 3, 0..2] = img[n, y, x, 0..2],
+// channels 3..7 and the 3 + 5 pad columns of every row stay zero (they are never written; the arena zero-fills).
+// With 16 bytes per pixel, the 64 consecutive elements starting at padded column x are the 8 pixels x-3 .. x+4 of that
+// row -- the horizontal window of the stem -- so a tensor map with a 16-byte pixel stride and a 64-element innermost
+// dimension (overlapping boxes) lets TMA deliver the row-unrolled operand without materialising it.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pad_image8(Ten<const float> img, Ten<T> out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= img.W) return;
+  const float* p = img.at(n, y, x);
+  T* o = out.at(n, y, x + 3);
+  o[0] = from_f<T>(p[0]); o[1] = from_f<T>(p[1]); o[2] = from_f<T>(p[2]);
+}
+
+template <typename T>
+int pad_image8(Ten<const float> img, Ten<T> out, cudaStream_t s) {
+  DFVO_REQUIRE(out.C == 8 && out.H == img.H && out.W == img.W + 8 && out.sW == 8, DFVO_ESHAPE, "pad_image8 shapes");
+  auto k = k_pad_image8<T>;
+  DFVO_LAUNCH(k, dim3(cdiv(img.W, 128), img.H, img.N), dim3(128), 0, s, img, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+template int pad_image8<float>(Ten<const float>, Ten<float>, cudaStream_t);
+template int pad_image8<bf16>(Ten<const float>, Ten<bf16>, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
 // depthwise ConvTranspose2d(k=4, s=2, p=1, groups=C, bias=False)  (lite_flow_net.py:109,117)
 // out[oy] += in[iy] * w[ky] with oy = 2*iy - 1 + ky
 // ---------------------------------------------------------------------------------------------
@@ -386,12 +414,98 @@ k_correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int l
   for (int i = 49; i < out.C; ++i) o[i] = from_f<T>(0.f);
 }
 
+// bf16 fast path (channel count a multiple of 32, 16-byte aligned pixels): 16x4 output pixels x 7 displacement rows per
+// 448-thread block -- thread (pixel, dy) keeps 7 accumulators -- with 128-bit global loads for both operands.  Seven
+// times the threads per pixel of the generic kernel and no scalar loads: the coarse pyramid levels (a dozen blocks) are
+// latency-bound, so the work per thread is what sets their run time.  Same per-displacement summation order as the
+// generic kernel (bit-identical results).
+#define CORRV_TW 16
+#define CORRV_TH 4
+#define CORRV_PW (CORRV_TW + 6)
+#define CORRV_PH (CORRV_TH + 6)
+__global__ void __launch_bounds__(CORRV_TW* CORRV_TH * 7)
+k_correlation49_bf16v(Ten<const bf16> f1, Ten<const bf16> f2, int f2_nxor, int stride, int leaky, Ten<bf16> out) {
+  __shared__ __align__(16) uint32_t patch[CORRV_PH * CORRV_PW * CORR_PITCH];
+  const int p = threadIdx.x % (CORRV_TW * CORRV_TH), dy = threadIdx.x / (CORRV_TW * CORRV_TH);
+  const int tx = p % CORRV_TW, ty = p / CORRV_TW;
+  const int x0 = blockIdx.x * CORRV_TW, y0 = blockIdx.y * CORRV_TH, n = blockIdx.z;
+  const int ox = x0 + tx, oy = y0 + ty;
+  const bool active = ox < out.W && oy < out.H;
+  const int C = f1.C;
+  float acc[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CORRV_PH * CORRV_PW * 4; i += CORRV_TW * CORRV_TH * 7) {
+      const int q = i & 3, pp = i >> 2;
+      const int sy = (y0 + pp / CORRV_PW - 3) * stride, sx = (x0 + pp % CORRV_PW - 3) * stride;
+      uint4 v; v.x = v.y = v.z = v.w = 0u;
+      if (sy >= 0 && sy < f2.H && sx >= 0 && sx < f2.W) v = *reinterpret_cast<const uint4*>(f2.at(n ^ f2_nxor, sy, sx) + c0 + q * 8);
+      *reinterpret_cast<uint4*>(&patch[pp * CORR_PITCH + q * 4]) = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float a[32];
+    {
+      const bf16* src = f1.at(n, oy * stride, ox * stride) + c0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + q * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        corr_unpack8(w, a + q * 8);
+      }
+    }
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const uint32_t* pw = &patch[((ty + dy) * CORRV_PW + tx + dx) * CORR_PITCH];
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(pw + q * 4);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        float b[8];
+        corr_unpack8(wv, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += a[q * 8 + j] * b[j];
+      }
+      acc[dx] += sum;
+    }
+  }
+  if (!active) return;
+  bf16* o = out.at(n, oy, ox) + dy * 7;
+  const float inv = 1.f / (float)C;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    float v = acc[i] * inv;
+    if (leaky) v = v > 0.f ? v : 0.1f * v;
+    o[i] = __float2bfloat16_rn(v);
+  }
+  if (dy == 6) for (int i = 49; i < out.C; ++i) out.at(n, oy, ox)[i] = __float2bfloat16_rn(0.f);
+}
+
+template <typename T> struct CorrFast { static bool launch(Ten<const T>, Ten<const T>, int, int, int, Ten<T>, cudaStream_t) { return false; } };
+template <> struct CorrFast<bf16> {
+  static bool launch(Ten<const bf16> f1, Ten<const bf16> f2, int f2_nxor, int stride, int leaky, Ten<bf16> out, cudaStream_t s) {
+    const bool ok = f1.C % 32 == 0 && ((uintptr_t)f1.p & 15) == 0 && ((uintptr_t)f2.p & 15) == 0 && f1.sW % 8 == 0 && f2.sW % 8 == 0 &&
+                    f1.sH % 8 == 0 && f2.sH % 8 == 0 && f1.sN % 8 == 0 && f2.sN % 8 == 0;
+    if (!ok) return false;
+    dim3 block(CORRV_TW * CORRV_TH * 7), grid(cdiv(out.W, CORRV_TW), cdiv(out.H, CORRV_TH), out.N);
+    DFVO_LAUNCH(k_correlation49_bf16v, grid, block, 0, s, f1, f2, f2_nxor, stride, leaky, out);
+    return true;
+  }
+};
+
 template <typename T>
 int correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out, cudaStream_t s) {
   DFVO_REQUIRE(stride == 1 || stride == 2, DFVO_EINVAL, "correlation stride must be 1 or 2");
   DFVO_REQUIRE(out.H == (f1.H + stride - 1) / stride && out.W == (f1.W + stride - 1) / stride &&
                    out.C >= 49 && f1.C == f2.C && f1.H == f2.H && f1.W == f2.W,
                DFVO_ESHAPE, "correlation shapes");
+  if (CorrFast<T>::launch(f1, f2, f2_nxor, stride, leaky, out, s)) {
+    DFVO_CHECK_LAUNCH();
+    return DFVO_OK;
+  }
   dim3 block(CORR_TW * CORR_TH), grid(cdiv(out.W, CORR_TW), cdiv(out.H, CORR_TH), out.N);
   auto k = k_correlation49<T>;
   DFVO_LAUNCH(k, grid, block, 0, s, f1, f2, f2_nxor, stride, leaky, out);

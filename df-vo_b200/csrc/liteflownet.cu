@@ -12,6 +12,7 @@
 //     >=16 input channels on the tcgen05 kernel, the rest on the CUDA-core kernel.
 #include "liteflownet.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace dfvo {
@@ -60,6 +61,8 @@ struct LfnImpl : public LiteFlowNetBase {
   } lv[7];
   // buffers
   float* img[7];              // [B,h,w,4] fp32 pyramid (img[1] = network input)
+  bool stem_window = false;
+  T* imgpad = nullptr;
   T *f1buf, *rowbuf, *t2a, *t2b, *feat2, *t3a, *t4a;
   T* subcat[7]; int subC[7];
   T *mfeat, *warpbuf, *corr, *corrU, *b128a, *b128b, *b64a, *b64b, *b32a, *b32b, *d0, *d1, *regcat;
@@ -108,19 +111,30 @@ struct LfnImpl : public LiteFlowNetBase {
     // ---------------- weights ----------------
     const std::string F = "moduleFeatures.";
     if (IsBf16<T>::v) {
-      // stem on tensor cores: 7x7x3 -> 7x1 over the row-unrolled 21 (padded 32) channels, w'[co][dx*3+c][ky] = w[co][c][ky][dx]
+      // stem on tensor cores: 7x7x3 -> 7x1 over a horizontal window of pixels.
+      //   window mode (default): K = 64 = 8 pixels x 8 channels read straight from the column-padded image through an
+      //     overlapping-box tensor map (flow_ops.cu::pad_image8), w'[co][px*8+c][ky] = w[co][c][ky][px], px < 7, c < 3;
+      //   row-unroll mode (DFVO_STEM_WINDOW=0): K = 32 over the materialised [.., 7*3 -> 32] buffer (im2row7).
       const HostTensor* w7 = find_weight(ws, F + "moduleOne.0.weight");
       const HostTensor* b7 = find_weight(ws, F + "moduleOne.0.bias");
       DFVO_REQUIRE(w7 && w7->shape.size() == 4 && w7->shape[1] == 3 && w7->shape[2] == 7 && w7->shape[3] == 7, DFVO_ESTATE, "moduleOne weight");
+      const char* env = getenv("DFVO_STEM_WINDOW");
+      stem_window = !(env && atoi(env) == 0);
+      const int kk = stem_window ? 64 : 21, cs = stem_window ? 8 : 3;
       HostTensor wr;
-      wr.shape = {w7->shape[0], 21, 7, 1};
-      wr.data.assign((size_t)w7->shape[0] * 21 * 7, 0.f);
+      wr.shape = {w7->shape[0], kk, 7, 1};
+      wr.data.assign((size_t)w7->shape[0] * kk * 7, 0.f);
       for (int co = 0; co < (int)w7->shape[0]; ++co)
         for (int c = 0; c < 3; ++c)
           for (int ky = 0; ky < 7; ++ky)
             for (int dx = 0; dx < 7; ++dx)
-              wr.data[((size_t)co * 21 + dx * 3 + c) * 7 + ky] = w7->data[(((size_t)co * 3 + c) * 7 + ky) * 7 + dx];
-      TRY(build_conv_layer(arena, wr, b7, {{21, 32}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
+              wr.data[((size_t)co * kk + dx * cs + c) * 7 + ky] = w7->data[(((size_t)co * 3 + c) * 7 + ky) * 7 + dx];
+      if (stem_window) {
+        TRY(build_conv_layer(arena, wr, b7, {{64, 64}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
+        fOne.Cin_ref = 21;                       // algorithmic FLOPs of the layer: 7 x 7 x 3 real taps per output channel
+      } else {
+        TRY(build_conv_layer(arena, wr, b7, {{21, 32}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
+      }
     } else {
       TRY(conv_layer(ws, F + "moduleOne.0", {{3, 3}}, 1, 3, 3, false, &fOne));
     }
@@ -181,7 +195,8 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 1; L <= 6; ++L) { img[L] = arena.alloc_t<float>(px(L) * 4); if (!img[L]) return DFVO_ENOMEM; }
 #define ALLOC(ptr, type, count) do { ptr = arena.alloc_t<type>(count); if (!ptr) return DFVO_ENOMEM; } while (0)
     ALLOC(f1buf, T, px(1) * 32);
-    ALLOC(rowbuf, T, IsBf16<T>::v ? px(1) * 32 : 64);
+    ALLOC(rowbuf, T, (IsBf16<T>::v && !stem_window) ? px(1) * 32 : 64);
+    ALLOC(imgpad, T, (IsBf16<T>::v && stem_window) ? (size_t)B * lh[1] * (lw[1] + 8) * 8 + 64 : 64);
     ALLOC(t2a, T, px(2) * 32); ALLOC(t2b, T, px(2) * 32); ALLOC(feat2, T, px(2) * 32);
     ALLOC(t3a, T, px(3) * 64); ALLOC(t4a, T, px(4) * 96);
     subcat[1] = nullptr; subC[1] = 0;
@@ -219,13 +234,25 @@ struct LfnImpl : public LiteFlowNetBase {
   }
 
   // ------------------------------------------------------------------------------------------
-  int features(const uint8_t* const* imgs_u8, cudaStream_t s) {
+  // the only launches that read caller memory: uint8 frames -> normalised, resized network input
+  int ingest(const uint8_t* const* imgs_u8, cudaStream_t s) override {
     Ten<float> i1 = fview(img[1], 1, 4, 4);
     for (int b = 0; b < B; ++b) TRY(prep_image_u8(imgs_u8[b], H0, W0, i1, b, s));
+    return DFVO_OK;
+  }
+
+  int features(cudaStream_t s) {
     for (int L = 2; L <= 6; ++L) TRY(resize_bilinear_f32(cfview(img[L - 1], L - 1, 3, 4), fview(img[L], L, 4, 4), 0, s));
     Ten<const T> none; memset(&none, 0, sizeof(none));
     // level 1: 7x7 3->32.  bf16: row-unroll + tcgen05 7x1 conv;  fp32: CUDA-core kernel on the float image
-    if (IsBf16<T>::v) {
+    if (IsBf16<T>::v && stem_window) {
+      Ten<T> pad = make_ten<T>(imgpad, B, lh[1], lw[1] + 8, 8, 8);
+      TRY(pad_image8<T>(cfview(img[1], 1, 3, 4), pad, s));
+      // window view: pixel x of the view starts at padded column x (= image column x - 3) and spans 64 elements
+      Ten<const T> win; win.p = imgpad; win.N = B; win.H = lh[1]; win.W = lw[1]; win.C = 64;
+      win.sW = 8; win.sH = (long long)(lw[1] + 8) * 8; win.sN = (long long)lh[1] * (lw[1] + 8) * 8;
+      TRY(run_conv<T>(fOne, win, view(f1buf, 1, 32, 32), ACT_LEAKY, none, 0, s));
+    } else if (IsBf16<T>::v) {
       TRY(im2row7<T>(cfview(img[1], 1, 3, 4), view(rowbuf, 1, 32, 32), s));
       TRY(run_conv<T>(fOne, cview(rowbuf, 1, 32, 32), view(f1buf, 1, 32, 32), ACT_LEAKY, none, 0, s));
     } else {
@@ -325,8 +352,10 @@ struct LfnImpl : public LiteFlowNetBase {
     return DFVO_OK;
   }
 
-  int forward(const uint8_t* const* imgs_u8, cudaStream_t s) {
-    TRY(features(imgs_u8, s));
+  // everything between the ingest and the emit: touches only buffers this object owns, so it is one fixed launch
+  // sequence (replayed as a CUDA graph by the C-ABI layer)
+  int body(cudaStream_t s) override {
+    TRY(features(s));
     const float* prev = nullptr;
     for (int L = 6; L >= 2; --L) {
       TRY(level(L, prev, s));
@@ -337,8 +366,8 @@ struct LfnImpl : public LiteFlowNetBase {
     return DFVO_OK;
   }
 
-  int run(const uint8_t* const* imgs_u8, float* flow_fwd, float* flow_bwd, float* flow_diff, cudaStream_t s) override {
-    TRY(forward(imgs_u8, s));
+  // the only launches that write caller memory: consistency map + copies of the two flows
+  int emit(float* flow_fwd, float* flow_bwd, float* flow_diff, cudaStream_t s) override {
     const size_t plane2 = (size_t)2 * H0 * W0;
     for (int p = 0; p < P; ++p) {
       const float* f = out_planar + (size_t)(2 * p) * plane2;
@@ -348,6 +377,12 @@ struct LfnImpl : public LiteFlowNetBase {
       if (flow_bwd) DFVO_CUDA(cudaMemcpyAsync(flow_bwd + p * plane2, b, plane2 * 4, cudaMemcpyDeviceToDevice, s));
     }
     return DFVO_OK;
+  }
+
+  int run(const uint8_t* const* imgs_u8, float* flow_fwd, float* flow_bwd, float* flow_diff, cudaStream_t s) override {
+    TRY(ingest(imgs_u8, s));
+    TRY(body(s));
+    return emit(flow_fwd, flow_bwd, flow_diff, s);
   }
 
   int debug_level_flow(int L, int which, float* out_nhwc2) override {

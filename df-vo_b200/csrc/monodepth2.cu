@@ -100,7 +100,7 @@ struct MonoImpl : public Monodepth2Base {
       snprintf(nm, sizeof(nm), "decoder.%d.conv.conv", idx);
       TRYM(plain_conv(ws, nm, ci1, true, &up[idx])); ++idx;
     }
-    TRYM(plain_conv(ws, "decoder.10.conv", 16, false, &disp0));
+    TRYM(plain_conv(ws, "decoder.10.conv", 16, true, &disp0));      // bf16: tensor-core kernel with N padded 1 -> 16
     // ---------------- buffers ----------------
     fh[0] = h / 2; fw[0] = w / 2; fc[0] = 64;
     for (int i = 1; i < 5; ++i) { fh[i] = h >> (i + 1); fw[i] = w >> (i + 1); fc[i] = enc[i]; }
@@ -183,9 +183,8 @@ struct MonoImpl : public Monodepth2Base {
     // dispconv scale 0: Conv3x3 (reflect) + sigmoid, 16 -> 1
     TRYM(upcat_reflect<T>(ctv(x, xh, xw, 16, 16), 1, none, tv(padbuf, xh + 2, xw + 2, 16, 16), s));
     {
-      ConvDirect d = {16, 1, 3, 3, 1, 0, 0, 0, ACT_SIGMOID, disp0.w_direct, disp0.w_pitch, disp0.bias};
       Ten<const float> fnone; memset(&fnone, 0, sizeof(fnone));
-      TRYM((conv_direct<T, float>(d, ctv(padbuf, xh + 2, xw + 2, 16, 16), make_ten<float>(disp, 1, h, w, 1, 1), fnone, s)));
+      TRYM(run_conv_f32out<T>(disp0, ctv(padbuf, xh + 2, xw + 2, 16, 16), make_ten<float>(disp, 1, h, w, 1, 1), ACT_SIGMOID, fnone, s));
     }
     TRYM(disp_to_depth(disp, h * w, min_depth, max_depth, baseline, depth_out, s));
     return DFVO_OK;

@@ -1,6 +1,7 @@
 #include "net_common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dfvo {
@@ -196,12 +197,20 @@ template <>
 int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out, int act, Ten<const float> residual,
                           cudaStream_t s) {
   if (!L.tc) return conv_direct<bf16, float>(to_direct(L, act), in, out, residual, s);
-  if (L.w_head && act == ACT_NONE && in.C == 32 && (L.kh == 3 || L.kh == 5 || L.kh == 7) && L.pad_y == L.kh / 2 && L.pad_x == L.kw / 2)
+  // 2-channel flow heads: the CUDA-core kernel wins on the coarse levels (one short launch), the tensor-core kernel
+  // (N padded to 16, halo-resident operand: 49 taps re-use one box) on the fine ones
+  static int head_tc = -1;
+  if (head_tc < 0) { const char* e = getenv("DFVO_HEAD_TC"); head_tc = !(e && atoi(e) == 0); }
+  const bool big = (long long)in.N * in.H * in.W >= 100000;
+  if (L.w_head && !(head_tc && big) && act == ACT_NONE && in.C == 32 && (L.kh == 3 || L.kh == 5 || L.kh == 7) &&
+      L.pad_y == L.kh / 2 && L.pad_x == L.kw / 2)
     return flow_head(in, L.w_head, L.bias_h[0], L.bias_h[1], L.kh, residual, out, s);
   DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc head: input view has %d channels, layer expects %d", in.C, L.Ktot);
+  DFVO_REQUIRE(L.stride == 1 && in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
+               "tc head: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
   ConvTc c;
   memset(&c, 0, sizeof(c));
-  c.N = in.N; c.H = in.H; c.W = in.W;
+  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W; c.stride = 1;
   c.nsrc = 1;
   c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
   fill_taps(L, &c);

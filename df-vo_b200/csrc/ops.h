@@ -17,6 +17,9 @@ int resize_bilinear_f32(Ten<const float> in, Ten<float> out, int align_corners, 
 // out[n,y,x,dx*3+c] = img[n,y,x+dx-3,c], zero padded, channels >= 21 zero (stem 7x7 -> 7x1 over 32 channels)
 template <typename T>
 int im2row7(Ten<const float> img, Ten<T> out, cudaStream_t s);
+// out[n, y, x+3, 0..2] = img[n, y, x, 0..2] into a zero-initialised [N, H, W+8, 8] buffer (overlapping-window stem operand)
+template <typename T>
+int pad_image8(Ten<const float> img, Ten<T> out, cudaStream_t s);
 // depthwise ConvTranspose2d k4 s2 p1, no bias (lite_flow_net.py:109,117); w = [C][4][4] float
 template <typename T>
 int deconv4x4s2_dw(Ten<const T> in, const float* w, Ten<T> out, cudaStream_t s);

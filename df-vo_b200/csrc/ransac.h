@@ -21,6 +21,12 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
 int recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx, double cy, double* Rt_out,
                  uint8_t* mask_out, int32_t* info, cudaStream_t s);
 
+// R repeats of cv2.solvePnPRansac (pnp.cu): rt_out [R][6] = rvec, tvec; info [R][4] = {found, inliers, iterations, best iteration}
+size_t pnp_workspace_bytes(int N, int R, int iters);
+int pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm, int R, const int32_t* subsets, int iters, double fx,
+               double fy, double cx, double cy, double threshold, double prob, void* workspace, size_t ws_bytes, double* rt_out,
+               int32_t* info, cudaStream_t s);
+
 // ops_3d.triangulation(kp1n, kp2n, eye(4), T_21) -> z of X2 per point (ops_3d.py:44-67)
 int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s);
 

@@ -74,6 +74,16 @@ __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo,
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; it must not touch data the predecessor produces (or overwrite
+// data it reads) before pdl_wait(), which returns once the predecessor grid has completed and flushed.  pdl_trigger()
+// lets the *next* kernel of the stream start its own prologue early.  The convolution kernels run their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch, bias staging: nothing a predecessor writes) before the wait.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
 // one elected lane of a fully active warp (cute::elect_one_sync): ptxas keeps tcgen05 / TMA issues under this
 // predicate on the uniform datapath without the per-instruction ELECT loop it emits under `if (lane == 0)`
 __device__ __forceinline__ bool elect_one() {
@@ -211,5 +221,9 @@ void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc
 int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
                   const unsigned* box);                              // bf16, SWIZZLE_128B, zero OOB fill
 int tc_num_sms();
+// launch config with the PDL attribute set unless DFVO_PDL=0 (attr must outlive the cudaLaunchKernelEx call)
+#ifndef DFVO_HOSTSIM
+void tc_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int block, size_t smem, cudaStream_t s);
+#endif
 
 }  // namespace dfvo

@@ -1,13 +1,12 @@
 """``PnpTracker`` with the reference's interface (libs/tracker/pnp_tracker.py:23-212).
 
-The PnP fallback only runs when the essential-matrix tracker is rejected (dfvo.py:227).  This round the
-keypoint filtering / unprojection are vectorised NumPy and the RANSAC itself is still
-``cv2.solvePnPRansac`` on the host -- the EPnP + LM device port is listed as open work in DESIGN.md; it is
-not a fallback for a CUDA path, it is the one row of SURVEY 8(a) not yet moved to the device."""
+The PnP fallback only runs when the essential-matrix tracker is rejected (dfvo.py:227).  Keypoint filtering is
+vectorised NumPy on the arrays the driver passes in; the RANSAC repeats (OpenCV's subset stream replayed, EPnP minimal
+solver, reprojection scoring) and the final least-squares refit run on the device (csrc/pnp.cu)."""
 import numpy as np
 
+from b200 import tracking
 from libs.geometry.camera_modules import SE3
-from libs.geometry.ops_3d import unprojection_kp
 
 
 class PnpTracker:
@@ -18,7 +17,6 @@ class PnpTracker:
 
     def compute_pose_3d2d(self, kp1, kp2, depth_1, is_iterative):
         """pnp_tracker.py:45-125 -> {'pose': SE3 (view-2 -> view-1), 'kp1', 'kp2'}."""
-        import cv2
         depth_1 = np.asarray(depth_1)
         height, width = depth_1.shape
         keep = (kp2[:, 0] >= 0) & (kp2[:, 0] < width)
@@ -29,24 +27,12 @@ class PnpTracker:
         d = depth_1[ki[:, 1], ki[:, 0]]
         keep = (d != 0) & (d < self.cfg.depth.max_depth) & (d > self.cfg.depth.min_depth)
         kp1, kp2 = kp1[keep], kp2[keep]
-        XYZ = unprojection_kp(kp1, d[keep], self.cam_intrinsics)
-        best_rt, best_inl = [], 0
         repeat = self.cfg.pnp_tracker.ransac.repeat if is_iterative else 3
-        for _ in range(repeat):
-            order = np.arange(0, kp2.shape[0], 1)
-            np.random.shuffle(order)                                   # host RNG, as the reference (:92)
-            nX, n2 = XYZ.copy()[order], kp2.copy()[order]
-            if n2.shape[0] > 4:
-                flag, r, t, inl = cv2.solvePnPRansac(objectPoints=nX, imagePoints=n2, cameraMatrix=self.cam_intrinsics.mat,
-                                                     distCoeffs=None, iterationsCount=self.cfg.pnp_tracker.ransac.iter,
-                                                     reprojectionError=self.cfg.pnp_tracker.ransac.reproj_thre)
-                if flag and inl.shape[0] > best_inl:
-                    best_rt, best_inl = [r, t], inl.shape[0]
-        pose = SE3()
-        if len(best_rt) != 0:
-            pose.R = cv2.Rodrigues(best_rt[0])[0]
-            pose.t = best_rt[1]
-        pose.pose = pose.inv_pose                                      # :118 (solvePnP gives ref -> cur)
+        K = [float(self.cam_intrinsics.cx), float(self.cam_intrinsics.cy), float(self.cam_intrinsics.fx), float(self.cam_intrinsics.fy)]
+        T, _ = tracking.compute_pose_3d2d(tracking.default_engine(), np.asarray(kp1, np.float64), np.asarray(kp2, np.float64),
+                                          d[keep], K, repeat=repeat, iters=self.cfg.pnp_tracker.ransac.iter,
+                                          reproj_thre=self.cfg.pnp_tracker.ransac.reproj_thre)
+        pose = SE3(T)                                                  # already inverted (:118: solvePnP gives ref -> cur)
         return {"pose": pose, "kp1": kp1, "kp2": kp2}
 
     def compute_rigid_flow_kp(self, cur_data, ref_data, pose):

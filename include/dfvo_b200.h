@@ -173,6 +173,17 @@ int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const doub
 int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx,
                       double cy, double* Rt_out, uint8_t* mask_out, int32_t* info, void* stream);
 
+/* R repeats of cv2.solvePnPRansac(obj[perm_r], img[perm_r], K, None, iterationsCount=iters, reprojectionError=threshold,
+ * confidence=prob, flags=SOLVEPNP_ITERATIVE) (pnp_tracker.py:86-112).  obj [N][3] = unprojected reference keypoints
+ * (ops_3d.py:70-94), img [N][2] pixels, float64; perm [R][N] int32 = the host np.random.shuffle permutations (NULL:
+ * identity); subsets [iters][5] int32 = dfvo_cv_subset_stream_host(N, 5, iters).  Per repeat: rt_out [R][6] = rvec, tvec
+ * of the final least-squares pose over the RANSAC inliers; info [R][4] = {found, RANSAC inliers, iterations run, winning
+ * iteration}.  The caller ranks repeats by the inlier count (pnp_tracker.py:108-110). */
+size_t dfvo_pnp_workspace_bytes(int N, int R, int iters);
+int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm, int R, const int32_t* subsets,
+                    int iters, double fx, double fy, double cx, double cy, double threshold, double prob,
+                    void* workspace, size_t workspace_bytes, double* rt_out, int32_t* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,106 @@
+"""Shared checks of the device PnP RANSAC (csrc/pnp.cu) against cv2.solvePnPRansac and the reference PnpTracker golden;
+run on the CPU emulation build by test_pnp.py and on the GPU by test_gpu_depth_pose.py.
+
+Tolerance: OpenCV's EPnP reads its null-space vectors from the LEFT singular vectors of a rank-deficient 12x12 matrix
+(5 points = 10 equations), i.e. from normalised round-off, so its minimal-sample poses are only reproducible to ~1e-6;
+the RANSAC trajectory usually still coincides (same winning iteration, same inlier count, refit pose equal to 1e-12).
+When it does not, the inlier sets differ by a few borderline points and the refit poses by < 1e-4 rad / 1e-3 |t|
+(BASELINE north-star tolerance), which is what is asserted; the fraction of exactly reproduced repeats is asserted too."""
+import numpy as np
+
+import synthdata
+from b200 import hostmath, tracking
+
+
+def scene(seed, outlier_frac, noise, n=1500, h=376, w=1241):
+    K = synthdata.kitti_intrinsics(h, w)
+    cx, cy, fx, fy = K
+    Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    rs = np.random.RandomState(seed)
+    kp1 = np.stack([rs.uniform(0, w, n), rs.uniform(0.3 * h, h, n)], 1)
+    d = rs.uniform(4, 45, n)
+    XYZ = (np.linalg.inv(Kmat) @ np.concatenate([kp1, np.ones((n, 1))], 1).T).T * d[:, None]
+    rvec = np.array([0.002, 0.015, -0.001]) * (1 + rs.rand())
+    tvec = np.array([0.03, -0.01, -0.8])
+    Xc = (hostmath.rodrigues(rvec) @ XYZ.T).T + tvec
+    kp2 = np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], 1) + rs.standard_normal((n, 2)) * noise
+    bad = rs.rand(n) < outlier_frac
+    kp2[bad] += rs.uniform(-40, 40, (int(bad.sum()), 2))
+    return K, Kmat, kp1, d, XYZ, kp2
+
+
+def pose_delta(Ra, ta, Rb, tb):
+    dR = Ra.T @ Rb
+    ang = float(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+    return ang, float(np.linalg.norm(ta - tb) / max(np.linalg.norm(tb), 1e-12))
+
+
+def check_vs_cv2(engine):
+    """Per repeat: the device RANSAC either reproduces cv2.solvePnPRansac exactly (inlier count equal, pose to 1e-9) or
+    lands on a neighbouring consensus set (see the module docstring); the best-of-5 result the tracker returns
+    (pnp_tracker.py:108-110) must agree within the north-star tolerance in every scene."""
+    import cv2
+    exact = total = 0
+    for seed, outl, noise in [(1, 0.0, 0.05), (2, 0.3, 0.05), (3, 0.5, 0.2), (4, 0.1, 0.5), (5, 0.3, 0.3), (6, 0.6, 0.1)]:
+        K, Kmat, kp1, d, XYZ, kp2 = scene(seed, outl, noise)
+        n = XYZ.shape[0]
+        np.random.seed(7)
+        perms = []
+        for _ in range(5):
+            o = np.arange(n)
+            np.random.shuffle(o)
+            perms.append(o)
+        rt, info = engine.pnp_ransac(XYZ, kp2, perms, K, 100, 1.0)
+        ref = []
+        for r in range(5):
+            flag, rv, tv, inl = cv2.solvePnPRansac(objectPoints=XYZ[perms[r]].copy(), imagePoints=kp2[perms[r]].copy(), cameraMatrix=Kmat,
+                                                   distCoeffs=None, iterationsCount=100, reprojectionError=1)
+            assert bool(info[r, 0]) == bool(flag)
+            ref.append((inl.shape[0], cv2.Rodrigues(rv)[0], tv.ravel()))
+            ang, dt = pose_delta(hostmath.rodrigues(rt[r, :3]), rt[r, 3:], ref[r][1], ref[r][2])
+            assert abs(int(info[r, 1]) - inl.shape[0]) <= 0.08 * inl.shape[0], (seed, r, info[r], inl.shape[0])
+            assert ang < 1e-3 and dt < 5e-2, (seed, r, ang, dt)
+            total += 1
+            exact += int(info[r, 1] == inl.shape[0] and ang < 1e-9 and dt < 1e-9)
+        # what the tracker returns: the first repeat with the largest inlier count
+        bc = max(range(5), key=lambda r: (ref[r][0], -r))
+        bd = max(range(5), key=lambda r: (int(info[r, 1]), -r))
+        ang, dt = pose_delta(hostmath.rodrigues(rt[bd, :3]), rt[bd, 3:], ref[bc][1], ref[bc][2])
+        assert ang < 1e-4 and dt < 1e-3, ("best of 5", seed, ang, dt)
+    assert exact >= 0.8 * total, "only %d of %d repeats reproduce cv2.solvePnPRansac exactly" % (exact, total)
+    return exact, total
+
+
+def check_vs_reference_golden(engine, g):
+    """tracking.compute_pose_3d2d after the same RNG consumption as the reference run (E-tracker shuffles, scale RANSAC)
+    against PnpTracker.compute_pose_3d2d of the unmodified reference (tests/golden/trackers_2000.npz)."""
+    K = synthdata.kitti_intrinsics()
+    cases = {"out00": dict(seed=31, outlier_frac=0.0), "out30": dict(seed=32, outlier_frac=0.3),
+             "out60": dict(seed=33, outlier_frac=0.6), "still": dict(seed=34, outlier_frac=0.1, zero_motion=True)}
+    worst = (0.0, 0.0)
+    for name, kw in cases.items():
+        kp_ref, kp_cur, info = synthdata.correspondences(n=2000, **kw)
+        np.random.seed(4869)
+        r = tracking.compute_pose_2d2d(engine, kp_ref, kp_cur, K)
+        depth = info["depth"].astype(np.float32)
+        dp = (depth * ((depth < 50) & (depth > 0))).astype(np.float64)
+        if np.linalg.norm(r["t"]) != 0:
+            pose = np.eye(4); pose[:3, :3] = r["R"]; pose[:3, 3:] = r["t"]
+            tracking.find_scale_from_depth(engine, kp_ref, kp_cur, np.linalg.inv(pose), dp, K)
+        # PnpTracker's keypoint filter (pnp_tracker.py:64-78)
+        keep = (kp_cur[:, 0] >= 0) & (kp_cur[:, 0] < 1241)
+        k1, k2 = kp_ref[keep], kp_cur[keep]
+        keep = (k2[:, 1] >= 0) & (k2[:, 1] < 376)
+        k1, k2 = k1[keep], k2[keep]
+        ki = k1.astype(int)
+        d = dp[ki[:, 1], ki[:, 0]]
+        keep = (d != 0) & (d < 50) & (d > 0)
+        k1, k2, d = k1[keep], k2[keep], d[keep]
+        assert k1.shape[0] == int(g[name + "_pnp_nkp"])
+        T, ninl = tracking.compute_pose_3d2d(engine, k1, k2, d, K)
+        want = g[name + "_pnp_pose"]
+        ang, dt = pose_delta(T[:3, :3], T[:3, 3], want[:3, :3], want[:3, 3])
+        assert ang < 1e-4 and dt < 1e-3, (name, ang, dt)
+        assert int(np.random.randint(0, 2 ** 31 - 1)) == int(g[name + "_rng_after"]), "host RNG position differs from the reference run"
+        worst = (max(worst[0], ang), max(worst[1], dt))
+    return worst

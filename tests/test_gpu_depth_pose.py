@@ -176,3 +176,23 @@ def test_lanczos_feed_bit_exact_with_pil(dev_lib):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ref)
     assert np.array_equal(f.cpu().numpy(), np.transpose(ref, (2, 0, 1)).astype(np.float32) / np.float32(255))
+
+
+def _gpu_engine():
+    from b200 import runtime as rt_mod, tracking
+    rt = rt_mod.CudaRuntime(0)
+    rt_mod.set_runtime(rt)
+    return tracking.Engine(376, 1241, rt)
+
+
+def test_pnp_ransac_vs_cv2(dev_lib):
+    """csrc/pnp.cu on the device against cv2.solvePnPRansac (pnp_tracker.py:98): see tests/pnp_cases.py for the bar."""
+    import pnp_cases
+    exact, total = pnp_cases.check_vs_cv2(_gpu_engine())
+    assert exact >= 0.8 * total
+
+
+def test_pnp_tracker_vs_reference_golden(dev_lib):
+    import pnp_cases
+    ang, dt = pnp_cases.check_vs_reference_golden(_gpu_engine(), np.load(os.path.join(G, "trackers_2000.npz")))
+    assert ang < 1e-4 and dt < 1e-3

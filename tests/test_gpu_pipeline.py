@@ -27,9 +27,10 @@ def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w):
         if st.fwd is not None:
             net_flows[fid] = (st.fwd.t.clone(), st.diff.t.clone())
             st.fwd.upload(a["fwd"][None]); st.bwd.upload(a["bwd"][None]); st.diff.upload(a["diff"][None, :, :, 0])
-        net_flows.setdefault("depth", {})[fid] = st.raw_depth.t.clone()
-        d = p._buf("dsrc", (h, w), np.float32).upload(a["depth"])
-        p.eng.depth_post(d, p.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
+        with p.depth_stream():                    # same stream as (hence ordered after) the depth network
+            net_flows.setdefault("depth", {})[fid] = st.raw_depth.t.clone()
+            d = p._buf("dsrc", (h, w), np.float32).upload(a["depth"])
+            p.eng.depth_post(d, p.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
         return st
 
     p.infer = infer
