@@ -165,9 +165,70 @@ __global__ void k_deconv4x4s2_dw(Ten<const T> in, const float* __restrict__ w, T
   out.at(n, y, x)[c] = from_f<T>(acc);
 }
 
+// bf16 fast path: one thread per (output pixel, 8 channels), 128-bit loads / stores; same tap order as the generic kernel
+__global__ void k_deconv4x4s2_dw_bf16v(Ten<const bf16> in, const float* __restrict__ w, Ten<bf16> out, int groups) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)out.N * out.H * out.W * groups;
+  if (gid >= total) return;
+  const int g = (int)(gid % groups);
+  long long p = gid / groups;
+  const int x = (int)(p % out.W); p /= out.W;
+  const int y = (int)(p % out.H);
+  const int n = (int)(p / out.H);
+  const int c0 = g * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int ky0 = (y + 1) & 1, kx0 = (x + 1) & 1;
+  for (int a = 0; a < 2; ++a) {
+    const int ky = ky0 + 2 * a;
+    const int iy = (y + 1 - ky) / 2;
+    if ((y + 1 - ky) < 0 || iy >= in.H) continue;
+    for (int b = 0; b < 2; ++b) {
+      const int kx = kx0 + 2 * b;
+      const int ix = (x + 1 - kx) / 2;
+      if ((x + 1 - kx) < 0 || ix >= in.W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in.at(n, iy, ix) + c0);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        if (c < in.C) {
+          const float f = (j & 1) ? __uint_as_float(u[j >> 1] & 0xffff0000u) : __uint_as_float(u[j >> 1] << 16);
+          acc[j] += f * w[c * 16 + ky * 4 + kx];
+        }
+      }
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bf16 lo = __float2bfloat16_rn(acc[2 * j]), hi = __float2bfloat16_rn(acc[2 * j + 1]);
+    o[j] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&lo)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&hi)) << 16);
+  }
+  *reinterpret_cast<uint4*>(out.at(n, y, x) + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <typename T> struct DeconvFast { static bool launch(Ten<const T>, const float*, Ten<T>, cudaStream_t) { return false; } };
+template <> struct DeconvFast<bf16> {
+  static bool launch(Ten<const bf16> in, const float* w, Ten<bf16> out, cudaStream_t s) {
+    const bool ok = out.C % 8 == 0 && ((uintptr_t)in.p & 15) == 0 && ((uintptr_t)out.p & 15) == 0 && in.sW % 8 == 0 && out.sW % 8 == 0 &&
+                    in.sH % 8 == 0 && out.sH % 8 == 0 && in.sN % 8 == 0 && out.sN % 8 == 0 && in.sW >= out.C;
+    if (!ok) return false;
+    const int groups = out.C / 8;
+    const long long total = (long long)out.N * out.H * out.W * groups;
+    DFVO_LAUNCH(k_deconv4x4s2_dw_bf16v, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, in, w, out, groups);
+    return true;
+  }
+};
+
 template <typename T>
 int deconv4x4s2_dw(Ten<const T> in, const float* w, Ten<T> out, cudaStream_t s) {
   DFVO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C <= 256, DFVO_ESHAPE, "deconv4x4s2 shape");
+  if (DeconvFast<T>::launch(in, w, out, s)) {
+    DFVO_CHECK_LAUNCH();
+    return DFVO_OK;
+  }
   int ppb = 256 / out.C;
   if (ppb < 1) ppb = 1;
   dim3 block(ppb * out.C), grid(cdiv(out.W, ppb), out.H, out.N);
@@ -712,9 +773,73 @@ __global__ void k_reg_tail(Ten<const T> dist, Ten<const float> flow, int k, cons
   o[1] = (ay + by) * inv;
 }
 
+// bf16 fast path: the k*k distances of a pixel are fetched once with 128-bit loads and kept in registers for both passes
+template <int K>
+__global__ void __launch_bounds__(128)
+k_reg_tail_bf16v(Ten<const bf16> dist, Ten<const float> flow, const float* __restrict__ wx, const float* __restrict__ wy, float bx,
+                 float by, Ten<float> out) {
+  constexpr int CD = K * K, NV = (CD + 7) / 8, R = K / 2;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.W) return;
+  const bf16* d = dist.at(n, y, x);
+  float v[NV * 8];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const uint4 u4 = *reinterpret_cast<const uint4*>(d + q * 8);
+    const uint32_t u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[q * 8 + 2 * j] = __uint_as_float(u[j] << 16); v[q * 8 + 2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u); }
+  }
+  float m = -3.4e38f;
+#pragma unroll
+  for (int j = 0; j < CD; ++j) {
+    const float nv = -(v[j] * v[j]);
+    m = nv > m ? nv : m;
+  }
+  float se = 0.f, ax = 0.f, ay = 0.f;
+#pragma unroll
+  for (int j = 0; j < CD; ++j) {
+    const float e = expf(-(v[j] * v[j]) - m);
+    se += e;
+    const int yy = y + j / K - R, xx = x + j % K - R;
+    if (yy >= 0 && yy < flow.H && xx >= 0 && xx < flow.W) {
+      const float* f = flow.at(n, yy, xx);
+      ax += wx[j] * (e * f[0]);
+      ay += wy[j] * (e * f[1]);
+    }
+  }
+  const float inv = 1.f / se;
+  float* o = out.at(n, y, x);
+  o[0] = (ax + bx) * inv;
+  o[1] = (ay + by) * inv;
+}
+
+template <typename T> struct RegTailFast {
+  static bool launch(Ten<const T>, Ten<const float>, int, const float*, const float*, float, float, Ten<float>, cudaStream_t) { return false; }
+};
+template <> struct RegTailFast<bf16> {
+  static bool launch(Ten<const bf16> dist, Ten<const float> flow, int k, const float* wx, const float* wy, float bx, float by,
+                     Ten<float> out, cudaStream_t s) {
+    const int nv8 = (k * k + 7) / 8 * 8;
+    const bool ok = (k == 3 || k == 5 || k == 7) && ((uintptr_t)dist.p & 15) == 0 && dist.sW % 8 == 0 && dist.sH % 8 == 0 && dist.sN % 8 == 0 &&
+                    dist.sW >= nv8 && flow.sW == 2 && ((uintptr_t)flow.p & 7) == 0;
+    if (!ok) return false;
+    dim3 block(128), grid(cdiv(out.W, 128), out.H, out.N);
+    if (k == 3) DFVO_LAUNCH(k_reg_tail_bf16v<3>, grid, block, 0, s, dist, flow, wx, wy, bx, by, out);
+    else if (k == 5) DFVO_LAUNCH(k_reg_tail_bf16v<5>, grid, block, 0, s, dist, flow, wx, wy, bx, by, out);
+    else DFVO_LAUNCH(k_reg_tail_bf16v<7>, grid, block, 0, s, dist, flow, wx, wy, bx, by, out);
+    return true;
+  }
+};
+
 template <typename T>
 int reg_tail(Ten<const T> dist, Ten<const float> flow, int k, const float* wx, const float* wy, float bx,
              float by, Ten<float> out, cudaStream_t s) {
+  if (RegTailFast<T>::launch(dist, flow, k, wx, wy, bx, by, out, s)) {
+    DFVO_CHECK_LAUNCH();
+    return DFVO_OK;
+  }
   dim3 block(128), grid(cdiv(out.W, 128), out.H, out.N);
   auto kk = k_reg_tail<T>;
   DFVO_LAUNCH(kk, grid, block, 0, s, dist, flow, k, wx, wy, bx, by, out);

@@ -43,6 +43,47 @@ def test_correlation(dev_lib, B, C, H, W, s, prec):
         assert (err <= 1e-2 * np.abs(ref) + 2e-3).all(), err.max()
 
 
+def test_correlation_fb_config3_batched(dev_lib):
+    """BASELINE configs[2]: 64 independent frame pairs (128 maps after fwd/bwd stacking) through the correlation at the
+    level-3 shape (C=64, 88x304, stride 2) and the consistency map at 376x1241.  Size-independent checks: batch entries
+    are independent (entry i of the batched call == the same pair run alone, bit for bit), sampled entries match the
+    oracle, and correlation is linear in its first argument."""
+    rs = np.random.RandomState(64)
+    B, C, H, W, s = 128, 64, 88, 304, 2
+    a = bf16_round(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    b = bf16_round(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    da, db = cu(a), cu(b)
+    out = torch.zeros((B, 49, H // s, W // s), dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_correlation(dptr(da), dptr(db), dptr(out), B, C, H, W, s, 0, 1, None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for i in (0, 77, 127):
+        ref = nets.correlation(torch.from_numpy(a[i:i + 1]), torch.from_numpy(b[i:i + 1]), s).numpy()
+        assert (np.abs(got[i:i + 1] - ref) <= 1e-2 * np.abs(ref) + 2e-3).all()
+        one = torch.zeros((1, 49, H // s, W // s), dtype=torch.float32, device="cuda")
+        dai, dbi = cu(a[i:i + 1]), cu(b[i:i + 1])
+        dev_lib.check(dev_lib.dfvo_correlation(dptr(dai), dptr(dbi), dptr(one), 1, C, H, W, s, 0, 1, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(one.cpu().numpy()[0], got[i])
+    # linearity in the first argument (exact in exact arithmetic; bf16 outputs -> 2 ulp of bf16)
+    a2 = bf16_round(2.0 * a[:2])
+    d2 = cu(a2)
+    out2 = torch.zeros((2, 49, H // s, W // s), dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_correlation(dptr(d2), dptr(db), dptr(out2), 2, C, H, W, s, 0, 1, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out2.cpu().numpy(), 2.0 * got[:2])        # scaling by 2 is exact in binary floating point
+    # consistency map, 64 pairs one after the other: |fwd + warp(bwd)| is zero for exactly opposite constant flows
+    Hf, Wf = 376, 1241
+    fwd = torch.full((2, Hf, Wf), 1.5, dtype=torch.float32, device="cuda")
+    bwd = -fwd
+    diff = torch.zeros((Hf, Wf), dtype=torch.float32, device="cuda")
+    for _ in range(64):
+        dev_lib.check(dev_lib.dfvo_fb_consistency(dptr(fwd), dptr(bwd), dptr(diff), Hf, Wf, None))
+    torch.cuda.synchronize()
+    d = diff.cpu().numpy()
+    assert np.abs(d[:-3, :-3]).max() < 1e-5        # interior: fwd + bwd(p + fwd) = 0 (the right / bottom borders warp out of the image)
+
+
 @pytest.mark.parametrize("prec", [0, 1])
 def test_backward_warp(dev_lib, prec):
     rs = np.random.RandomState(3)
