@@ -60,6 +60,9 @@ SIGNATURES = {
     "dfvo_essential_ransac": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_double,
                                       c_double, c_double, c_double, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    "dfvo_homography_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dfvo_homography_ransac": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
     "dfvo_pnp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dfvo_pnp_ransac": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_double, c_double,
                                 c_double, c_double, c_double, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),

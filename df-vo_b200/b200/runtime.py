@@ -57,6 +57,7 @@ class CudaRuntime:
         native.require_cuda()
         self.torch = torch
         self.device = torch.device("cuda", device)
+        self.device_index = int(device)
         torch.cuda.set_device(self.device)
         self.lib = native.load()
         self.stream = None          # None -> torch's current stream (0 = legacy default is never used implicitly)

@@ -26,7 +26,7 @@ class Engine:
     def __init__(self, height, width, runtime=None):
         self.rt = runtime or rt_mod.get()
         self.lib = self.rt.lib
-        self.ctx = native.Context(self.lib)
+        self.ctx = native.Context(self.lib, getattr(self.rt, "device_index", 0))     # the dfvo_ctx lives on the runtime's device
         self.H, self.W = int(height), int(width)
         self.flow_ready = False
         self.depth_ready = False
@@ -165,6 +165,22 @@ class Engine:
                                                   w["pmask"].ptr, w["pinfo"].ptr, self.rt.stream_ptr()))
         return w["Rt"].numpy(), int(w["pinfo"].numpy()[0])
 
+    def homography_launch(self, kp_cur_buf, kp_ref_buf, n, threshold=1.0, prob=0.99, max_iters=2000):
+        """Enqueue cv2.findHomography(kp_cur, kp_ref, RANSAC, confidence, ransacReprojThreshold) + GRIC-H
+        (E_tracker.py:199-215) on the device (csrc/homog.cu); returns the buffers (H [9], mask [n], info [4], gric [1])."""
+        key = (n, max_iters)
+        if not hasattr(self, "_h_ws"):
+            self._h_ws = {}
+        if key not in self._h_ws:
+            nb = int(self.lib.dfvo_homography_workspace_bytes(n, max_iters))
+            self._h_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), H=self.rt.empty((9,), np.float64), mask=self.rt.empty((n,), np.uint8),
+                                   info=self.rt.empty((4,), np.int32), gric=self.rt.empty((1,), np.float64))
+        w = self._h_ws[key]
+        self.lib.check(self.lib.dfvo_homography_ransac(kp_cur_buf.ptr, kp_ref_buf.ptr, n, max_iters, float(threshold), prob, w["ws"].ptr,
+                                                       w["ws"].shape[0], w["H"].ptr, w["mask"].ptr, w["info"].ptr, w["gric"].ptr,
+                                                       self.rt.stream_ptr()))
+        return w
+
     def pnp_ransac(self, XYZ, kp2, perms, K, iters=100, reproj_thre=1.0, prob=0.99):
         """len(perms) repeats of cv2.solvePnPRansac(XYZ[perm], kp2[perm], K, None, iterationsCount=iters,
         reprojectionError=reproj_thre) on the device (pnp_tracker.py:86-112; csrc/pnp.cu).  XYZ [n,3], kp2 [n,2] float64
@@ -198,30 +214,17 @@ class Engine:
 # ---------------------------------------------------------------------------------------------
 # host-level orchestration of the E-tracker (E_tracker.py:154-307, validity.method == 'GRIC')
 # ---------------------------------------------------------------------------------------------
-_h_pool = None
-
-
-def _homography_gric(kp_cur, kp_ref, n):
-    """E_tracker.py:199-215: cv2.findHomography (RANSAC, 1 px) + GRIC-H.  Runs in a worker thread: OpenCV releases the
-    GIL, so it overlaps the host's waits on the device RANSAC / pose recovery / triangulation."""
-    import cv2
-    H, _ = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
-    return hostmath.calc_gric(hostmath.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
-
-
 def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=np.random, kp_ref_buf=None, kp_cur_buf=None,
                       defer_validity=False):
     """Same contract as ``EssTracker.compute_pose_2d2d`` with the default GRIC validity check.
-    kp_ref/kp_cur: float64 [N,2] host arrays (device copies optional).  The five RANSAC repeats, their
-    GRIC-E scores and recoverPose run on the device; cv2.findHomography + GRIC-H (the model-selection
-    counterpart) run on a host worker thread concurrently.
+    kp_ref/kp_cur: float64 [N,2] host arrays (device copies optional).  Everything numeric runs on the device: the
+    homography model + GRIC-H (csrc/homog.cu), the five essential-matrix RANSAC repeats + GRIC-E (ransac.cu) and
+    recoverPose; the host draws the shuffles, takes the majority vote and the cheirality decision.
     Returns dict(R, t, inliers, valid, cheirality).
 
-    defer_validity=True: the homography vote is not joined here.  R, t are the pose *as if* the E-model is valid and the
-    caller must call :func:`resolve_validity` (which resets them to identity / zero when GRIC prefers the homography)
-    before using them for a decision -- this lets device work that only depends on the pose (triangulation for the
-    scale) run while the homography is still being estimated.  Results are identical either way."""
-    global _h_pool
+    defer_validity=True: R, t are the pose *as if* the E-model is valid and the caller must call
+    :func:`resolve_validity` (which resets them to identity / zero when GRIC prefers the homography) before using them
+    for a decision; lets a caller issue pose-dependent device work before it reads the vote.  Results are identical."""
     n = kp_ref.shape[0]
     R, t = np.eye(3), np.zeros((3, 1))
     out = dict(R=R, t=t, inliers=np.ones(n, bool), valid=False, cheirality=0)
@@ -233,13 +236,10 @@ def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=
         order = np.arange(0, n, 1)
         rng.shuffle(order)
         perms.append(order)
-    if _h_pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _h_pool = ThreadPoolExecutor(max_workers=1)
-    fut = _h_pool.submit(_homography_gric, kp_cur, kp_ref, n)       # homography model (E_tracker.py:199-215)
     rt = engine.rt
     kp_cur_buf = kp_cur_buf or rt.from_host(kp_cur)
     kp_ref_buf = kp_ref_buf or rt.from_host(kp_ref)
+    h = engine.homography_launch(kp_cur_buf, kp_ref_buf, n)         # homography model (E_tracker.py:199-215)
     w = engine.essential_launch(kp_cur_buf, kp_ref_buf, n, perms, K, threshold=reproj_thre)
     info = w["info"].numpy()
     gric = w["gric"].numpy()
@@ -250,24 +250,24 @@ def compute_pose_2d2d(engine, kp_ref, kp_cur, K, repeat=5, reproj_thre=0.2, rng=
     out["E_gric"], out["ransac_info"] = gric, info
     if best >= 0:
         out["inliers"] = w["mask"].numpy()[best].astype(bool)
-        # recoverPose before the validity vote is known (a wasted ~30 us of device time when the vote fails)
+        # recoverPose before the validity vote is read (a wasted ~30 us of device time when the vote fails)
         Rt, cheir = engine.recover_pose(w, best, kp_cur_buf, kp_ref_buf, n, K)
         out["cheirality"] = cheir
         if cheir > n * 0.1:                                         # :299-300
             out["R"], out["t"] = Rt[:9].reshape(3, 3).copy(), Rt[9:].reshape(3, 1).copy()
-    out["_vote"] = (fut, gric, repeat, best)
+    out["_vote"] = (h, gric, repeat, best)
     if not defer_validity:
         resolve_validity(out)
     return out
 
 
 def resolve_validity(out):
-    """Join the homography worker and apply the majority vote H_gric > E_gric (E_tracker.py:270,286-290)."""
+    """Read GRIC-H and apply the majority vote H_gric > E_gric (E_tracker.py:270,286-290)."""
     vote = out.pop("_vote", None)
     if vote is None:
         return out
-    fut, gric, repeat, best = vote
-    H_gric = fut.result()
+    h, gric, repeat, best = vote
+    H_gric = float(h["gric"].numpy()[0])
     num_valid = sum(int(H_gric > gric[r]) for r in range(repeat))
     out["valid"] = num_valid > repeat / 2
     out["H_gric"] = H_gric

@@ -435,6 +435,17 @@ int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N
   API_END
 }
 
+size_t dfvo_homography_workspace_bytes(int N, int max_iters) { return homography_workspace_bytes(N, max_iters); }
+
+int dfvo_homography_ransac(const double* p1, const double* p2, int N, int max_iters, double threshold, double prob, void* workspace,
+                           size_t workspace_bytes, double* H_out, uint8_t* mask_out, int32_t* info, double* gric, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(workspace != nullptr, DFVO_EINVAL, "dfvo_homography_ransac: null workspace");
+  return homography_ransac(p1, p2, N, max_iters, threshold, prob, workspace, workspace_bytes, H_out, mask_out, info, gric,
+                           (cudaStream_t)stream);
+  API_END
+}
+
 size_t dfvo_pnp_workspace_bytes(int N, int R, int iters) { return pnp_workspace_bytes(N, R, iters); }
 
 int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm, int R, const int32_t* subsets, int iters,

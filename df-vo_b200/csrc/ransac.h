@@ -27,6 +27,11 @@ int pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm,
                double fy, double cx, double cy, double threshold, double prob, void* workspace, size_t ws_bytes, double* rt_out,
                int32_t* info, cudaStream_t s);
 
+// cv2.findHomography(p1, p2, RANSAC, threshold, maxIters, confidence) + GRIC-H (homog.cu)
+size_t homography_workspace_bytes(int N, int max_iters);
+int homography_ransac(const double* p1, const double* p2, int N, int max_iters, double threshold, double prob, void* workspace, size_t ws_bytes,
+                      double* H_out, uint8_t* mask_out, int32_t* info, double* gric, cudaStream_t s);
+
 // ops_3d.triangulation(kp1n, kp2n, eye(4), T_21) -> z of X2 per point (ops_3d.py:44-67)
 int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s);
 

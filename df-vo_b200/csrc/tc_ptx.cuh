@@ -132,8 +132,44 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 
 }  // namespace tc
 
+// Slow path of the epilogue (partial channel groups, unaligned pixels, fp32 outputs: the 2-channel heads, the 1-channel
+// disparity head, 9/25/49-channel distance maps).  Deliberately NOT inlined and with rolled loops: the convolution
+// kernels are launched ~115 times per frame, most of them for a few microseconds, and every kilobyte of unrolled
+// epilogue is instruction-cache traffic at each of those launches.
+static __device__ __noinline__ void tc_epilogue16_slow(const TcEpi& p, float4 f0, float4 f1, float4 f2, float4 f3, int c, long long opix,
+                                                 long long rpix) {
+  const float f[16] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w};
+  if (!p.out_f32) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
+    const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+      if (c + j < p.Cout) {
+        const float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
+        o[j] = __float2bfloat16_rn(apply_act(val, p.act));
+      } else if (c + j < p.zero_pad_to) {
+        o[j] = __float2bfloat16_rn(0.f);
+      }
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + opix + c;
+    const float* r = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+      if (c + j < p.Cout) {
+        const float val = f[j] + (r ? r[j] : 0.f);
+        o[j] = apply_act(val, p.act);
+      } else if (c + j < p.zero_pad_to) {
+        o[j] = 0.f;
+      }
+    }
+  }
+}
+
 // bias + optional residual + activation + store of 16 consecutive output channels [c, c+16) of one pixel.
 // v = 16 fp32 accumulator words (tcgen05.ld), bias4 = shared-memory bias, opix/rpix = element offsets of the pixel.
+// Fast path (bf16 output, full aligned group): two 16-byte stores; LeakyReLU / ReLU / identity are one fmaxf with a
+// per-launch slope (0.1 / 0 / 1), only ELU / sigmoid branch.
 __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v, const float4* bias4, int c, long long opix, long long rpix) {
   float f[16];
 #pragma unroll
@@ -144,70 +180,43 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v,
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
   }
-  if (!p.out_f32) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
-    const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
-    const bool full = (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
-                      (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
-    if (full) {
-      if (r) {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
-        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
+  const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
+  const bool full = !p.out_f32 && (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
+                    (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
+  if (!full) {
+    tc_epilogue16_slow(p, make_float4(f[0], f[1], f[2], f[3]), make_float4(f[4], f[5], f[6], f[7]), make_float4(f[8], f[9], f[10], f[11]),
+                       make_float4(f[12], f[13], f[14], f[15]), c, opix, rpix);
+    return;
+  }
+  if (r) {
+    const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[2 * j] += __uint_as_float(rw[j] << 16);
-          f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-        }
-      }
-      switch (p.act) {            // one uniform branch per chunk, loops inside
-        case ACT_LEAKY:
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
-          break;
-        case ACT_RELU:
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          break;
-        case ACT_ELU:
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
-          break;
-        case ACT_SIGMOID:
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
-          break;
-        default: break;
-      }
-      uint32_t w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-    } else {
-      for (int j = 0; j < 16; ++j) {
-        if (c + j < p.Cout) {
-          float val = f[j] + (r ? __bfloat162float(r[j]) : 0.f);
-          o[j] = __float2bfloat16_rn(apply_act(val, p.act));
-        } else if (c + j < p.zero_pad_to) {
-          o[j] = __float2bfloat16_rn(0.f);
-        }
-      }
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + opix + c;
-    const float* r = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
-    for (int j = 0; j < 16; ++j) {
-      if (c + j < p.Cout) {
-        float val = f[j] + (r ? r[j] : 0.f);
-        o[j] = apply_act(val, p.act);
-      } else if (c + j < p.zero_pad_to) {
-        o[j] = 0.f;
-      }
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] += __uint_as_float(rw[j] << 16);
+      f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
     }
   }
+  if (p.act <= ACT_RELU) {
+    const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);      // max(f, f) = f for ACT_NONE
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope * f[j]);
+  } else if (p.act == ACT_ELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 #endif  // !DFVO_HOSTSIM
 

@@ -173,6 +173,14 @@ int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const doub
 int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx,
                       double cy, double* Rt_out, uint8_t* mask_out, int32_t* info, void* stream);
 
+/* cv2.findHomography(p1, p2, RANSAC, ransacReprojThreshold=threshold, maxIters=max_iters, confidence=prob) followed by the
+ * GRIC score of the result (E_tracker.py:199-215, gric.py:40-132): p1 = kp_cur, p2 = kp_ref [N][2] float64 pixels.
+ * H_out [9] row-major (H[8] = 1), mask_out [N] uint8 = RANSAC inliers, info [4] = {found, inliers, iterations run, winning
+ * iteration}, gric [1] = calc_GRIC(compute_homography_residual(H, p1, p2), 0.8, N, 'HMat'). */
+size_t dfvo_homography_workspace_bytes(int N, int max_iters);
+int dfvo_homography_ransac(const double* p1, const double* p2, int N, int max_iters, double threshold, double prob,
+                           void* workspace, size_t workspace_bytes, double* H_out, uint8_t* mask_out, int32_t* info,
+                           double* gric, void* stream);
 /* R repeats of cv2.solvePnPRansac(obj[perm_r], img[perm_r], K, None, iterationsCount=iters, reprojectionError=threshold,
  * confidence=prob, flags=SOLVEPNP_ITERATIVE) (pnp_tracker.py:86-112).  obj [N][3] = unprojected reference keypoints
  * (ops_3d.py:70-94), img [N][2] pixels, float64; perm [R][N] int32 = the host np.random.shuffle permutations (NULL:

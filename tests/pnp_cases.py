@@ -104,3 +104,25 @@ def check_vs_reference_golden(engine, g):
         assert int(np.random.randint(0, 2 ** 31 - 1)) == int(g[name + "_rng_after"]), "host RNG position differs from the reference run"
         worst = (max(worst[0], ang), max(worst[1], dt))
     return worst
+
+
+def check_homography_vs_cv2(engine):
+    """csrc/homog.cu against cv2.findHomography(RANSAC, 1 px, 0.99) + the reference GRIC-H (E_tracker.py:199-215):
+    RANSAC inlier masks bit-equal, H to 1e-8 relative (measured 2e-10), GRIC-H to 1e-9 relative (measured 7e-12)."""
+    import cv2
+    from oracle import vo
+    cases = {"out00": dict(seed=31, outlier_frac=0.0), "out30": dict(seed=32, outlier_frac=0.3), "out60": dict(seed=33, outlier_frac=0.6),
+             "still": dict(seed=34, outlier_frac=0.1, zero_motion=True), "still60": dict(seed=35, outlier_frac=0.6, zero_motion=True)}
+    worst = 0.0
+    for name, kw in cases.items():
+        kp_ref, kp_cur, _ = synthdata.correspondences(n=2000, **kw)
+        n = kp_ref.shape[0]
+        H, mask = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
+        want = vo.calc_gric(vo.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
+        h = engine.homography_launch(engine.rt.from_host(kp_cur), engine.rt.from_host(kp_ref), n)
+        Hd, md, info, g = h["H"].numpy().reshape(3, 3), h["mask"].numpy(), h["info"].numpy(), float(h["gric"].numpy()[0])
+        assert info[0] == 1 and np.array_equal(md, mask.ravel()), (name, info, int(mask.sum()))
+        assert np.abs(Hd - H).max() / np.abs(H).max() < 1e-8, name
+        assert abs(g - want) < 1e-9 * abs(want), (name, g, want)
+        worst = max(worst, abs(g - want) / abs(want))
+    return worst

@@ -196,3 +196,9 @@ def test_pnp_tracker_vs_reference_golden(dev_lib):
     import pnp_cases
     ang, dt = pnp_cases.check_vs_reference_golden(_gpu_engine(), np.load(os.path.join(G, "trackers_2000.npz")))
     assert ang < 1e-4 and dt < 1e-3
+
+
+def test_homography_ransac_gric_vs_cv2(dev_lib):
+    """csrc/homog.cu on the device against cv2.findHomography + GRIC-H (E_tracker.py:199-215)."""
+    import pnp_cases
+    assert pnp_cases.check_homography_vs_cv2(_gpu_engine()) < 1e-9

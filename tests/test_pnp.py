@@ -26,3 +26,8 @@ def test_pnp_ransac_vs_cv2(hostsim_lib):
 def test_pnp_tracker_vs_reference_golden(hostsim_lib):
     worst = pnp_cases.check_vs_reference_golden(_engine(hostsim_lib), np.load(os.path.join(G, "trackers_2000.npz")))
     print("worst rotation / relative translation difference: %.2e rad, %.2e" % worst)
+
+
+def test_homography_ransac_gric_vs_cv2(hostsim_lib):
+    worst = pnp_cases.check_homography_vs_cv2(_engine(hostsim_lib))
+    print("worst relative GRIC-H difference: %.2e" % worst)
