@@ -176,9 +176,18 @@ class Engine:
             self._h_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), H=self.rt.empty((9,), np.float64), mask=self.rt.empty((n,), np.uint8),
                                    info=self.rt.empty((4,), np.int32), gric=self.rt.empty((1,), np.float64))
         w = self._h_ws[key]
-        self.lib.check(self.lib.dfvo_homography_ransac(kp_cur_buf.ptr, kp_ref_buf.ptr, n, max_iters, float(threshold), prob, w["ws"].ptr,
-                                                       w["ws"].shape[0], w["H"].ptr, w["mask"].ptr, w["info"].ptr, w["gric"].ptr,
-                                                       self.rt.stream_ptr()))
+        # forked onto a side stream so it runs beside the essential-matrix RANSAC (both are short chains of small kernels);
+        # whoever reads the result waits on w["done"] first (resolve_validity)
+        if not hasattr(self, "_h_stream"):
+            self._h_stream = self.rt.new_stream(high_priority=True)
+        fork = self.rt.record_event()
+        with self.rt.on_stream(self._h_stream):
+            self.rt.wait_event(fork)
+            self.lib.check(self.lib.dfvo_homography_ransac(kp_cur_buf.ptr, kp_ref_buf.ptr, n, max_iters, float(threshold), prob, w["ws"].ptr,
+                                                           w["ws"].shape[0], w["H"].ptr, w["mask"].ptr, w["info"].ptr, w["gric"].ptr,
+                                                           self.rt.stream_ptr()))
+            w["done"] = self.rt.record_event()
+        w["rt"] = self.rt
         return w
 
     def pnp_ransac(self, XYZ, kp2, perms, K, iters=100, reproj_thre=1.0, prob=0.99):
@@ -267,6 +276,7 @@ def resolve_validity(out):
     if vote is None:
         return out
     h, gric, repeat, best = vote
+    h["rt"].wait_event(h["done"])                                   # join the homography side stream
     H_gric = float(h["gric"].numpy()[0])
     num_valid = sum(int(H_gric > gric[r]) for r in range(repeat))
     out["valid"] = num_valid > repeat / 2

@@ -25,43 +25,41 @@ struct HState { int niters, best_good, best_iter, it, done, n_subsets; };
 
 namespace hmg {
 
-// cyclic Jacobi eigen-decomposition of a symmetric 9x9 (rolled loops, local memory): returns the eigenvector of the
-// smallest eigenvalue
+// Eigenvector of the smallest eigenvalue of the symmetric positive semi-definite 9x9 normal matrix, by inverse iteration on
+// A + mu I (mu = 1e-13 trace: keeps the LDL^T factorisation regular when the matrix is exactly singular, as it is for a
+// minimal 4-point sample).  The smallest eigenvalue is separated from the next by many orders of magnitude in both uses
+// (minimal sample: exact null space; inlier refit: noise level vs signal), so a handful of iterations reach round-off; a
+// single GPU thread does this in ~2k dependent flops instead of the ~40k of a cyclic Jacobi sweep sequence.
 DFVO_HD_NOINLINE void smallest_eigvec9(double A[9][9], double out[9]) {
-  double V[9][9];
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 50; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < 9; ++i) {
-      diag += A[i][i] * A[i][i];
-      for (int j = i + 1; j < 9; ++j) off += A[i][j] * A[i][j];
+  double tr = 0;
+  for (int i = 0; i < 9; ++i) tr += A[i][i];
+  const double mu = 1e-13 * tr;
+  // LDL^T (no pivoting; SPD + shift): L unit lower in-place, D on the diagonal
+  double L[9][9], D[9];
+  for (int j = 0; j < 9; ++j) {
+    double d = A[j][j] + mu;
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+    D[j] = d;
+    for (int i = j + 1; i < 9; ++i) {
+      double v = A[i][j];
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = v / d;
     }
-    if (off <= 1e-36 * diag || off == 0.0) break;
-    for (int p = 0; p < 8; ++p)
-      for (int q = p + 1; q < 9; ++q) {
-        const double apq = A[p][q];
-        if (apq == 0.0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 9; ++k) {
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 9; ++k) {
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 9; ++k) {
-          const double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
-        }
-      }
   }
-  int m = 0;
-  for (int i = 1; i < 9; ++i) if (A[i][i] < A[m][m]) m = i;
-  for (int i = 0; i < 9; ++i) out[i] = V[i][m];
+  double x[9], y[9];
+  for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;           // generic start (not orthogonal to anything special)
+  for (int it = 0; it < 8; ++it) {
+    for (int i = 0; i < 9; ++i) { double v = x[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v; }
+    for (int i = 0; i < 9; ++i) y[i] /= D[i];
+    for (int i = 8; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 9; ++k) v -= L[k][i] * y[k]; y[i] = v; }
+    double nn = 0;
+    for (int i = 0; i < 9; ++i) nn += y[i] * y[i];
+    nn = 1.0 / sqrt(nn);
+    double diff = 0, diffm = 0;
+    for (int i = 0; i < 9; ++i) { const double v = y[i] * nn; diff += (v - x[i]) * (v - x[i]); diffm += (v + x[i]) * (v + x[i]); x[i] = v; }
+    if ((diff < 1e-30 || diffm < 1e-30) && it > 0) break;
+  }
+  for (int i = 0; i < 9; ++i) out[i] = x[i];
 }
 
 // H from the accumulated normal matrix and the two normalisations (HomographyEstimatorCallback::runKernel tail)
@@ -111,22 +109,18 @@ DFVO_HD bool check_subset(const float* s, const float* d) {
 }  // namespace hmg
 
 // float32 copies of the points (cv::findHomography converts both sets to CV_32FC2)
-__global__ void k_h_prepare(const double* __restrict__ p1, const double* __restrict__ p2, int N, float* __restrict__ src, float* __restrict__ dst,
-                            HState* st, int max_iters) {
+__global__ void k_h_prepare(const double* __restrict__ p1, const double* __restrict__ p2, int N, float* __restrict__ src, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { st->niters = max_iters; st->best_good = -1; st->best_iter = -1; st->it = 0; st->done = 0; st->n_subsets = 0; }
   if (i >= N) return;
   src[2 * i] = (float)p1[2 * i]; src[2 * i + 1] = (float)p1[2 * i + 1];
   dst[2 * i] = (float)p2[2 * i]; dst[2 * i + 1] = (float)p2[2 * i + 1];
 }
 
-// one thread: subsets [i0, i1) of the RANSAC loop (RANSACPointSetRegistrator::getSubset with the homography checkSubset);
-// the generator state is carried in rng_state between rounds
-__global__ void k_h_subsets(const float* __restrict__ src, const float* __restrict__ dst, int N, int i0, int i1, uint64_t* rng_state,
-                            int32_t* __restrict__ subsets, HState* st) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (st->done) return;
-  uint64_t state = i0 == 0 ? 0xFFFFFFFFFFFFFFFFull : *rng_state;
+// thread 0 of the block: subsets [i0, i1) of the RANSAC loop (RANSACPointSetRegistrator::getSubset with the homography
+// checkSubset); the generator state is carried between rounds.  Returns the number of subsets available so far.
+DFVO_D int h_make_subsets(const float* __restrict__ src, const float* __restrict__ dst, int N, int i0, int i1, uint64_t* state_io,
+                          int32_t* __restrict__ subsets) {
+  uint64_t state = *state_io;
   int made = i0;
   for (int it = i0; it < i1; ++it) {
     int idx[4];
@@ -149,16 +143,13 @@ __global__ void k_h_subsets(const float* __restrict__ src, const float* __restri
     for (int i = 0; i < 4; ++i) subsets[it * 4 + i] = idx[i];
     made = it + 1;
   }
-  *rng_state = state;
-  st->n_subsets = made;
+  *state_io = state;
+  return made;
 }
 
 // one thread per iteration: 4-point normalised DLT -> hyp [max_iters][9], ok [max_iters]
-__global__ void k_h_hypotheses(const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ subsets, int i0, int i1,
-                               const HState* __restrict__ st, double* __restrict__ hyp, int32_t* __restrict__ ok) {
-  const int it = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= i1) return;
-  if (st->done || it >= st->n_subsets) { ok[it] = 0; return; }
+DFVO_D void h_hypothesis(const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ subsets, int it,
+                         double* __restrict__ hyp, int32_t* __restrict__ ok) {
   double Mx[4], My[4], mx[4], my[4];
   double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
   for (int i = 0; i < 4; ++i) {
@@ -193,24 +184,6 @@ DFVO_D float h_err(const float* Hf, float Mx, float My, float mx, float my) {
   return dx * dx + dy * dy;
 }
 
-// one warp per iteration: inlier count
-__global__ void __launch_bounds__(256)
-k_h_score(const double* __restrict__ hyp, const int32_t* __restrict__ ok, const float* __restrict__ src, const float* __restrict__ dst, int N,
-          int i0, int i1, float thr2, const HState* __restrict__ st, int32_t* __restrict__ counts) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int it = i0 + w;
-  if (it >= i1) return;
-  if (st->done) return;
-  int c = 0;
-  if (ok[it]) {
-    float Hf[8];
-    for (int q = 0; q < 8; ++q) Hf[q] = (float)hyp[(size_t)it * 9 + q];
-    for (int j = lane; j < N; j += 32) c += (h_err(Hf, src[2 * j], src[2 * j + 1], dst[2 * j], dst[2 * j + 1]) <= thr2) ? 1 : 0;
-  }
-  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-  if (lane == 0) counts[it] = c;
-}
-
 DFVO_HD int h_update_num_iters(double p, double ep, int model_points, int max_iters) {
   p = p < 0 ? 0 : (p > 1 ? 1 : p);
   ep = ep < 0 ? 0 : (ep > 1 ? 1 : ep);
@@ -224,41 +197,77 @@ DFVO_HD int h_update_num_iters(double p, double ep, int model_points, int max_it
   return (int)rint(num / denom);
 }
 
-__global__ void k_h_replay(const int32_t* __restrict__ ok, const int32_t* __restrict__ counts, int N, int i1, double prob, HState* st) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  HState s = *st;
-  if (s.done) return;
-  int it = s.it;
-  while (it < s.niters && it < i1) {
-    if (it >= s.n_subsets) { s.done = 1; break; }               // getSubset failed: the loop ends
-    if (ok[it]) {
-      const int good = counts[it];
-      const int lim = s.best_good > 3 ? s.best_good : 3;
-      if (good > lim) {
-        s.best_good = good; s.best_iter = it;
-        s.niters = h_update_num_iters(prob, (double)(N - good) / (double)N, 4, s.niters);
-      }
-    }
-    ++it;
-  }
-  s.it = it;
-  if (it >= s.niters) s.done = 1;
-  *st = s;
-}
-
-// one block: inlier mask of the winner, DLT over the inliers, LM refinement, GRIC-H.
+// ONE block runs the whole estimation: RANSAC rounds (thread 0 draws the subsets, one thread per minimal solve, one warp
+// per hypothesis score, thread 0 replays the acceptance rule; later rounds only if the adaptive iteration count asks
+// for them), then the inlier mask of the winner, the DLT over the inliers, the LM refinement and GRIC-H.  A single
+// launch matters: the tracker's kernels run beside the next frame's persistent convolution kernels, and every
+// dependent launch waits for an SM to take it.
 // out: H_out [9], mask [N] (inliers of the refined H), info [4] = {found, inliers, iterations, winning iteration}, gric [1]
 __global__ void __launch_bounds__(256)
-k_h_finalize(const double* __restrict__ hyp, const HState* __restrict__ st, const float* __restrict__ src, const float* __restrict__ dst,
-             const double* __restrict__ p1, const double* __restrict__ p2, int N, float thr2, double* __restrict__ H_out,
-             uint8_t* __restrict__ mask, int32_t* __restrict__ info, double* __restrict__ gric) {
+k_h_ransac(const float* __restrict__ src, const float* __restrict__ dst, const double* __restrict__ p1, const double* __restrict__ p2, int N,
+           int max_iters, double prob, float thr2, double* __restrict__ hyp, int32_t* __restrict__ subsets, int32_t* __restrict__ ok,
+           int32_t* __restrict__ counts, double* __restrict__ H_out, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
+           double* __restrict__ gric) {
   __shared__ double part[8][48];
   __shared__ double acc[48];
   __shared__ double Hs[9], xs[8], xd[8], dvec[8], Amat[8][8], vvec[8];
   __shared__ double S_cur, S_new, lambda, lc;
   __shared__ int stop, ninl;
+  __shared__ HState sst;
+  __shared__ uint64_t rng_state;
   const int t = threadIdx.x;
-  const HState s = *st;
+  if (t == 0) {
+    sst.niters = max_iters; sst.best_good = -1; sst.best_iter = -1; sst.it = 0; sst.done = 0; sst.n_subsets = 0;
+    rng_state = 0xFFFFFFFFFFFFFFFFull;                          // cv::RNG((uint64)-1)
+  }
+  __syncthreads();
+  {
+    const int bounds[5] = {0, 64, 320, 1088, max_iters};
+    for (int rd = 0; rd < 4; ++rd) {
+      const int i0 = bounds[rd] < max_iters ? bounds[rd] : max_iters, i1 = bounds[rd + 1] < max_iters ? bounds[rd + 1] : max_iters;
+      if (i1 <= i0) continue;
+      if (t == 0) sst.n_subsets = h_make_subsets(src, dst, N, i0, i1, &rng_state, subsets);
+      __syncthreads();
+      for (int it = i0 + t; it < i1; it += 256) {
+        if (it < sst.n_subsets) h_hypothesis(src, dst, subsets, it, hyp, ok);
+        else ok[it] = 0;
+      }
+      __syncthreads();
+      for (int it = i0 + (t >> 5); it < i1; it += 8) {          // one warp per hypothesis
+        int c = 0;
+        if (ok[it]) {
+          float Hf[8];
+          for (int q = 0; q < 8; ++q) Hf[q] = (float)hyp[(size_t)it * 9 + q];
+          for (int j = (t & 31); j < N; j += 32) c += (h_err(Hf, src[2 * j], src[2 * j + 1], dst[2 * j], dst[2 * j + 1]) <= thr2) ? 1 : 0;
+        }
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if ((t & 31) == 0) counts[it] = c;
+      }
+      __syncthreads();
+      if (t == 0) {                                             // acceptance rule of RANSACPointSetRegistrator::run
+        HState s2 = sst;
+        int it = s2.it;
+        while (it < s2.niters && it < i1) {
+          if (it >= s2.n_subsets) { s2.done = 1; break; }       // getSubset failed: the loop ends
+          if (ok[it]) {
+            const int good = counts[it];
+            const int lim = s2.best_good > 3 ? s2.best_good : 3;
+            if (good > lim) {
+              s2.best_good = good; s2.best_iter = it;
+              s2.niters = h_update_num_iters(prob, (double)(N - good) / (double)N, 4, s2.niters);
+            }
+          }
+          ++it;
+        }
+        s2.it = it;
+        if (it >= s2.niters) s2.done = 1;
+        sst = s2;
+      }
+      __syncthreads();
+      if (sst.done) break;
+    }
+  }
+  const HState s = sst;
   auto block_sum_vec = [&](const double* a, int n) {            // sums of n <= 48 per-thread values -> acc[0..n)
     for (int k = 0; k < n; ++k) {
       double v = a[k];
@@ -504,21 +513,10 @@ int homography_ransac(const double* p1, const double* p2, int N, int max_iters, 
   int32_t* subsets = (int32_t*)take((size_t)max_iters * 4 * 4);
   int32_t* ok = (int32_t*)take((size_t)max_iters * 4);
   int32_t* counts = (int32_t*)take((size_t)max_iters * 4);
-  HState* st = (HState*)take(sizeof(HState));
-  uint64_t* rng = (uint64_t*)take(8);
   const float thr2 = (float)(threshold * threshold);
-  DFVO_LAUNCH(k_h_prepare, dim3(cdiv(N, 128)), dim3(128), 0, s, p1, p2, N, src, dst, st, max_iters);
-  // rounds: a good scene stops within the first dozens of iterations; later rounds early-exit on st.done
-  const int bounds[4] = {0, 64 < max_iters ? 64 : max_iters, 512 < max_iters ? 512 : max_iters, max_iters};
-  for (int rd = 0; rd < 3; ++rd) {
-    const int i0 = bounds[rd], i1 = bounds[rd + 1];
-    if (i1 <= i0) continue;
-    DFVO_LAUNCH(k_h_subsets, dim3(1), dim3(32), 0, s, src, dst, N, i0, i1, rng, subsets, st);
-    DFVO_LAUNCH(k_h_hypotheses, dim3(cdiv(i1 - i0, 32)), dim3(32), 0, s, src, dst, subsets, i0, i1, st, hyp, ok);
-    DFVO_LAUNCH(k_h_score, dim3(cdiv((i1 - i0) * 32, 256)), dim3(256), 0, s, hyp, ok, src, dst, N, i0, i1, thr2, st, counts);
-    DFVO_LAUNCH(k_h_replay, dim3(1), dim3(32), 0, s, ok, counts, N, i1, prob, st);
-  }
-  DFVO_LAUNCH(k_h_finalize, dim3(1), dim3(256), 0, s, hyp, st, src, dst, p1, p2, N, thr2, H_out, mask_out, info, gric);
+  DFVO_LAUNCH(k_h_prepare, dim3(cdiv(N, 128)), dim3(128), 0, s, p1, p2, N, src, dst);
+  DFVO_LAUNCH(k_h_ransac, dim3(1), dim3(256), 0, s, src, dst, p1, p2, N, max_iters, prob, thr2, hyp, subsets, ok, counts, H_out, mask_out,
+              info, gric);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }

@@ -120,6 +120,7 @@ def check_homography_vs_cv2(engine):
         H, mask = cv2.findHomography(kp_cur, kp_ref, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
         want = vo.calc_gric(vo.homography_residual(H, kp_cur, kp_ref), 0.8, n, "HMat")
         h = engine.homography_launch(engine.rt.from_host(kp_cur), engine.rt.from_host(kp_ref), n)
+        engine.rt.wait_event(h["done"])
         Hd, md, info, g = h["H"].numpy().reshape(3, 3), h["mask"].numpy(), h["info"].numpy(), float(h["gric"].numpy()[0])
         assert info[0] == 1 and np.array_equal(md, mask.ravel()), (name, info, int(mask.sum()))
         assert np.abs(Hd - H).max() / np.abs(H).max() < 1e-8, name
