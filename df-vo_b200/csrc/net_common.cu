@@ -197,10 +197,12 @@ template <>
 int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out, int act, Ten<const float> residual,
                           cudaStream_t s) {
   if (!L.tc) return conv_direct<bf16, float>(to_direct(L, act), in, out, residual, s);
-  // 2-channel flow heads: the CUDA-core kernel wins on the coarse levels (one short launch), the tensor-core kernel
-  // (N padded to 16, halo-resident operand: 49 taps re-use one box) on the fine ones
+  // 2-channel flow heads: dedicated CUDA-core kernel; the tensor-core kernel (N padded to 16) serves the other
+  // float-output layers (monodepth2's disparity head)
+  // (measured with ncu on B200: the 7x7 head at 176x608x2 takes 77 us on the CUDA-core kernel and 94 us on the tensor-core
+  //  kernel -- 49 taps of N = 16 MMAs are issue / barrier bound -- so the tensor-core route is opt-in: DFVO_HEAD_TC=1)
   static int head_tc = -1;
-  if (head_tc < 0) { const char* e = getenv("DFVO_HEAD_TC"); head_tc = !(e && atoi(e) == 0); }
+  if (head_tc < 0) { const char* e = getenv("DFVO_HEAD_TC"); head_tc = (e && atoi(e) == 1); }
   const bool big = (long long)in.N * in.H * in.W >= 100000;
   if (L.w_head && !(head_tc && big) && act == ACT_NONE && in.C == 32 && (L.kh == 3 || L.kh == 5 || L.kh == 7) &&
       L.pad_y == L.kh / 2 && L.pad_x == L.kw / 2)

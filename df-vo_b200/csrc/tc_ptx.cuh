@@ -136,8 +136,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 // disparity head, 9/25/49-channel distance maps).  Deliberately NOT inlined and with rolled loops: the convolution
 // kernels are launched ~115 times per frame, most of them for a few microseconds, and every kilobyte of unrolled
 // epilogue is instruction-cache traffic at each of those launches.
-static __device__ __noinline__ void tc_epilogue16_slow(const TcEpi& p, float4 f0, float4 f1, float4 f2, float4 f3, int c, long long opix,
-                                                 long long rpix) {
+static __device__ __noinline__ void tc_epilogue16_slow(TcEpi p, float4 f0, float4 f1, float4 f2, float4 f3, int c, long long opix,
+                                                        long long rpix) {
   const float f[16] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w};
   if (!p.out_f32) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
@@ -182,8 +182,12 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v,
   }
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c;
   const __nv_bfloat16* r = p.res ? reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c : nullptr;
-  const bool full = !p.out_f32 && (c + 16 <= p.Cout) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
-                    (!r || (reinterpret_cast<uintptr_t>(r) & 15u) == 0);
+  // a group that straddles Cout but lies inside the zero-padded range (49 -> 64, 25 -> 32, 9 -> 16 distance channels) is
+  // still two vector stores: channels >= Cout are written as zeros
+  const int cend = p.Cout > p.zero_pad_to ? p.Cout : p.zero_pad_to;
+  const bool tail = c + 16 > p.Cout;
+  const bool full = !p.out_f32 && (c + 16 <= cend) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
+                    (!r || (!tail && (reinterpret_cast<uintptr_t>(r) & 15u) == 0));
   if (!full) {
     tc_epilogue16_slow(p, make_float4(f[0], f[1], f[2], f[3]), make_float4(f[4], f[5], f[6], f[7]), make_float4(f[8], f[9], f[10], f[11]),
                        make_float4(f[12], f[13], f[14], f[15]), c, opix, rpix);
@@ -208,6 +212,10 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v,
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+  }
+  if (tail) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = (c + j < p.Cout) ? f[j] : 0.f;
   }
   uint32_t w[8];
 #pragma unroll
