@@ -16,10 +16,16 @@ consistent correspondences, so the tracker stages (selection, RANSAC, scale, PnP
 rigid-scene flow / depth of the same shapes, copied over the network outputs on the device inside the
 timed region; every kernel of the frame runs every step.
 
+The pipeline is `b200.pipeline.FramePipeline(overlap=True)`: LiteFlowNet and monodepth2 of frame t are enqueued on
+their own streams (their bodies replayed as CUDA graphs) while frame t-1 is tracked on a third stream, so K steps =
+K frames inferred AND K frames tracked (`DFVO_OVERLAP=0` times the in-order variant; both give identical poses,
+tests/test_gpu_pipeline.py).
+
 Output: ONE JSON line (rank 0).  `value` = frames/s with frames already in HBM; `e2e` = the same metric
 through the public API (host uint8 frames in pinned memory -> pose on the host) with H2D/D2H inside the
-timed region; `roofline` = the tcgen05 convolution kernel against the measured bf16 peak; `cpu_baseline`
-= the CPU oracle port of the same frame timed on this box's cores.
+timed region; `roofline` = the tcgen05 convolution kernels against the measured bf16 peak (per-launch CUDA events
+on an in-order stream; `traffic` = their DRAM bytes per frame from ncu, profiles/conv_tc_traffic.json);
+`cpu_baseline` = the CPU oracle port of the same frame timed on this box's cores.
 """
 import argparse
 import json
