@@ -31,3 +31,40 @@ def test_pnp_tracker_vs_reference_golden(hostsim_lib):
 def test_homography_ransac_gric_vs_cv2(hostsim_lib):
     worst = pnp_cases.check_homography_vs_cv2(_engine(hostsim_lib))
     print("worst relative GRIC-H difference: %.2e" % worst)
+
+
+def test_pose_solver_edge_cases(hostsim_lib):
+    """Sentinel behaviour at the degenerate ends (pnp_tracker.py:97,113-118; E_tracker.py:196,216-217,299-300):
+    fewer than 5 PnP correspondences -> identity pose and no solver call; hopeless correspondences -> the solvers still
+    return a model (RANSAC always keeps its best) but the essential-matrix tracker falls back to R = I, t = 0;
+    no more than 10 keypoints -> E-tracker gives up before consuming any randomness."""
+    import synthdata
+    from b200 import tracking
+    eng = _engine(hostsim_lib)
+    K = synthdata.kitti_intrinsics()
+    rs = np.random.RandomState(3)
+    # PnP with 4 points: n > 4 is false -> identity, but the five shuffles are still drawn (pnp_tracker.py:90-97)
+    k1, k2, d = rs.uniform(0, 300, (4, 2)), rs.uniform(0, 300, (4, 2)), rs.uniform(5, 20, 4)
+    np.random.seed(1)
+    T, ninl = tracking.compute_pose_3d2d(eng, k1, k2, d, K)
+    a = np.random.randint(0, 2 ** 31 - 1)
+    np.random.seed(1)
+    for _ in range(5):
+        np.random.shuffle(np.arange(4))
+    assert np.array_equal(T, np.eye(4)) and ninl == 0 and a == np.random.randint(0, 2 ** 31 - 1)
+    # E-tracker with 10 keypoints: early out, RNG untouched (E_tracker.py:196)
+    kp = rs.uniform(0, 300, (10, 2))
+    np.random.seed(2)
+    r = tracking.compute_pose_2d2d(eng, kp, kp + 1.0, K)
+    after = np.random.randint(0, 2 ** 31 - 1)
+    assert not r["valid"] and np.array_equal(r["R"], np.eye(3)) and not r["t"].any() and r["inliers"].all()
+    np.random.seed(2)
+    assert after == np.random.randint(0, 2 ** 31 - 1)
+    # pure-noise correspondences: finite outputs, identity pose or a rejected / low-support model
+    kp_ref = np.stack([rs.uniform(0, 1241, 400), rs.uniform(0, 376, 400)], 1)
+    kp_cur = np.stack([rs.uniform(0, 1241, 400), rs.uniform(0, 376, 400)], 1)
+    np.random.seed(3)
+    r = tracking.compute_pose_2d2d(eng, kp_ref, kp_cur, K)
+    assert np.isfinite(r["R"]).all() and np.isfinite(r["t"]).all() and r["inliers"].sum() < 60
+    T, ninl = tracking.compute_pose_3d2d(eng, kp_ref, kp_cur, rs.uniform(5, 40, 400), K)
+    assert np.isfinite(T).all() and ninl < 60
