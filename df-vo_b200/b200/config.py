@@ -28,10 +28,14 @@ def default_cfg(height=376, width=1241):
         "kp_selection": {
             "local_bestN": {"enable": True, "num_bestN": 2000, "num_row": 10, "num_col": 10, "score_method": "flow", "thre": 0.1},
             "bestN": {"enable": False, "num_bestN": 2000},
+            "rigid_flow_kp": {"enable": False, "num_bestN": 2000, "num_row": 10, "num_col": 10, "score_method": "opt_flow",
+                              "rigid_flow_thre": 5, "optical_flow_thre": 0.1},
         },
         "tracking_method": "hybrid",
-        "e_tracker": {"ransac": {"reproj_thre": 0.2, "repeat": 5}, "validity": {"method": "GRIC"}},
-        "scale_recovery": {"method": "simple",
+        "e_tracker": {"ransac": {"reproj_thre": 0.2, "repeat": 5}, "validity": {"method": "GRIC"}, "kp_src": "kp_best",
+                      "iterative_kp": {"enable": False, "kp_src": "kp_depth", "score_method": "opt_flow"}},
+        "scale_recovery": {"method": "simple", "kp_src": "kp_best", "iterative_kp": {"enable": False, "kp_src": "kp_depth", "score_method": "rigid_flow"},
                            "ransac": {"method": "depth_ratio", "min_samples": 3, "max_trials": 100, "stop_prob": 0.99, "thre": 0.1}},
-        "pnp_tracker": {"ransac": {"iter": 100, "reproj_thre": 1, "repeat": 5}},
+        "pnp_tracker": {"ransac": {"iter": 100, "reproj_thre": 1, "repeat": 5}, "kp_src": "kp_best",
+                        "iterative_kp": {"enable": False, "kp_src": "kp_depth", "score_method": "rigid_flow"}},
     })

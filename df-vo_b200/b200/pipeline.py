@@ -156,7 +156,8 @@ class FramePipeline:
                                        reproj_thre=c.e_tracker.ransac.reproj_thre, rng=self.rng,
                                        kp_ref_buf=kp1_buf, kp_cur_buf=kp2_buf, defer_validity=True)
         prep = None
-        if np.linalg.norm(r["t"]) != 0:
+        iterative = c.scale_recovery.method == "iterative"
+        if np.linalg.norm(r["t"]) != 0 and not iterative:
             E_spec = np.eye(4)
             E_spec[:3, :3], E_spec[:3, 3:] = r["R"], r["t"]
             prep = self.scale_prepare(kp_ref, kp_cur, kp2_buf, np.linalg.inv(E_spec), cur.depth, n)
@@ -168,7 +169,7 @@ class FramePipeline:
         scale = None
         self.last.update(valid=r["valid"], inliers=r["inliers"], mode="E")
         if np.linalg.norm(E_pose[:3, 3]) != 0:
-            scale = self.scale_finish(prep)
+            scale = self.scale_iterative(cur, ref, kp_ref, kp_cur, E_pose) if iterative else self.scale_finish(prep)
             if scale != -1:
                 hybrid[:3, 3] = E_pose[:3, 3] * scale
         self.last["scale"] = scale
@@ -196,6 +197,27 @@ class FramePipeline:
         if nvalid > 10:
             return hostmath.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
         return -1
+
+    def scale_iterative(self, cur, ref, kp_ref, kp_cur, E_pose):
+        """E_tracker.py:509-569 with kp_selection.rigid_flow_kp: rigid-flow keypoint selection on the
+        device each round; the depth ratios / scale RANSAC as in the simple method."""
+        c = self.cfg
+        rk = c.kp_selection.rigid_flow_kp
+        T_21 = np.linalg.inv(E_pose)
+
+        def select(T, score_method):
+            return self.eng.rigid_flow_keypoints(ref.raw_depth, cur.fwd, cur.diff, T, self.K, rk.num_row, rk.num_col, rk.num_bestN,
+                                                 float(rk.rigid_flow_thre), float(rk.optical_flow_thre), score_method, want_best=False)
+
+        def find_scale(k_ref, k_cur):
+            k2 = self._buf("kcur_it", (k_cur.shape[0], 2), np.float64).upload(k_cur)
+            return self.scale_finish(self.scale_prepare(k_ref, k_cur, k2, T_21, cur.depth, k_cur.shape[0]))
+
+        o = tracking.scale_recovery_iterative(select, find_scale, E_pose, getattr(self, "prev_scale", 0), (kp_ref, kp_cur),
+                                              kp_src=c.scale_recovery.kp_src, score_method=c.scale_recovery.iterative_kp.score_method)
+        self.prev_scale = o["scale"]
+        self.last["rigid_flow_mask"] = o["rigid_flow_mask"]
+        return o["scale"]
 
     def scale_recovery(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
         """E_tracker.py:476-507,571-643 in one call (scale_prepare + scale_finish)."""

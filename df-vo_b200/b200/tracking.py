@@ -127,6 +127,49 @@ class Engine:
                                                       s["kp2"].ptr, None, st))
         return True, N, s["kp1"], s["kp2"]
 
+    def rigid_flow_keypoints(self, raw_depth_buf, flow_fwd_buf, flow_diff_buf, T, K, rows=10, cols=10, num_bestN=2000, rigid_thre=5.0,
+                             flow_thre=0.1, score_method="opt_flow", want_best=True):
+        """``EssTracker.kp_selection_good_depth`` (E_tracker.py:645-705) on the device: rigid-flow inconsistency map of the
+        reference depth under pose ``T`` (4x4, float64), then ``opt_rigid_flow_kp`` (kp_selection.py:203-324): the
+        'uniform' list per cell and (optionally) the 'best' set by ``score_method``.  Returns dict with the device map
+        ``rigid_flow_diff`` [H,W] and host float64 keypoints kp1/kp2_uniform [n,2], kp1/kp2_best [m,2] (canonical order:
+        cell-major; uniform in the reference's own order, best ascending by pixel index inside a cell)."""
+        cx, cy, fx, fy = K
+        quota = num_bestN // (rows * cols)
+        cells = rows * cols
+        if not hasattr(self, "_rf"):
+            mk = lambda: dict(idx=self.rt.empty((cells * quota,), np.int32), cc=self.rt.empty((cells,), np.int32),
+                              kp1=self.rt.empty((cells * quota, 2), np.float64), kp2=self.rt.empty((cells * quota, 2), np.float64),
+                              n=self.rt.empty((1,), np.int32))
+            self._rf = dict(map=self.rt.empty((self.H, self.W), np.float32), u=mk(), b=mk(), st=self.rt.empty((4,), np.int32))
+        r = self._rf
+        st = self.rt.stream_ptr()
+        Th = np.ascontiguousarray(np.asarray(T, np.float64).reshape(-1)[:16])
+        self.lib.check(self.lib.dfvo_rigid_flow_diff(raw_depth_buf.ptr, flow_fwd_buf.ptr, self.H, self.W, Th.ctypes.data_as(ctypes.c_void_p),
+                                                     fx, fy, cx, cy, r["map"].ptr, st))
+        u = r["u"]
+        self.lib.check(self.lib.dfvo_uniform_cells(r["map"].ptr, flow_diff_buf.ptr, self.H, self.W, rows, cols, num_bestN, rigid_thre,
+                                                   flow_thre, u["idx"].ptr, u["cc"].ptr, st))
+        self.lib.check(self.lib.dfvo_gather_keypoints(u["idx"].ptr, u["cc"].ptr, cells, quota, flow_fwd_buf.ptr, self.H, self.W,
+                                                      u["kp1"].ptr, u["kp2"].ptr, u["n"].ptr, st))
+        out = dict(rigid_flow_diff=r["map"])
+        if want_best:
+            b = r["b"]
+            if score_method == "rigid_flow":                      # score = rigid-flow inconsistency (kp_selection.py:266-269)
+                args = (r["map"].ptr, flow_diff_buf.ptr, rigid_thre, flow_thre)
+            else:
+                args = (flow_diff_buf.ptr, r["map"].ptr, flow_thre, rigid_thre)
+            self.lib.check(self.lib.dfvo_local_bestn(args[0], args[1], self.H, self.W, rows, cols, num_bestN, args[2], args[3],
+                                                     b["idx"].ptr, b["cc"].ptr, r["st"].ptr, st))
+            self.lib.check(self.lib.dfvo_gather_keypoints(b["idx"].ptr, b["cc"].ptr, cells, quota, flow_fwd_buf.ptr, self.H, self.W,
+                                                          b["kp1"].ptr, b["kp2"].ptr, b["n"].ptr, st))
+            nb = int(b["n"].numpy()[0])
+            out["kp1_best"], out["kp2_best"] = b["kp1"].numpy()[:nb], b["kp2"].numpy()[:nb]
+        nu = int(u["n"].numpy()[0])
+        assert nu != 0, "sampling threshold is too small."          # kp_selection.py:306
+        out["kp1_uniform"], out["kp2_uniform"] = u["kp1"].numpy()[:nu], u["kp2"].numpy()[:nu]
+        return out
+
     # ------------------------------------------------------------------ pose
     def _subset_table(self, n, max_iters=1000):
         key = (n, max_iters)
@@ -328,6 +371,27 @@ def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_
     if nvalid > 10:
         return hostmath.ransac_scale(ratio, min_samples, max_trials, stop_prob, thre, rng)
     return -1
+
+
+def scale_recovery_iterative(select, find_scale, E_pose, prev_scale, kp_best, kp_src="kp_best", score_method="rigid_flow"):
+    """``EssTracker.scale_recovery_iterative`` (E_tracker.py:509-569).  ``select(T, score_method)`` = the rigid-flow keypoint
+    selection under pose T (Engine.rigid_flow_keypoints bound to the frame's buffers), ``find_scale(kp_ref, kp_cur)`` =
+    find_scale_from_depth on the frame, ``kp_best`` = (kp_ref, kp_cur) of the best-N selection.  Up to five rounds; stops when
+    the scale moves by less than 0.001.  Returns dict(scale, cur_kp, ref_kp, rigid_flow_mask) -- the last round's."""
+    scale, delta = prev_scale, 0.001
+    out = {}
+    for _ in range(5):
+        P = np.array(E_pose, np.float64)
+        P[:3, 3] = P[:3, 3] * scale                               # rigid_flow_pose.t *= scale (:535)
+        sel = select(np.linalg.inv(P), score_method)              # ref_data['rigid_flow_pose'] = SE3(inv) (:537)
+        ref_kp, cur_kp = (sel["kp1_uniform"], sel["kp2_uniform"]) if kp_src == "kp_depth" else kp_best
+        new_scale = find_scale(ref_kp, cur_kp)
+        d = abs(new_scale - scale)
+        scale = new_scale
+        out = dict(scale=scale, cur_kp=sel["kp2_uniform"], ref_kp=sel["kp1_uniform"], rigid_flow_mask=sel["rigid_flow_diff"])
+        if d < delta:
+            break
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

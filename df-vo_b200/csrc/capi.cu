@@ -350,6 +350,24 @@ int dfvo_local_bestn(const float* flow_diff, const float* depth_diff, int H, int
   API_END
 }
 
+int dfvo_rigid_flow_diff(const float* raw_depth, const float* flow_fwd, int H, int W, const double* T_host, double fx, double fy, double cx,
+                         double cy, float* out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(raw_depth && flow_fwd && T_host && out && H > 0 && W > 0, DFVO_EINVAL, "dfvo_rigid_flow_diff args");
+  return rigid_flow_diff(raw_depth, flow_fwd, H, W, T_host, fx, fy, cx, cy, out, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_uniform_cells(const float* rigid_diff, const float* flow_diff, int H, int W, int rows, int cols, int num_bestN, float rigid_thre,
+                       float flow_thre, int32_t* idx_out, int32_t* cell_counts, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(rigid_diff && flow_diff && idx_out && cell_counts && H > 0 && W > 0 && rows > 0 && cols > 0, DFVO_EINVAL, "dfvo_uniform_cells args");
+  const int quota = num_bestN / (rows * cols);
+  DFVO_REQUIRE(quota > 0, DFVO_EINVAL, "dfvo_uniform_cells: num_bestN < rows*cols");
+  return uniform_cells(rigid_diff, flow_diff, H, W, rows, cols, quota, rigid_thre, flow_thre, idx_out, cell_counts, (cudaStream_t)stream);
+  API_END
+}
+
 size_t dfvo_bestn_workspace_bytes(int H, int W) { return bestn_workspace_bytes(H, W); }
 
 int dfvo_bestn(const float* flow_diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {

@@ -140,6 +140,12 @@ int local_bestn(const float* diff, const float* depth_diff, int H, int W, int ro
 int bestn(const float* diff, int H, int W, int N, int32_t* idx_out, void* workspace, size_t ws_bytes,
           cudaStream_t s);
 size_t bestn_workspace_bytes(int H, int W);
+// opt_rigid_flow_kp 'uniform' sampling per cell (kp_selection.py:277-284); output format of local_bestn
+int uniform_cells(const float* rigid_diff, const float* flow_diff, int H, int W, int rows, int cols, int n_best, float rigid_thre,
+                  float flow_thre, int32_t* idx_out, int32_t* cell_counts, cudaStream_t s);
+// |RigidFlow(depth, T, K) - flow| per pixel (E_tracker.py:666-691); T_host = row-major 3x4 (or 4x4) float64 on the host
+int rigid_flow_diff(const float* depth, const float* flow, int H, int W, const double* T_host, double fx, double fy, double cx, double cy,
+                    float* out, cudaStream_t s);
 int gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, cudaStream_t s);
 // idx: [ncells*n_best] slots (cell-major); cell_counts may be null (all slots valid, e.g. bestN with ncells=1)
 int gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int n_best, const float* flow_fwd, int H, int W,

@@ -137,6 +137,96 @@ k_local_bestn(const float* __restrict__ diff, const float* __restrict__ depth_di
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 'uniform' keypoints of opt_rigid_flow_kp (kp_selection.py:203-324, :277-284): inside each cell the pixels that pass both
+// masks (rigid-flow inconsistency < rigid_thre, forward-backward inconsistency < flow_thre) are enumerated in row-major
+// order of the cell slice (np.where), and every step-th of them is kept: step = int(n / k), k = min(n_best, n), positions
+// 0, step, 2 step, ... (the first k).  One 256-thread block per cell; each thread owns a contiguous run of the cell's
+// row-major order so that ranks come from one exclusive scan.  idx_out [cells * n_best] (-1 padded), cell_counts [cells].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+k_uniform_cells(const float* __restrict__ rigid_diff, const float* __restrict__ flow_diff, int H, int W, int rows, int cols, int n_best,
+                float rigid_thre, float flow_thre, int32_t* __restrict__ idx_out, int32_t* __restrict__ cell_counts) {
+  __shared__ int scratch[SEL_THREADS];
+  const int cell = blockIdx.x;
+  const CellGeom g = cell_geom(cell, H, W, rows, cols);
+  const int ch = g.y1 - g.y0, cw = g.x1 - g.x0;
+  const int npx = (ch > 0 && cw > 0) ? ch * cw : 0;
+  const int t = threadIdx.x;
+  const int chunk = (npx + SEL_THREADS - 1) / SEL_THREADS;
+  const int i0 = t * chunk < npx ? t * chunk : npx, i1 = i0 + chunk < npx ? i0 + chunk : npx;
+  auto valid = [&](int i) -> bool {
+    const size_t o = (size_t)(g.y0 + i / cw) * W + (g.x0 + i % cw);
+    return rigid_diff[o] < rigid_thre && flow_diff[o] < flow_thre;
+  };
+  int cnt = 0;
+  for (int i = i0; i < i1; ++i) cnt += valid(i) ? 1 : 0;
+  int n;
+  int rank = block_exclusive_scan(cnt, scratch, &n);
+  const int k = n < n_best ? n : n_best;
+  if (t == 0) cell_counts[cell] = k;
+  for (int i = t; i < n_best; i += SEL_THREADS) idx_out[cell * n_best + i] = -1;
+  __syncthreads();
+  if (k == 0) return;
+  const int step = n / k;
+  for (int i = i0; i < i1; ++i) {
+    if (!valid(i)) continue;
+    if (rank % step == 0 && rank / step < k) idx_out[cell * n_best + rank / step] = (g.y0 + i / cw) * W + (g.x0 + i % cw);
+    ++rank;
+  }
+}
+
+int uniform_cells(const float* rigid_diff, const float* flow_diff, int H, int W, int rows, int cols, int n_best, float rigid_thre,
+                  float flow_thre, int32_t* idx_out, int32_t* cell_counts, cudaStream_t s) {
+  DFVO_REQUIRE(rows > 0 && cols > 0 && n_best > 0 && rows * cols <= 65535, DFVO_EINVAL, "uniform_cells args");
+  DFVO_LAUNCH(k_uniform_cells, dim3(rows * cols), dim3(SEL_THREADS), 0, s, rigid_diff, flow_diff, H, W, rows, cols, n_best, rigid_thre,
+              flow_thre, idx_out, cell_counts);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rigid-flow inconsistency map (E_tracker.py:666-691): the RigidFlow layer (backproject the reference depth with K^-1,
+// transform by T, project with K, subtract the pixel grid; rigid_flow.py / backprojection.py / projection.py, float32,
+// eps = 1e-7 in the perspective division) and the norm of its difference to the optical flow, fused per pixel.
+// T, Kinv rows: float32 copies of the float64 inputs (torch.from_numpy(..).float()).
+// ------------------------------------------------------------------------------------------------
+struct RigidP { float T[12]; float ik[9]; float fx, fy, cx, cy; };
+
+__global__ void k_rigid_flow_diff(const float* __restrict__ depth, const float* __restrict__ flow, int H, int W, RigidP p,
+                                  float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const size_t i = (size_t)y * W + x, hw = (size_t)H * W;
+  const float fxp = (float)x, fyp = (float)y, d = depth[i];
+  // points = inv_K[:3,:3] @ (x, y, 1); points *= depth
+  const float X = d * (p.ik[0] * fxp + p.ik[1] * fyp + p.ik[2]);
+  const float Y = d * (p.ik[3] * fxp + p.ik[4] * fyp + p.ik[5]);
+  const float Z = d * (p.ik[6] * fxp + p.ik[7] * fyp + p.ik[8]);
+  // T @ (X, Y, Z, 1)
+  const float qx = p.T[0] * X + p.T[1] * Y + p.T[2] * Z + p.T[3];
+  const float qy = p.T[4] * X + p.T[5] * Y + p.T[6] * Z + p.T[7];
+  const float qz = p.T[8] * X + p.T[9] * Y + p.T[10] * Z + p.T[11];
+  // K[:3,:] @ q ; xy = uv / (w + eps)
+  const float ux = p.fx * qx + p.cx * qz, uy = p.fy * qy + p.cy * qz, uw = qz + 1e-7f;
+  const float rx = ux / uw - fxp, ry = uy / uw - fyp;
+  const float dx = rx - flow[i], dy = ry - flow[hw + i];
+  out[i] = sqrtf(dx * dx + dy * dy);
+}
+
+int rigid_flow_diff(const float* depth, const float* flow, int H, int W, const double* T_host, double fx, double fy, double cx, double cy,
+                    float* out, cudaStream_t s) {
+  RigidP p;
+  for (int i = 0; i < 12; ++i) p.T[i] = (float)T_host[i];
+  // inverse of [[fx,0,cx],[0,fy,cy],[0,0,1]] in float64 (Intrinsics.inv_mat = np.linalg.inv), then float32
+  const double ik[9] = {1.0 / fx, 0.0, -cx / fx, 0.0, 1.0 / fy, -cy / fy, 0.0, 0.0, 1.0};
+  for (int i = 0; i < 9; ++i) p.ik[i] = (float)ik[i];
+  p.fx = (float)fx; p.fy = (float)fy; p.cx = (float)cx; p.cy = (float)cy;
+  DFVO_LAUNCH(k_rigid_flow_diff, dim3(cdiv(W, 128), H), dim3(128), 0, s, depth, flow, H, W, p, out);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 __global__ void k_count_below(const float* __restrict__ diff, int n, float thre, int32_t* __restrict__ out) {
   __shared__ int scratch[SEL_THREADS];
   int c = 0;

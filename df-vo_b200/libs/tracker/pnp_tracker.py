@@ -13,7 +13,7 @@ class PnpTracker:
     def __init__(self, cfg, cam_intrinsics):
         self.cfg = cfg
         self.cam_intrinsics = cam_intrinsics
-        assert not cfg.kp_selection.rigid_flow_kp.enable, "rigid_flow_kp is a 'next' row (SURVEY.md 8f rank 1)"
+        self.K = [float(cam_intrinsics.cx), float(cam_intrinsics.cy), float(cam_intrinsics.fx), float(cam_intrinsics.fy)]
 
     def compute_pose_3d2d(self, kp1, kp2, depth_1, is_iterative):
         """pnp_tracker.py:45-125 -> {'pose': SE3 (view-2 -> view-1), 'kp1', 'kp2'}."""
@@ -36,4 +36,18 @@ class PnpTracker:
         return {"pose": pose, "kp1": kp1, "kp2": kp2}
 
     def compute_rigid_flow_kp(self, cur_data, ref_data, pose):
-        raise NotImplementedError("rigid-flow keypoints are a 'next' row (SURVEY.md 8f rank 1)")
+        """pnp_tracker.py:126-145 (kp_selection_good_depth, :148-212, is the same routine as the E-tracker's)."""
+        import copy
+        from libs.tracker.E_tracker import EssTracker
+        rigid_pose = copy.deepcopy(pose)
+        ref_data["rigid_flow_pose"] = SE3(rigid_pose.inv_pose)
+        k = EssTracker.kp_selection_good_depth(self, cur_data, ref_data, self.cfg.pnp_tracker.iterative_kp.score_method)
+        ref_data["kp_depth"], cur_data["kp_depth"] = k["kp1_depth"][0], k["kp2_depth"][0]
+        ref_data["kp_depth_uniform"], cur_data["kp_depth_uniform"] = k["kp1_depth_uniform"][0], k["kp2_depth_uniform"][0]
+        cur_data["rigid_flow_mask"] = k["rigid_flow_mask"]
+
+    _dev = None          # bound below (shared helper of the two trackers)
+
+
+from libs.tracker.E_tracker import EssTracker as _E          # noqa: E402
+PnpTracker._dev = _E._dev

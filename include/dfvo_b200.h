@@ -140,6 +140,18 @@ int dfvo_gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int nc
                           const float* flow_fwd, int H, int W, double* kp1, double* kp2, int32_t* n_out,
                           void* stream);
 
+/* ---- rigid-flow keypoints (EssTracker.kp_selection_good_depth, E_tracker.py:645-705) --------------------
+ * rigid_flow_diff [H,W] = | RigidFlow(raw_depth, T, K) - flow_fwd | (rigid_flow.py:38-60, float32): raw_depth [H,W] and
+ * flow_fwd [2,H,W] device fp32; T_host = the 4x4 (row-major, first 12 entries used) float64 pose on the HOST. */
+int dfvo_rigid_flow_diff(const float* raw_depth, const float* flow_fwd, int H, int W, const double* T_host, double fx, double fy,
+                         double cx, double cy, float* rigid_flow_diff, void* stream);
+/* opt_rigid_flow_kp (kp_selection.py:203-324), 'uniform' list: per cell every step-th pixel (row-major) that passes both masks.
+ * Same output format as dfvo_local_bestn.  The 'best' list is dfvo_local_bestn with (score map, threshold) = (flow_diff,
+ * optical_flow_thre) and (second mask map, threshold) = (rigid_flow_diff, rigid_flow_thre), or swapped for score_method
+ * 'rigid_flow'. */
+int dfvo_uniform_cells(const float* rigid_flow_diff, const float* flow_diff, int H, int W, int rows, int cols, int num_bestN,
+                       float rigid_flow_thre, float optical_flow_thre, int32_t* idx_out, int32_t* cell_counts, void* stream);
+
 /* depth[int(kp_y), int(kp_x)] for n keypoints (ops_3d.py:29, pnp_tracker.py:72-73); 0 outside the image. */
 int dfvo_gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, void* stream);
 

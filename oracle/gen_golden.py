@@ -236,7 +236,15 @@ def gen_cv_solvers():
     save("cv_solvers", **out)
 
 
-def gen_dfvo_driver():
+ITERATIVE_CFG = {"kp_selection.rigid_flow_kp.enable": True, "scale_recovery.method": "iterative"}      # ablation_scale_iterative.yml
+
+
+def gen_dfvo_driver_iter():
+    """gen_dfvo_driver with rigid-flow keypoints + iterative scale recovery (kitti_*_extend.yml)."""
+    gen_dfvo_driver(ITERATIVE_CFG, "dfvo_driver_iter_188x620")
+
+
+def gen_dfvo_driver(extra_cfg=None, name="dfvo_driver_188x620"):
     """The UNMODIFIED reference driver (libs/dfvo.py main loop) on a synthetic sequence with analytic
     network outputs injected at DeepModel.forward_flow / forward_depth; trackers, selection, GRIC, scale
     recovery and PnP fallback are the reference's own.  Poses are the golden for the drop-in test."""
@@ -245,7 +253,7 @@ def gen_dfvo_driver():
     with tempfile.TemporaryDirectory() as tmp:
         K = seqdata.write_sequence(os.path.join(tmp, "seqs"), n, h, w)
         cfg = build_cfg(h, w, **{"directory.img_seq_dir": os.path.join(tmp, "seqs"), "directory.result_dir": os.path.join(tmp, "res"),
-                                 "image.ext": "png", "seq": "00"})
+                                 "image.ext": "png", "seq": "00", **(extra_cfg or {})})
         os.makedirs(cfg.directory.result_dir, exist_ok=True)
         dm = shims.import_reference("libs.deep_models.deep_models")
         seqdata.patch_deep_model(dm.DeepModel, h, w, K)
@@ -255,13 +263,66 @@ def gen_dfvo_driver():
         np.random.seed(cfg.seed)                                    # apis/run.py:81-84
         torch.manual_seed(cfg.seed)
         poses = seqdata.run_driver(dfvo, cfg, n)
-    save("dfvo_driver_188x620", poses=poses, K=np.array(K), hw=np.array([h, w]))
+    save(name, poses=poses, K=np.array(K), hw=np.array([h, w]))
+
+
+def gen_rigid_flow_kp():
+    """EssTracker.kp_selection_good_depth (RigidFlow layer + opt_rigid_flow_kp), compute_rigid_flow_kp
+    and scale_recovery_iterative of the reference, with rigid_flow_kp enabled (kitti_*_extend.yml / ablation_scale_iterative.yml)."""
+    h, w = 376, 1241
+    cam = shims.import_reference("libs.geometry.camera_modules")
+    timer = shims.import_reference("libs.general.timer")
+    trk = shims.import_reference("libs.tracker")
+    ks = shims.import_reference("libs.matching.keypoint_sampler")
+    out = {}
+    cases = {"clean": dict(seed=51), "outliers": dict(seed=52, outlier_frac=0.3, diff_sigma=0.12)}
+    for kp_src in ("kp_best", "kp_depth"):
+        for name, kw in cases.items():
+            cfg = build_cfg(h, w, **{"kp_selection.rigid_flow_kp.enable": True, "scale_recovery.method": "iterative",
+                                     "scale_recovery.kp_src": kp_src})
+            K = cam.Intrinsics(synth.kitti_intrinsics(h, w))
+            ess = trk.EssTracker(cfg, K, timer.Timer())
+            fr = synth.analytic_frame(h=h, w=w, **kw)
+            depth_proc = fr["depth"] * ((fr["depth"] < 50) & (fr["depth"] > 0))
+            cur = {"depth": depth_proc.astype(np.float64), "raw_depth": fr["depth"]}
+            ref = {"flow": fr["flow_fwd"], "flow_diff": fr["flow_diff"], "raw_depth": fr["depth"], "depth": depth_proc.astype(np.float64)}
+            sampler = ks.KeypointSampler(cfg)
+            o = sampler.kp_selection(cur, ref)
+            lin = (o["kp1_best"][0][:, 1] * w + o["kp1_best"][0][:, 0]).astype(np.int64)
+            order = np.argsort(lin)                                    # canonical order (SURVEY H2)
+            ref["kp_best"], cur["kp_best"] = o["kp1_best"][0][order], o["kp2_best"][0][order]
+            np.random.seed(4869)
+            r = ess.compute_pose_2d2d(ref["kp_best"], cur["kp_best"], True)
+            E_pose = r["pose"]
+            key = "%s_%s" % (name, kp_src)
+            out[key + "_E_pose"] = E_pose.pose.copy()
+            so = ess.scale_recovery(cur, ref, E_pose, False)
+            out[key + "_scale"] = np.array(so["scale"])
+            out[key + "_prev_scale"] = np.array(ess.prev_scale)
+            out[key + "_rng_after"] = np.array(np.random.randint(0, 2 ** 31 - 1))
+            if kp_src == "kp_best":
+                # the maps / keypoint sets of the LAST iteration (pose scaled by the converged scale)
+                out[key + "_rigid_flow_pose"] = ref["rigid_flow_pose"].pose.copy()
+                out[key + "_rigid_flow_diff_s9"] = ref["rigid_flow_diff"][::9, ::9, 0].astype(np.float32)     # every 9th pixel
+                out[key + "_kp1_uniform"] = so["ref_kp_depth"].astype(np.int32)       # integer pixel grid
+                out[key + "_kp2_uniform"] = so["cur_kp_depth"].astype(np.float32)     # kp1 + float32 flow
+                # compute_rigid_flow_kp with the hybrid pose (dfvo.py:195-200): best + uniform sets
+                hyb = cam.SE3(E_pose.pose.copy())
+                hyb.t = E_pose.t * so["scale"]
+                ess.compute_rigid_flow_kp(cur, ref, hyb)
+                k1 = ref["kp_depth"]
+                lin = (k1[:, 1] * w + k1[:, 0]).astype(np.int64)
+                out[key + "_best_idx_sorted"] = np.sort(lin)
+                out[key + "_kp1_uniform_hyb"] = ref["kp_depth_uniform"].astype(np.int32)
+                out[key + "_rigid_flow_diff_hyb_s9"] = ref["rigid_flow_diff"][::9, ::9, 0].astype(np.float32)
+    save("rigid_flow_kp_376x1241", **out)
 
 
 GENERATORS = {
     "correlation": gen_correlation, "warp_fb": gen_warp_fb, "liteflownet": gen_liteflownet,
     "deep_models": gen_deep_models, "selection": gen_selection, "trackers": gen_trackers,
-    "cv_solvers": gen_cv_solvers, "dfvo_driver": gen_dfvo_driver,
+    "cv_solvers": gen_cv_solvers, "dfvo_driver": gen_dfvo_driver, "rigid_flow_kp": gen_rigid_flow_kp,
+    "dfvo_driver_iter": gen_dfvo_driver_iter,
 }
 
 if __name__ == "__main__":

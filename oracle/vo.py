@@ -296,3 +296,90 @@ def compute_pose_3d2d(kp1, kp2, depth_1, K, repeat=5, iters=100, reproj_thre=1, 
         pose[:3, :3] = cv2.Rodrigues(best_rt[0])[0]
         pose[:3, 3:] = best_rt[1]
     return np.linalg.inv(pose), kp1, kp2, best_inl
+
+
+# ----------------------------------------------------------------------------------------
+# rigid-flow keypoints + iterative scale recovery  
+# ----------------------------------------------------------------------------------------
+def rigid_flow_diff(raw_depth, flow, T, K):
+    """``EssTracker.kp_selection_good_depth`` up to ``rigid_flow_diff`` (E_tracker.py:666-691): the RigidFlow layer
+    (rigid_flow.py:38-60 = Backprojection backprojection.py:45-63, Transformation3D, Projection projection.py:31-52 with
+    normalized=False, PixToFlow layers.py:252-266) in the same torch float32 operations, then
+    ``np.linalg.norm(rigid_flow - flow, axis=0)``.  raw_depth [h,w] f32, flow [2,h,w] f32, T 4x4 (float64, cast to
+    float32 like ``torch.from_numpy(pose).float()``), K = [cx, cy, fx, fy].  Returns float32 [h,w]."""
+    import torch
+    h, w = raw_depth.shape
+    cx, cy, fx, fy = K
+    Km = np.eye(4); Km[:3, :3] = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    iKm = np.eye(4); iKm[:3, :3] = np.linalg.inv(Km[:3, :3])
+    Kt = torch.from_numpy(Km).float().unsqueeze(0)
+    iKt = torch.from_numpy(iKm).float().unsqueeze(0)
+    Tt = torch.from_numpy(np.asarray(T, np.float64)).float().unsqueeze(0)
+    depth = torch.from_numpy(np.ascontiguousarray(raw_depth)).float().unsqueeze(0).unsqueeze(0)
+    mesh = np.meshgrid(range(w), range(h), indexing="xy")
+    idc = torch.tensor(np.stack(mesh, axis=0).astype(np.float32))
+    ones = torch.ones(1, 1, h * w)
+    xy = torch.cat([torch.unsqueeze(torch.stack([idc[0].view(-1), idc[1].view(-1)], 0), 0), ones], 1)
+    points = torch.matmul(iKt[:, :3, :3], xy)
+    points = depth.view(1, 1, -1) * points
+    points = torch.cat([points, ones], 1)
+    points = torch.matmul(Tt, points)
+    p2 = torch.matmul(Kt[:, :3, :], points)
+    pix = p2[:, :2, :] / (p2[:, 2:3, :] + 1e-7)
+    pix = pix.view(1, 2, h, w).permute(0, 2, 3, 1)
+    rigid = (pix.permute(0, 3, 1, 2) - idc.unsqueeze(0)).numpy()[0]
+    return np.linalg.norm(rigid - flow, axis=0)
+
+
+def opt_rigid_flow_kp(rigid_diff, flow_diff, rows=10, cols=10, N=2000, rigid_thre=5, flow_thre=0.1, score_method="opt_flow"):
+    """``opt_rigid_flow_kp`` (kp_selection.py:203-324) reduced to what it decides: per cell the 'best' set (sorted linear
+    indices; ties at the k-th score by smaller index, like :func:`local_bestn_indices`) and the 'uniform' list (row-major
+    order of ``np.where(valid_mask)``, every ``step``-th, kp_selection.py:277-282).  Returns (best, uniform): lists of
+    int64 arrays of linear pixel indices per cell."""
+    h, w = rigid_diff.shape
+    n_best = math.floor(N / (rows * cols))
+    best, uniform = [], []
+    for (y0, y1, x0, x1) in cell_bounds(h, w, rows, cols):
+        rd, fd = rigid_diff[y0:y1, x0:x1], flow_diff[y0:y1, x0:x1]
+        valid = (rd < rigid_thre) & (fd < flow_thre)
+        ys, xs = np.where(valid)
+        lin = (ys + y0) * w + (xs + x0)
+        n = len(lin)
+        k = min(n_best, n)
+        if k > 0:
+            step = int(n / k)
+            uniform.append(lin[np.arange(0, n, step)[:k]].astype(np.int64))
+        else:
+            uniform.append(np.zeros(0, np.int64))
+        score = (rd if score_method == "rigid_flow" else fd)[valid]
+        order = np.lexsort((lin, score))[:k]
+        best.append(np.sort(lin[order]).astype(np.int64))
+    return best, uniform
+
+
+def scale_recovery_iterative(kp_ref_best, kp_cur_best, E_pose, depth2, raw_depth_ref, flow, flow_diff, K, prev_scale,
+                             kp_src="kp_best", score_method="rigid_flow", ransac=None):
+    """``EssTracker.scale_recovery_iterative`` (E_tracker.py:509-569): up to five rounds of [pose scaled by the current
+    scale -> inverse -> rigid-flow keypoint selection (kp_selection_good_depth, :645-705) -> find_scale_from_depth on
+    ``cfg.scale_recovery.kp_src`` keypoints]; stops when the scale moves by < 0.001.  E_pose: 4x4 (cur -> ref).
+    Returns dict(scale, kp1_uniform, kp2_uniform, rigid_flow_diff, rigid_flow_pose, rounds)."""
+    h, w = raw_depth_ref.shape
+    fd = np.asarray(flow_diff).reshape(h, w)
+    scale, delta = prev_scale, 0.001
+    out = {}
+    for it in range(5):
+        P = np.array(E_pose, np.float64)
+        P[:3, 3] = P[:3, 3] * scale
+        T = np.linalg.inv(P)                                       # SE3(rigid_flow_pose.inv_pose)
+        rd = rigid_flow_diff(raw_depth_ref, flow, T, K)
+        best, uniform = opt_rigid_flow_kp(rd, fd, score_method=score_method)
+        kp1u, kp2u = keypoints_from_indices(uniform, flow, w)
+        ref_kp, cur_kp = (kp1u, kp2u) if kp_src == "kp_depth" else (kp_ref_best, kp_cur_best)
+        new_scale = find_scale_from_depth(ref_kp, cur_kp, np.linalg.inv(np.array(E_pose, np.float64)), depth2, K, **(ransac or {}))
+        d = abs(new_scale - scale)
+        scale = new_scale
+        out = dict(scale=scale, kp1_uniform=kp1u, kp2_uniform=kp2u, rigid_flow_diff=rd, rigid_flow_pose=T, rounds=it + 1,
+                   best=best, uniform=uniform)
+        if d < delta:
+            break
+    return out

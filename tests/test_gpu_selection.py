@@ -69,3 +69,24 @@ def test_local_bestn_degenerate(dev_lib):
         if good:
             sel = idx.cpu().numpy()
             assert np.array_equal(sel, np.concatenate(cells))
+
+
+def _gpu_engine():
+    from b200 import runtime as rt_mod, tracking
+    rt = rt_mod.CudaRuntime(0)
+    rt_mod.set_runtime(rt)
+    return tracking.Engine(376, 1241, rt)
+
+
+@pytest.mark.parametrize("name", ["clean", "outliers"])
+def test_rigid_flow_map_and_selection(dev_lib, name):
+    """SURVEY 8f rank 1 on the device: rigid-flow inconsistency map vs the oracle, 'uniform' / 'best' keypoint lists of
+    opt_rigid_flow_kp bit-equal to the oracle and the reference golden (tests/rigid_cases.py)."""
+    import rigid_cases
+    assert rigid_cases.check_maps_and_selection(_gpu_engine(), name) < 5e-3
+
+
+@pytest.mark.parametrize("kp_src", ["kp_best", "kp_depth"])
+def test_iterative_scale_vs_reference(dev_lib, kp_src):
+    import rigid_cases
+    rigid_cases.check_iterative_scale(_gpu_engine(), "outliers", kp_src)

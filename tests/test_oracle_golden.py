@@ -120,3 +120,45 @@ def test_trackers_vs_reference(name):
     assert np.allclose(ppose, g[name + "_pnp_pose"], atol=1e-12)
     assert kp1.shape[0] == int(g[name + "_pnp_nkp"])
     assert np.random.randint(0, 2 ** 31 - 1) == int(g[name + "_rng_after"])      # RNG stream position (H8)
+
+
+def _rigid_case(name):
+    import synthdata
+    kw = {"clean": dict(seed=51), "outliers": dict(seed=52, outlier_frac=0.3, diff_sigma=0.12)}[name]
+    fr = synthdata.analytic_frame(h=376, w=1241, **kw)
+    depth_proc = (fr["depth"] * ((fr["depth"] < 50) & (fr["depth"] > 0))).astype(np.float64)
+    good, cells = vo.local_bestn_indices(fr["flow_diff"])
+    kp1, kp2 = vo.keypoints_from_indices([np.sort(np.concatenate(cells))], fr["flow_fwd"], 1241)
+    return fr, depth_proc, kp1, kp2
+
+
+@pytest.mark.parametrize("name", ["clean", "outliers"])
+@pytest.mark.parametrize("kp_src", ["kp_best", "kp_depth"])
+def test_rigid_flow_kp_iterative_scale_vs_reference(name, kp_src):
+    """oracle restatement of kp_selection_good_depth / opt_rigid_flow_kp / scale_recovery_iterative
+    against the reference classes (golden rigid_flow_kp_376x1241.npz): scale, RNG position, uniform keypoints, the
+    rigid-flow inconsistency map (sampled), the 'best' index set of compute_rigid_flow_kp."""
+    g = np.load(os.path.join(G, "rigid_flow_kp_376x1241.npz"))
+    K = synth.kitti_intrinsics(376, 1241)
+    fr, depth_proc, kp1, kp2 = _rigid_case(name)
+    key = "%s_%s" % (name, kp_src)
+    np.random.seed(4869)
+    r = vo.compute_pose_2d2d(kp1, kp2, K)
+    E = np.eye(4); E[:3, :3] = r["R"]; E[:3, 3:] = r["t"]
+    assert np.abs(E - g[key + "_E_pose"]).max() < 1e-12
+    o = vo.scale_recovery_iterative(kp1, kp2, E, depth_proc, fr["depth"], fr["flow_fwd"], fr["flow_diff"], K, 0, kp_src=kp_src)
+    assert abs(o["scale"] - float(g[key + "_scale"])) < 1e-12
+    assert int(np.random.randint(0, 2 ** 31 - 1)) == int(g[key + "_rng_after"])
+    if kp_src == "kp_best":
+        assert np.abs(o["rigid_flow_pose"] - g[key + "_rigid_flow_pose"]).max() < 1e-12
+        assert np.abs(o["rigid_flow_diff"][::9, ::9] - g[key + "_rigid_flow_diff_s9"]).max() < 1e-4      # torch float32 kernels may differ per CPU
+        assert np.array_equal(o["kp1_uniform"].astype(np.int32), g[key + "_kp1_uniform"])
+        assert np.array_equal(o["kp2_uniform"].astype(np.float32), g[key + "_kp2_uniform"])
+        # compute_rigid_flow_kp with the hybrid pose (E_tracker.py:421-440; e_tracker.iterative_kp.score_method)
+        hyb = E.copy(); hyb[:3, 3] *= o["scale"]
+        rd = vo.rigid_flow_diff(fr["depth"], fr["flow_fwd"], np.linalg.inv(hyb), K)
+        assert np.abs(rd[::9, ::9] - g[key + "_rigid_flow_diff_hyb_s9"]).max() < 1e-4
+        best, uniform = vo.opt_rigid_flow_kp(rd, fr["flow_diff"][:, :, 0], score_method="opt_flow")
+        assert np.array_equal(np.sort(np.concatenate(best)), g[key + "_best_idx_sorted"])
+        ku, _ = vo.keypoints_from_indices(uniform, fr["flow_fwd"], 1241)
+        assert np.array_equal(ku.astype(np.int32), g[key + "_kp1_uniform_hyb"])

@@ -12,13 +12,15 @@ from oracle import seqdata
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-def test_pipeline_matches_reference_driver(hostsim_lib, overlap):
+@pytest.mark.parametrize("overlap,iterative", [(False, False), (True, False), (True, True)])
+def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     from runtime import HostsimRuntime
     from b200 import pipeline, runtime as rt_mod
     rt_mod.set_runtime(HostsimRuntime(hostsim_lib))
-    g = np.load(os.path.join(G, "dfvo_driver_188x620.npz"))
+    # iterative: kp_selection.rigid_flow_kp + scale_recovery.method 'iterative' (SURVEY 8f rank 1), golden from the same
+    # unmodified driver under ablation_scale_iterative.yml's settings
+    g = np.load(os.path.join(G, "dfvo_driver_iter_188x620.npz" if iterative else "dfvo_driver_188x620.npz"))
     h, w = [int(v) for v in g["hw"]]
     K = list(g["K"])
     n = g["poses"].shape[0]
@@ -43,7 +45,12 @@ def test_pipeline_matches_reference_driver(hostsim_lib, overlap):
             return st
 
     np.random.seed(4869)
-    p = Injected(K, h, w, overlap=overlap)
+    from b200 import config
+    cfg = config.default_cfg(h, w)
+    if iterative:
+        cfg.kp_selection.rigid_flow_kp.enable = True
+        cfg.scale_recovery.method = "iterative"
+    p = Injected(K, h, w, cfg=cfg, overlap=overlap)
     modes = []
     if overlap:                          # two-stream mode: step(t) returns the pose of frame t-1, flush() the last one
         assert p.step(None) is None
