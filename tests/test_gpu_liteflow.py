@@ -62,3 +62,30 @@ def test_liteflow_full_size_properties(dev_lib):
     f4, b4, d4 = run_device(dev_lib, H, W, ref, cur, native.PREC_FP32, w)
     epe = np.sqrt(((f1 - f4) ** 2).sum(0))
     assert epe.mean() < 0.1, epe.mean()
+
+
+def test_liteflow_two_pairs_batched(dev_lib):
+    """Batched many-pairs mode (BASELINE configs[2] / SURVEY 8e): two independent pairs in one forward == each pair alone,
+    bit for bit (tcgen05 path, bf16)."""
+    H, W = 128, 416
+    imgs = [synth.value_noise_image(H, W, s) for s in (1, 2, 3, 4)]
+    w = synth.liteflownet_weights()
+
+    def run(pairs, frames):
+        ctx = native.Context(dev_lib)
+        ctx.load_weights(native.NET_LITEFLOWNET, w)
+        ctx.liteflow_build(H, W, pairs, native.PREC_BF16)
+        d = [torch.from_numpy(f).cuda() for f in frames]
+        fwd = torch.zeros((pairs, 2, H, W), dtype=torch.float32, device="cuda")
+        bwd = torch.zeros_like(fwd)
+        diff = torch.zeros((pairs, H, W), dtype=torch.float32, device="cuda")
+        ctx.liteflow_forward([t.data_ptr() for t in d], dptr(fwd), dptr(bwd), dptr(diff))
+        torch.cuda.synchronize()
+        out = fwd.cpu().numpy(), bwd.cpu().numpy(), diff.cpu().numpy()
+        ctx.close()
+        return out
+
+    f2, b2, d2 = run(2, imgs)
+    for p in range(2):
+        f1, b1, d1 = run(1, imgs[2 * p:2 * p + 2])
+        assert np.array_equal(f2[p], f1[0]) and np.array_equal(b2[p], b1[0]) and np.array_equal(d2[p], d1[0]), p

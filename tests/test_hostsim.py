@@ -97,6 +97,31 @@ def test_liteflownet_bf16_plumbing(hostsim_lib):
     assert epe.mean() < 0.05 and epe.max() < 0.5
 
 
+def test_liteflownet_two_pairs_batched(hostsim_lib):
+    """The batched many-pairs mode (BASELINE configs[2] / SURVEY 8e pair-level sharding): two independent frame pairs in one
+    forward (batch of 4 images, 'second image' = n ^ 1 inside each pair) give, pair by pair, exactly what each pair gives
+    alone -- same kernels, same per-image arithmetic."""
+    H, W = 64, 128
+    imgs = [synth.value_noise_image(H, W, s) for s in (1, 2, 3, 4)]
+    w = synth.liteflownet_weights()
+
+    def run(pairs, frames):
+        ctx = native.Context(hostsim_lib)
+        ctx.load_weights(native.NET_LITEFLOWNET, w)
+        ctx.liteflow_build(H, W, pairs, native.PREC_BF16)
+        fwd, bwd = np.zeros((pairs, 2, H, W), np.float32), np.zeros((pairs, 2, H, W), np.float32)
+        diff = np.zeros((pairs, H, W), np.float32)
+        ctx.liteflow_forward([f.ctypes.data for f in frames], hptr(fwd), hptr(bwd), hptr(diff))
+        ctx.close()
+        return fwd, bwd, diff
+
+    f2, b2, d2 = run(2, imgs)
+    for p in range(2):
+        f1, b1, d1 = run(1, imgs[2 * p:2 * p + 2])
+        assert np.array_equal(f2[p], f1[0]) and np.array_equal(b2[p], b1[0]) and np.array_equal(d2[p], d1[0]), p
+    assert np.abs(f2[0] - f2[1]).max() > 1e-3          # the two pairs really are different problems
+
+
 def test_monodepth2_vs_reference_golden(hostsim_lib):
     g = np.load(os.path.join(G, "deep_models_70x150.npz"))
     fh, fw = [int(x) for x in g["feed_hw"]]
