@@ -68,3 +68,34 @@ def test_pose_solver_edge_cases(hostsim_lib):
     assert np.isfinite(r["R"]).all() and np.isfinite(r["t"]).all() and r["inliers"].sum() < 60
     T, ninl = tracking.compute_pose_3d2d(eng, kp_ref, kp_cur, rs.uniform(5, 40, 400), K)
     assert np.isfinite(T).all() and ninl < 60
+
+
+def test_homography_edge_cases_vs_cv2(hostsim_lib):
+    """Degenerate ends of findHomography: all points collinear (getSubset never passes checkSubset: cv2 returns None, the
+    device reports found = 0), an exact 12-point homography, the 5-point minimum above the 4-point model, pure noise
+    (RANSAC runs all 2000 iterations and keeps a 5-inlier model) -- inlier counts / masks equal, H to 1e-8."""
+    import cv2
+    eng = _engine(hostsim_lib)
+    rt = eng.rt
+    rs = np.random.RandomState(0)
+
+    def run(p1, p2):
+        H, mask = cv2.findHomography(p1, p2, method=cv2.RANSAC, confidence=0.99, ransacReprojThreshold=1)
+        h = eng.homography_launch(rt.from_host(p1), rt.from_host(p2), p1.shape[0])
+        rt.wait_event(h["done"])
+        return H, mask, h["H"].numpy().reshape(3, 3), h["mask"].numpy(), h["info"].numpy()
+
+    x = np.linspace(10, 500, 50)
+    p1 = np.stack([x, 2 * x + 5], 1)
+    H, mask, Hd, md, info = run(p1, p1 + np.array([3.0, 1.0]))
+    assert H is None and info[0] == 0 and not md.any()
+    p1 = rs.uniform(0, 500, (12, 2))
+    Ht = np.array([[1.01, 0.02, 3], [-0.01, 0.99, -2], [1e-5, 2e-5, 1]])
+    q = (Ht @ np.c_[p1, np.ones(12)].T).T
+    p2 = q[:, :2] / q[:, 2:]
+    for n in (12, 5):
+        H, mask, Hd, md, info = run(p1[:n].copy(), p2[:n].copy())
+        assert info[0] == 1 and info[1] == n == int(mask.sum()) and np.abs(H - Hd).max() < 1e-8
+    p1, p2 = rs.uniform(0, 1000, (300, 2)), rs.uniform(0, 1000, (300, 2))
+    H, mask, Hd, md, info = run(p1, p2)
+    assert info[2] == 2000 and np.array_equal(mask.ravel(), md) and np.abs(H - Hd).max() / np.abs(H).max() < 1e-8
