@@ -207,7 +207,8 @@ def run_b200(args):
     K, frames, analytic = make_inputs(rank)
     np.random.seed(4869 + rank)
     overlap = os.environ.get("DFVO_OVERLAP", "1") != "0"
-    pipe = pipeline.FramePipeline(K, H, W, precision=native.PREC_BF16, runtime=rt, overlap=overlap)
+    inflight = int(os.environ.get("DFVO_INFLIGHT", "2")) if overlap else 1       # network engines in flight (measured: 2 > 1 by ~5 %)
+    pipe = pipeline.FramePipeline(K, H, W, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight)
     pipe.load_weights(flow_w, enc, dec)
 
     # device-resident copies of everything a step consumes
@@ -223,8 +224,8 @@ def run_b200(args):
         # analytic flow / depth over the (random-weight) network outputs: D2D, inside the timed region
         if st.fwd is not None:
             st.fwd.t.copy_(d_fwd[slot].t); st.bwd.t.copy_(d_bwd[slot].t); st.diff.t.copy_(d_diff[slot].t)
-        with pipe.depth_stream():                       # ordered after the depth network's own post-processing
-            tmp = pipe._buf("dsrc", (H, W), np.float32)
+        with pipe.depth_stream(st.id):                  # ordered after the depth network's own post-processing
+            tmp = pipe._buf("dsrc%d" % pipe.slot(st.id), (H, W), np.float32)
             tmp.t.copy_(d_depth[slot].t)
             pipe.eng.depth_post(tmp, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
 
@@ -234,22 +235,25 @@ def run_b200(args):
             st = pipeline.FrameState()
             st.id = fid
             s2 = pipe.slot(fid)
+            eng = pipe.engine_for(fid)
             if state["resident"]:
                 st.img = d_frames[slot]
-                feed = pipe.eng.depth_feed(st.img)
+                feed = eng.depth_feed(st.img)
             else:
                 st.img = pipe._buf("img%d" % s2, (H, W, 3), np.uint8)
                 st.img.t.copy_(pinned[slot], non_blocking=True)                       # H2D from pinned memory
-                feed = pipe.eng.depth_feed(st.img)                                     # PIL-exact LANCZOS + ToTensor on the device
+                pipe.mark_image_ready(st)
+                feed = eng.depth_feed(st.img)                                          # PIL-exact LANCZOS + ToTensor on the device
                 state["h2d"] += frames[slot].nbytes
             st.raw_depth = pipe._buf("raw%d" % s2, (H, W), np.float32)
             st.depth = pipe._buf("dep%d" % s2, (H, W), np.float32)
-            with pipe.depth_stream():                       # monodepth2 on its side stream (overlap mode), as FramePipeline.infer does
-                d = pipe.eng.depth(feed)
-                pipe.eng.depth_post(d, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
+            with pipe.depth_stream(fid):                    # monodepth2 on its side stream (overlap mode), as FramePipeline.infer does
+                d = eng.depth(feed)
+                eng.depth_post(d, pipe.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
             if pipe.ref is not None:
+                pipe.wait_reference_image()
                 st.fwd, st.bwd, st.diff = pipe.flow_slot(s2)
-                pipe.eng.flow([pipe.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
+                eng.flow([pipe.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
             inject(pipe, slot, st)
             return st
         return infer
@@ -285,7 +289,8 @@ def run_b200(args):
             pipe.step(None)               # overlap mode: networks of frame t on one stream while frame t-1 is tracked on the other
         if overlap:                       # the closing event waits for both of the pipeline's streams
             cs = torch.cuda.current_stream()
-            cs.wait_stream(pipe.s_net); cs.wait_stream(pipe.s_trk)
+            for sx in pipe.s_nets + pipe.s_depths + [pipe.s_trk]:
+                cs.wait_stream(sx)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -294,8 +299,10 @@ def run_b200(args):
             ms = multi.max_over_ranks(ms, device=torch.device("cuda", local_rank))
         return ms, lib.dfvo_launch_count() - l0
 
+    # warm-up: every network engine needs three forwards before it replays its CUDA graph (eager, capture, replay)
+    warmup = max(3 * inflight + 1, args.warmup)
     pipe.step(None)                                   # frame 0 (no flow yet)
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warmup):
         pipe.step(None)
     clocks = Clocks(local_rank)
     if rank == 0:
@@ -348,13 +355,14 @@ def run_b200(args):
         base = None          # profiling runs only (ncu): the driver's runs always include the baseline
     value = world * args.steps / (ms / 1e3)
     line = dict(
-        metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+        metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=warmup,
         ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="bf16 tensor-core convs (fp32 accumulate) + fp32 flow/selection + fp64 pose solvers",
         data="synthetic frames + seeded random-init weights; tracker stages fed analytic rigid-scene flow/depth (see bench.py docstring)",
         config=dict(workload=WORKLOAD, image=[H, W], flow_net_input=[352, 1216], depth_feed=[FEED_H, FEED_W], keypoints=2000,
                     ransac_repeats=5, sequences_per_gpu=1, parallelism="1 sequence per GPU, NCCL weight broadcast only",
-                    streams="2 (networks of frame t overlap the tracker of frame t-1; K steps = K frames tracked)" if overlap else "1 (in order)",
+                    streams=("%d network engine(s) on their own streams, tracker %d frame(s) behind; K steps = K frames inferred and K tracked"
+                             % (inflight, inflight)) if overlap else "1 (in order)",
                     l2="per-frame activation working set (>1 GB written/read per frame) exceeds the 126 MB L2; no explicit flush",
                     last_frame_branch=modes["last"]),
         clocks=clk,

@@ -21,10 +21,10 @@ from . import runtime as rt_mod
 class FrameState:
     """Device buffers of one frame: image, depths and (for every frame but the first) the flows of the pair
     (previous frame -> this frame).  `ready` = event recorded after the frame's networks (two-stream mode)."""
-    __slots__ = ("id", "img", "depth", "raw_depth", "fwd", "bwd", "diff", "ready")
+    __slots__ = ("id", "img", "depth", "raw_depth", "fwd", "bwd", "diff", "ready", "img_ready")
 
     def __init__(self):
-        self.fwd = self.bwd = self.diff = self.ready = None
+        self.fwd = self.bwd = self.diff = self.ready = self.img_ready = None
 
 
 class _ForkJoin:
@@ -47,14 +47,17 @@ class _ForkJoin:
 
 class FramePipeline:
     def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
-                 overlap=False, engine=None):
+                 overlap=False, engine=None, inflight=1):
         """K = [cx, cy, fx, fy].
 
         overlap=False: ``step(img)`` returns the pose of ``img`` (one stream, in order).
         overlap=True : two CUDA streams; ``step(img)`` enqueues the networks of ``img`` and then tracks the
         PREVIOUS frame while the GPU runs them, returning the previous frame's pose (``None`` on the first
         call); ``flush()`` tracks the last frame.  Same arithmetic, same RNG order, same poses -- frames only
-        depend on each other through the reference image / depth, which are triple-buffered here."""
+        depend on each other through the reference image / depth, which are triple-buffered here.
+        inflight=2 (overlap mode only): a second, independent network engine, so the networks of two consecutive frames run
+        concurrently (their small-grid phases fill each other's idle SMs) and tracking lags by two frames: ``step``
+        returns the pose of frame t-2, ``flush()`` the remaining ones (a list).  Same poses again."""
         self.cfg = cfg or cfg_mod.default_cfg(height, width)
         self.K = [float(v) for v in K]
         self.H, self.W = height, width
@@ -67,21 +70,31 @@ class FramePipeline:
         self.global_pose = np.eye(4)
         self.motion = np.eye(4)
         self.poses = {}
+        self.modes = {}              # frame id -> branch taken by the tracker ('E', 'PnP', 'const'; None for the first frame)
         self.last = {}
         self._bufs = {}
         self.overlap = bool(overlap)
-        self.nslots = 3 if self.overlap else 2
-        self.pending = None          # overlap mode: frame whose networks are enqueued but which is not tracked yet
+        self.inflight = int(inflight) if self.overlap else 1
+        assert self.inflight in (1, 2)
+        self.nslots = self.inflight + 2 if self.overlap else 2
+        self.pending = []            # overlap mode: frames whose networks are enqueued but which are not tracked yet
         self.trk_ref = None          # overlap mode: the tracker's reference frame (self.ref is the networks')
+        self.engs = [self.eng] + [tracking.Engine(height, width, self.rt) for _ in range(self.inflight - 1)]
         if self.overlap:
-            self.s_net = self.rt.new_stream()                      # LiteFlowNet
-            self.s_depth = self.rt.new_stream()                    # monodepth2: independent of the flow network, its small
-            self.s_trk = self.rt.new_stream(high_priority=True)    # launches fill the SMs LiteFlowNet's coarse levels leave idle
+            self.s_nets = [self.rt.new_stream() for _ in self.engs]      # LiteFlowNet (per engine)
+            self.s_depths = [self.rt.new_stream() for _ in self.engs]    # monodepth2: independent of the flow network, its small
+            self.s_net, self.s_depth = self.s_nets[0], self.s_depths[0]  # launches fill the SMs LiteFlowNet's coarse levels leave idle
+            self.s_trk = self.rt.new_stream(high_priority=True)
 
     # ------------------------------------------------------------------ setup
     def load_weights(self, flow_weights, depth_enc, depth_dec):
-        self.eng.build_flow(flow_weights, pairs=1, precision=self.precision)
-        self.eng.build_depth(depth_enc, depth_dec, precision=self.precision, dataset=self.cfg.dataset)
+        for e in self.engs:
+            e.build_flow(flow_weights, pairs=1, precision=self.precision)
+            e.build_depth(depth_enc, depth_dec, precision=self.precision, dataset=self.cfg.dataset)
+
+    def engine_for(self, fid):
+        """The network engine of frame `fid` (tracking always uses engine 0's solvers)."""
+        return self.engs[fid % len(self.engs)]
 
     def slot(self, fid):
         """Buffer slot of frame `fid` (images / depths / flows are multi-buffered so a reference frame stays valid)."""
@@ -107,26 +120,40 @@ class FramePipeline:
         st.id = fid
         # multi-buffer images / depths / flows so the previous frame's stay valid as 'ref'
         slot = self.slot(fid)
+        eng = self.engine_for(fid)
         st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
+        self.mark_image_ready(st)
         st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
         st.depth = self._buf("dep%d" % slot, (self.H, self.W), np.float32)
-        with self.depth_stream():
-            d = self.eng.depth(self.eng.depth_feed(st.img))              # LANCZOS resize + ToTensor on the device
+        with self.depth_stream(fid):
+            d = eng.depth(eng.depth_feed(st.img))                        # LANCZOS resize + ToTensor on the device
             c = self.cfg
-            self.eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
+            eng.depth_post(d, c.crop.depth_crop, float(c.depth.min_depth), float(c.depth.max_depth), st.raw_depth, st.depth)
         if self.ref is not None:
+            self.wait_reference_image()
             st.fwd, st.bwd, st.diff = self.flow_slot(slot)
-            self.eng.flow([self.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
+            eng.flow([self.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
         return st
 
-    def depth_stream(self):
+    def mark_image_ready(self, st):
+        """Called by infer() right after the frame's image is on the device (its upload was enqueued on this frame's
+        network stream); with two engines the next frame's flow network, on the other stream, waits for it."""
+        if self.overlap and self.inflight > 1:
+            st.img_ready = self.rt.record_event()
+
+    def wait_reference_image(self):
+        if self.overlap and self.inflight > 1 and self.ref is not None and self.ref.img_ready is not None:
+            self.rt.wait_event(self.ref.img_ready)
+
+    def depth_stream(self, fid=None):
         """Context for the depth network of the frame being inferred: in overlap mode a side stream forked from the
         network stream (after the image upload) and joined back into it by ``step`` -- monodepth2 and LiteFlowNet share
         only the input image; in-order mode: the current stream."""
         import contextlib
         if not self.overlap:
             return contextlib.nullcontext()
-        return _ForkJoin(self.rt, self.s_depth, self)
+        fid = self.stage - 1 if fid is None else fid                   # the frame being inferred
+        return _ForkJoin(self.rt, self.s_depths[fid % len(self.engs)], self)
 
     def flow_slot(self, slot):
         """The (fwd, bwd, diff) output buffers of buffer slot `slot`."""
@@ -254,6 +281,7 @@ class FramePipeline:
             self.global_pose[:3, 3:] = self.global_pose[:3, :3] @ rel[:3, 3:] + self.global_pose[:3, 3:]
             self.global_pose[:3, :3] = self.global_pose[:3, :3] @ rel[:3, :3]
         self.poses[fid] = self.global_pose.copy()
+        self.modes[fid] = self.last.get("mode") if ref is not None else None
         return self.poses[fid]
 
     def step(self, img):
@@ -266,27 +294,31 @@ class FramePipeline:
             pose = self._advance(cur, self.ref)
             self.ref = cur
             return pose
-        with self.rt.on_stream(self.s_net):
+        with self.rt.on_stream(self.s_nets[fid % len(self.engs)]):
             self._depth_done = None
             cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
             if self._depth_done is not None:                # join the depth side stream
                 self.rt.wait_event(self._depth_done)
             cur.ready = self.rt.record_event()
         self.ref = cur
-        pose = self._track_pending()
-        self.pending = cur
+        pose = self._track_oldest() if len(self.pending) >= self.inflight else None
+        self.pending.append(cur)
         return pose
 
-    def _track_pending(self):
-        if self.pending is None:
-            return None
+    def _track_oldest(self):
+        nxt = self.pending.pop(0)
         with self.rt.on_stream(self.s_trk):
-            self.rt.wait_event(self.pending.ready)
-            pose = self._advance(self.pending, self.trk_ref)
-        self.trk_ref = self.pending
-        self.pending = None
+            self.rt.wait_event(nxt.ready)
+            pose = self._advance(nxt, self.trk_ref)
+        self.trk_ref = nxt
         return pose
 
     def flush(self):
-        """Overlap mode: track the frame whose networks are still in flight; returns its pose (None if none)."""
-        return self._track_pending() if self.overlap else None
+        """Overlap mode: track the frames whose networks are still in flight; returns the last pose for inflight=1 (None if
+        there is none), the list of remaining poses for inflight=2."""
+        poses = []
+        while self.overlap and self.pending:
+            poses.append(self._track_oldest())
+        if self.inflight > 1:
+            return poses
+        return poses[-1] if poses else None

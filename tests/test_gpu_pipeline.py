@@ -10,11 +10,11 @@ from b200 import native, pipeline, runtime as rt_mod
 pytestmark = pytest.mark.gpu
 
 
-def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w):
+def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1):
     rt = rt_mod.CudaRuntime(0)
     rt_mod.set_runtime(rt)
     np.random.seed(4869)
-    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap)
+    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight)
     p.load_weights(flow_w, enc, dec)
     base_infer = p.infer
     net_flows = {}
@@ -27,9 +27,9 @@ def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w):
         if st.fwd is not None:
             net_flows[fid] = (st.fwd.t.clone(), st.diff.t.clone())
             st.fwd.upload(a["fwd"][None]); st.bwd.upload(a["bwd"][None]); st.diff.upload(a["diff"][None, :, :, 0])
-        with p.depth_stream():                    # same stream as (hence ordered after) the depth network
+        with p.depth_stream(fid):                 # same stream as (hence ordered after) the depth network
             net_flows.setdefault("depth", {})[fid] = st.raw_depth.t.clone()
-            d = p._buf("dsrc", (h, w), np.float32).upload(a["depth"])
+            d = p._buf("dsrc%d" % p.slot(fid), (h, w), np.float32).upload(a["depth"])
             p.eng.depth_post(d, p.cfg.crop.depth_crop, 0.0, 50.0, st.raw_depth, st.depth)
         return st
 
@@ -40,8 +40,9 @@ def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w):
         if r is not None:
             poses.append(r.copy())
     last = p.flush()
-    if last is not None:
-        poses.append(last.copy())
+    for q in (last if isinstance(last, list) else [last]):
+        if q is not None:
+            poses.append(q.copy())
     rt.torch.cuda.synchronize()
     return poses, net_flows, [p.poses[i] for i in sorted(p.poses)]
 
@@ -56,10 +57,14 @@ def test_overlap_pipeline_equals_in_order(dev_lib):
     analytic = [synthdata.frame_inputs(i, h, w, K, "normal") for i in range(n)]
     pa, fa, all_a = run(False, frames, analytic, K, h, w, enc, dec, flow_w)
     pb, fb, all_b = run(True, frames, analytic, K, h, w, enc, dec, flow_w)
-    assert len(pa) == n and len(pb) == n
+    pc, fc, all_c = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2)       # two network engines in flight
+    assert len(pa) == n and len(pb) == n and len(pc) == n
     for i in range(1, n):
         assert (fa[i][0] == fb[i][0]).all() and (fa[i][1] == fb[i][1]).all(), "network flow of frame %d differs" % i
         assert (fa["depth"][i] == fb["depth"][i]).all(), "network depth of frame %d differs" % i
+    for i in range(1, n):
+        assert (fa[i][0] == fc[i][0]).all() and (fa["depth"][i] == fc["depth"][i]).all(), "two-engine networks of frame %d differ" % i
     for i in range(n):
         assert np.array_equal(all_a[i], all_b[i]), "pose of frame %d differs between in-order and overlapped pipeline" % i
+        assert np.array_equal(all_a[i], all_c[i]), "pose of frame %d differs with two frames in flight" % i
     assert not np.allclose(all_a[-1], np.eye(4))

@@ -50,17 +50,29 @@ def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative):
     if iterative:
         cfg.kp_selection.rigid_flow_kp.enable = True
         cfg.scale_recovery.method = "iterative"
-    p = Injected(K, h, w, cfg=cfg, overlap=overlap)
+    inflight = 2 if iterative else 1     # the (True, True) case also runs two frames in flight (tracker two frames behind)
+    p = Injected(K, h, w, cfg=cfg, overlap=overlap, inflight=inflight)
     modes = []
-    if overlap:                          # two-stream mode: step(t) returns the pose of frame t-1, flush() the last one
-        assert p.step(None) is None
+    if overlap:                          # two-stream mode: step(t) returns the pose of frame t-inflight, flush() the rest
+        for _ in range(inflight):
+            assert p.step(None) is None
+    tail = []
     for t in range(n):
-        pose = (p.step(None) if t + 1 < n else p.flush()) if overlap else p.step(None)
+        if not overlap:
+            pose = p.step(None)
+        elif t + inflight < n:
+            pose = p.step(None)
+        else:
+            if not tail:
+                f = p.flush()
+                tail = f if isinstance(f, list) else [f]
+            pose = tail.pop(0)
         modes.append(p.last.get("mode"))
         dR = pose[:3, :3].T @ g["poses"][t][:3, :3]
         ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
         dt = np.linalg.norm(pose[:3, 3] - g["poses"][t][:3, 3])
         assert ang < 1e-6 and dt < 1e-6 * max(1.0, np.linalg.norm(g["poses"][t][:3, 3])), (t, ang, dt)
+    modes = list(p.modes.values())
     assert "PnP" in modes and "const" in modes and "E" in modes      # all three branches of dfvo.py:121-262 exercised
 
 
