@@ -349,10 +349,10 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_tc_traffic.json")))["dram_bytes_per_frame"]
     except Exception:
         pass
-    if args.cpu_frames > 0:
+    if args.cpu_frames > 0 and world == 1:
         base, cpu_poses = cpu_baseline(args.cpu_frames, K, frames, analytic)
     else:
-        base = None          # profiling runs only (ncu): the driver's runs always include the baseline
+        base = None          # the CPU baseline is reported at N = 1 only (and skipped in ncu profiling runs)
     value = world * args.steps / (ms / 1e3)
     line = dict(
         metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=warmup,
