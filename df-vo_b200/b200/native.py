@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 LIB_PATH = os.path.join(CSRC, "libdfvo_b200.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
+PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 NET_LITEFLOWNET, NET_MONODEPTH2 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 
@@ -34,10 +35,16 @@ SIGNATURES = {
     "dfvo_destroy": (c_int, [c_void_p]),
     "dfvo_load_weight": (c_int, [c_void_p, c_int, c_char_p, c_void_p, ctypes.POINTER(ctypes.c_int64), c_int]),
     "dfvo_liteflow_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
-    "dfvo_liteflow_forward": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dfvo_liteflow_forward": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_liteflow_level_flow": (c_int, [c_void_p, c_int, c_void_p]),
     "dfvo_liteflow_geometry": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "dfvo_correlation": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "dfvo_correlation_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "dfvo_backproject": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dfvo_transform3d": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
+    "dfvo_project": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dfvo_reproject": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dfvo_rigid_flow": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "dfvo_fb_consistency": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dfvo_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
@@ -53,7 +60,7 @@ SIGNATURES = {
     "dfvo_monodepth2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_lanczos_resize_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dfvo_depth_post": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+    "dfvo_depth_post": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
     "dfvo_gather_depth": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dfvo_five_point": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -70,6 +77,7 @@ SIGNATURES = {
                                 c_double, c_double, c_double, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "dfvo_cv_subset_stream_host": (c_int, [c_int, c_int, c_int, c_void_p]),
     "dfvo_triangulate_depth": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dfvo_triangulate_points": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_recover_pose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
 }
@@ -149,7 +157,7 @@ class Context:
 
     def liteflow_forward(self, img_ptrs, flow_fwd, flow_bwd, flow_diff, stream=0):
         arr = (c_void_p * len(img_ptrs))(*img_ptrs)
-        self.lib.check(self.lib.dfvo_liteflow_forward(self.h, arr, flow_fwd, flow_bwd, flow_diff, stream))
+        self.lib.check(self.lib.dfvo_liteflow_forward(self.h, arr, len(img_ptrs), flow_fwd, flow_bwd, flow_diff, stream))
 
 
 _lib = None

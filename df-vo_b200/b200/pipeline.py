@@ -100,11 +100,21 @@ class FramePipeline:
         """Buffer slot of frame `fid` (images / depths / flows are multi-buffered so a reference frame stays valid)."""
         return fid % self.nslots
 
-    def _buf(self, name, shape, dtype):
+    def _buf(self, name, shape, dtype, cap0=None):
+        """Named device buffer, grow-only: allocated for a capacity (`cap0` rows if given) and handed out as an exactly-shaped
+        view, so per-frame keypoint counts never reallocate."""
+        shape = tuple(int(d) for d in shape)
+        n = int(np.prod(shape)) if shape else 1
         b = self._bufs.get(name)
-        if b is None or b.shape != tuple(shape):
-            b = self._bufs[name] = self.rt.empty(shape, dtype)
-        return b
+        if b is None or b.size < n or b.dtype != np.dtype(dtype):
+            cap = n
+            if cap0 is not None and shape:
+                rows = int(cap0)
+                while rows < shape[0]:
+                    rows *= 2
+                cap = rows * (n // max(shape[0], 1))
+            b = self._bufs[name] = self.rt.empty((max(cap, 1),), dtype)
+        return b.view(shape)
 
     # ------------------------------------------------------------------ per-frame stages
     def depth_feed_host(self, img):
@@ -210,10 +220,10 @@ class FramePipeline:
         """E_tracker.py:476-507,571-616: device triangulation + device gather of the CNN depth at the keypoints ->
         (depth ratios, number of valid ones).  Consumes no host RNG."""
         cx, cy, fx, fy = self.K
-        k1 = self._buf("k1n", (n, 2), np.float64).upload((kp_ref - np.array([cx, cy])) / np.array([fx, fy]))
-        k2 = self._buf("k2n", (n, 2), np.float64).upload((kp_cur - np.array([cx, cy])) / np.array([fx, fy]))
+        k1 = self._buf("k1n", (n, 2), np.float64, self.eng.kp_capacity).upload((kp_ref - np.array([cx, cy])) / np.array([fx, fy]))
+        k2 = self._buf("k2n", (n, 2), np.float64, self.eng.kp_capacity).upload((kp_cur - np.array([cx, cy])) / np.array([fx, fy]))
         z = self.eng.triangulate_depth(k1, k2, n, T_21)
-        dk = self._buf("dkp", (n,), np.float32)
+        dk = self._buf("dkp", (n,), np.float32, self.eng.kp_capacity)
         self.rt.lib.check(self.rt.lib.dfvo_gather_depth(depth_buf.ptr, self.H, self.W, kp_cur_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
         return hostmath.last_writer_depth_ratio_sparse(kp_cur, z, dk.numpy(), self.H, self.W)
 
@@ -237,7 +247,7 @@ class FramePipeline:
                                                  float(rk.rigid_flow_thre), float(rk.optical_flow_thre), score_method, want_best=False)
 
         def find_scale(k_ref, k_cur):
-            k2 = self._buf("kcur_it", (k_cur.shape[0], 2), np.float64).upload(k_cur)
+            k2 = self._buf("kcur_it", (k_cur.shape[0], 2), np.float64, self.eng.kp_capacity).upload(k_cur)
             return self.scale_finish(self.scale_prepare(k_ref, k_cur, k2, T_21, cur.depth, k_cur.shape[0]))
 
         o = tracking.scale_recovery_iterative(select, find_scale, E_pose, getattr(self, "prev_scale", 0), (kp_ref, kp_cur),
@@ -255,7 +265,7 @@ class FramePipeline:
         at the keypoints gathered on the device, the five solvePnPRansac repeats + refits on the device (csrc/pnp.cu)."""
         c = self.cfg
         ref = ref or self.ref
-        dk = self._buf("dkp", (n,), np.float32)
+        dk = self._buf("dkp", (n,), np.float32, self.eng.kp_capacity)
         self.rt.lib.check(self.rt.lib.dfvo_gather_depth(ref.depth.ptr, self.H, self.W, kp_ref_buf.ptr, n, dk.ptr, self.rt.stream_ptr()))
         d_all = dk.numpy().astype(np.float64)
         keep = (kp_cur[:, 0] >= 0) & (kp_cur[:, 0] < self.W) & (kp_cur[:, 1] >= 0) & (kp_cur[:, 1] < self.H)

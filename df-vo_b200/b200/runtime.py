@@ -33,6 +33,22 @@ class Buf:
         self.rt.upload(self, arr)
         return self
 
+    def view(self, shape):
+        """A Buf over the first prod(shape) elements of this buffer (no copy): capacity-allocated workspaces hand out
+        exactly-shaped views so a changing keypoint count never reallocates."""
+        return self.rt.view(self, shape)
+
+    def clone(self):
+        """Device-side copy (same stream as the producer: ordered after it)."""
+        return self.rt.clone(self)
+
+    @property
+    def size(self):
+        n = 1
+        for d in self.shape:
+            n *= int(d)
+        return n
+
 
 _TORCH_DTYPES = None
 
@@ -83,6 +99,13 @@ class CudaRuntime:
 
     def to_host(self, buf):
         return buf.t.cpu().numpy()
+
+    def view(self, buf, shape):
+        n = int(np.prod(shape)) if len(shape) else 1
+        return Buf(buf.t.reshape(-1)[:n].view(tuple(shape)), shape, buf.dtype, self)
+
+    def clone(self, buf):
+        return Buf(buf.t.clone(), buf.shape, buf.dtype, self)
 
     def ptr_of(self, t):
         return ctypes.c_void_p(t.data_ptr())

@@ -5,6 +5,7 @@ Every numeric step is a call into the C ABI (``include/dfvo_b200.h``); this modu
 the order of calls and the few host-side decisions the reference makes on the host as well (RNG draws,
 majority vote, sentinels).  There is no CPU implementation of the kernels here.
 """
+import collections
 import ctypes
 
 import numpy as np
@@ -30,8 +31,14 @@ class Engine:
         self.H, self.W = int(height), int(width)
         self.flow_ready = False
         self.depth_ready = False
-        self._subsets = {}          # N -> device table of OpenCV's 5-point subset stream
-        self._ess_ws = {}
+        # Workspaces are allocated once per configuration for a CAPACITY of keypoints (grown geometrically if a frame ever
+        # exceeds it) and handed out as exactly-shaped views: with local_bestN the keypoint count changes almost every
+        # frame, and a per-count cache would grow without bound and put cudaMalloc into the tracked region.
+        self._subsets = collections.OrderedDict()    # (N, iters) -> device table of OpenCV's subset stream; LRU-bounded
+        self._subsets_cap = 256
+        self._ess_ws, self._h_ws, self._pnp_ws = {}, {}, {}
+        self._sel, self._bsel, self._rf = {}, {}, {}
+        self.kp_capacity = 2048
 
     # ------------------------------------------------------------------ networks
     def build_flow(self, weights, pairs=1, precision=native.PREC_BF16):
@@ -101,11 +108,12 @@ class Engine:
         """local_bestN (kp_selection.py:74-200) + keypoint gather.  Returns (good, n, kp1, kp2, mask-less)
         with kp buffers float64 [num_bestN, 2] (first n rows valid).  One small D2H (status)."""
         quota = num_bestN // (rows * cols)
-        if not hasattr(self, "_sel"):
-            self._sel = dict(idx=self.rt.empty((rows * cols * quota,), np.int32), cc=self.rt.empty((rows * cols,), np.int32),
-                             st=self.rt.empty((4,), np.int32), kp1=self.rt.empty((rows * cols * quota, 2), np.float64),
-                             kp2=self.rt.empty((rows * cols * quota, 2), np.float64), n=self.rt.empty((1,), np.int32))
-        s = self._sel
+        key = (rows, cols, quota)
+        if key not in self._sel:
+            self._sel[key] = dict(idx=self.rt.empty((rows * cols * quota,), np.int32), cc=self.rt.empty((rows * cols,), np.int32),
+                                  st=self.rt.empty((4,), np.int32), kp1=self.rt.empty((rows * cols * quota, 2), np.float64),
+                                  kp2=self.rt.empty((rows * cols * quota, 2), np.float64), n=self.rt.empty((1,), np.int32))
+        s = self._sel[key]
         st = self.rt.stream_ptr()
         self.lib.check(self.lib.dfvo_local_bestn(diff_buf.ptr, depth_diff_buf.ptr if depth_diff_buf else None, self.H, self.W,
                                                  rows, cols, num_bestN, thre, depth_thre, s["idx"].ptr, s["cc"].ptr, s["st"].ptr, st))
@@ -116,11 +124,11 @@ class Engine:
 
     def select_bestn(self, diff_buf, flow_fwd_buf, N):
         """bestN_flow_kp (kp_selection.py:33-71)."""
-        if not hasattr(self, "_bsel"):
+        if N not in self._bsel:
             nb = int(self.lib.dfvo_bestn_workspace_bytes(self.H, self.W))
-            self._bsel = dict(idx=self.rt.empty((N,), np.int32), ws=self.rt.empty((nb,), np.uint8),
-                              kp1=self.rt.empty((N, 2), np.float64), kp2=self.rt.empty((N, 2), np.float64))
-        s = self._bsel
+            self._bsel[N] = dict(idx=self.rt.empty((N,), np.int32), ws=self.rt.empty((nb,), np.uint8),
+                                 kp1=self.rt.empty((N, 2), np.float64), kp2=self.rt.empty((N, 2), np.float64))
+        s = self._bsel[N]
         st = self.rt.stream_ptr()
         self.lib.check(self.lib.dfvo_bestn(diff_buf.ptr, self.H, self.W, N, s["idx"].ptr, s["ws"].ptr, s["ws"].shape[0], st))
         self.lib.check(self.lib.dfvo_gather_keypoints(s["idx"].ptr, None, 1, N, flow_fwd_buf.ptr, self.H, self.W, s["kp1"].ptr,
@@ -135,35 +143,48 @@ class Engine:
         ``rigid_flow_diff`` [H,W] and host float64 keypoints kp1/kp2_uniform [n,2], kp1/kp2_best [m,2] (canonical order:
         cell-major; uniform in the reference's own order, best ascending by pixel index inside a cell)."""
         cx, cy, fx, fy = K
-        quota = num_bestN // (rows * cols)
-        cells = rows * cols
-        if not hasattr(self, "_rf"):
+        r = self._rf_buffers(rows, cols, num_bestN // (rows * cols))
+        Th = np.ascontiguousarray(np.asarray(T, np.float64).reshape(-1)[:16])
+        self.lib.check(self.lib.dfvo_rigid_flow_diff(raw_depth_buf.ptr, flow_fwd_buf.ptr, self.H, self.W, Th.ctypes.data_as(ctypes.c_void_p),
+                                                     fx, fy, cx, cy, r["map"].ptr, self.rt.stream_ptr()))
+        return self.opt_rigid_flow_select(r["map"], flow_fwd_buf, flow_diff_buf, rows, cols, num_bestN, rigid_thre, flow_thre,
+                                          score_method, want_best)
+
+    def _rf_buffers(self, rows, cols, quota):
+        key = (rows, cols, quota)
+        if key not in self._rf:
+            cells = rows * cols
             mk = lambda: dict(idx=self.rt.empty((cells * quota,), np.int32), cc=self.rt.empty((cells,), np.int32),
                               kp1=self.rt.empty((cells * quota, 2), np.float64), kp2=self.rt.empty((cells * quota, 2), np.float64),
                               n=self.rt.empty((1,), np.int32))
-            self._rf = dict(map=self.rt.empty((self.H, self.W), np.float32), u=mk(), b=mk(), st=self.rt.empty((4,), np.int32))
-        r = self._rf
+            self._rf[key] = dict(map=self.rt.empty((self.H, self.W), np.float32), u=mk(), b=mk(), st=self.rt.empty((4,), np.int32))
+        return self._rf[key]
+
+    def opt_rigid_flow_select(self, rigid_map_buf, flow_fwd_buf, flow_diff_buf, rows=10, cols=10, num_bestN=2000, rigid_thre=5.0,
+                              flow_thre=0.1, score_method="opt_flow", want_best=True):
+        """``opt_rigid_flow_kp`` (kp_selection.py:203-324) on a given rigid-flow inconsistency map [H,W] (device)."""
+        quota = num_bestN // (rows * cols)
+        cells = rows * cols
+        r = self._rf_buffers(rows, cols, quota)
         st = self.rt.stream_ptr()
-        Th = np.ascontiguousarray(np.asarray(T, np.float64).reshape(-1)[:16])
-        self.lib.check(self.lib.dfvo_rigid_flow_diff(raw_depth_buf.ptr, flow_fwd_buf.ptr, self.H, self.W, Th.ctypes.data_as(ctypes.c_void_p),
-                                                     fx, fy, cx, cy, r["map"].ptr, st))
         u = r["u"]
-        self.lib.check(self.lib.dfvo_uniform_cells(r["map"].ptr, flow_diff_buf.ptr, self.H, self.W, rows, cols, num_bestN, rigid_thre,
+        self.lib.check(self.lib.dfvo_uniform_cells(rigid_map_buf.ptr, flow_diff_buf.ptr, self.H, self.W, rows, cols, num_bestN, rigid_thre,
                                                    flow_thre, u["idx"].ptr, u["cc"].ptr, st))
         self.lib.check(self.lib.dfvo_gather_keypoints(u["idx"].ptr, u["cc"].ptr, cells, quota, flow_fwd_buf.ptr, self.H, self.W,
                                                       u["kp1"].ptr, u["kp2"].ptr, u["n"].ptr, st))
-        out = dict(rigid_flow_diff=r["map"])
+        out = dict(rigid_flow_diff=rigid_map_buf)
         if want_best:
             b = r["b"]
             if score_method == "rigid_flow":                      # score = rigid-flow inconsistency (kp_selection.py:266-269)
-                args = (r["map"].ptr, flow_diff_buf.ptr, rigid_thre, flow_thre)
+                args = (rigid_map_buf.ptr, flow_diff_buf.ptr, rigid_thre, flow_thre)
             else:
-                args = (flow_diff_buf.ptr, r["map"].ptr, flow_thre, rigid_thre)
+                args = (flow_diff_buf.ptr, rigid_map_buf.ptr, flow_thre, rigid_thre)
             self.lib.check(self.lib.dfvo_local_bestn(args[0], args[1], self.H, self.W, rows, cols, num_bestN, args[2], args[3],
                                                      b["idx"].ptr, b["cc"].ptr, r["st"].ptr, st))
             self.lib.check(self.lib.dfvo_gather_keypoints(b["idx"].ptr, b["cc"].ptr, cells, quota, flow_fwd_buf.ptr, self.H, self.W,
                                                           b["kp1"].ptr, b["kp2"].ptr, b["n"].ptr, st))
             nb = int(b["n"].numpy()[0])
+            assert nb != 0, "sampling threshold is too small."       # kp_selection.py:298
             out["kp1_best"], out["kp2_best"] = b["kp1"].numpy()[:nb], b["kp2"].numpy()[:nb]
         nu = int(u["n"].numpy()[0])
         assert nu != 0, "sampling threshold is too small."          # kp_selection.py:306
@@ -173,26 +194,43 @@ class Engine:
     # ------------------------------------------------------------------ pose
     def _subset_table(self, n, max_iters=1000):
         key = (n, max_iters)
-        if key not in self._subsets:
+        t = self._subsets.get(key)
+        if t is None:
             host = np.zeros((max_iters, 5), np.int32)
             self.lib.check(self.lib.dfvo_cv_subset_stream_host(n, 5, max_iters, host.ctypes.data_as(ctypes.c_void_p)))
-            self._subsets[key] = self.rt.from_host(host)
-        return self._subsets[key]
+            while len(self._subsets) >= self._subsets_cap:          # recycle the least recently used table (no allocation)
+                _, t = self._subsets.popitem(last=False)
+                t = t.view((max_iters, 5)) if t.size >= max_iters * 5 else None
+            t = t.upload(host) if t is not None else self.rt.from_host(host)
+            self._subsets[key] = t
+        else:
+            self._subsets.move_to_end(key)
+        return t
+
+    def _capacity(self, n):
+        """Keypoint capacity covering n: the configured one, doubled until it fits."""
+        cap = self.kp_capacity
+        while cap < n:
+            cap *= 2
+        return cap
 
     def essential_launch(self, kp_cur_buf, kp_ref_buf, n, perms, K, threshold=0.2, prob=0.99, max_iters=1000):
         """Enqueue R = len(perms) repeats of findEssentialMat(kp_cur[perm], kp_ref[perm]) + GRIC-E
         (E_tracker.py:223-286).  Returns a handle for :meth:`essential_result`."""
         cx, cy, fx, fy = K
         R = len(perms)
-        key = (n, R, max_iters)
-        if key not in self._ess_ws:
-            nb = int(self.lib.dfvo_essential_workspace_bytes(n, R, max_iters))
-            self._ess_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), E=self.rt.empty((R, 9), np.float64),
-                                     mask=self.rt.empty((R, n), np.uint8), info=self.rt.empty((R, 4), np.int32),
-                                     gric=self.rt.empty((R,), np.float64), perm=self.rt.empty((R, n), np.int32),
-                                     Rt=self.rt.empty((12,), np.float64), pmask=self.rt.empty((n,), np.uint8),
-                                     pinfo=self.rt.empty((5,), np.int32))
-        w = self._ess_ws[key]
+        key = (R, max_iters)
+        c = self._ess_ws.get(key)
+        if c is None or c["cap"] < n:
+            cap = self._capacity(n)
+            nb = int(self.lib.dfvo_essential_workspace_bytes(cap, R, max_iters))
+            c = self._ess_ws[key] = dict(cap=cap, ws=self.rt.empty((nb,), np.uint8), E=self.rt.empty((R, 9), np.float64),
+                                         mask_c=self.rt.empty((R * cap,), np.uint8), info=self.rt.empty((R, 4), np.int32),
+                                         gric=self.rt.empty((R,), np.float64), perm_c=self.rt.empty((R * cap,), np.int32),
+                                         Rt=self.rt.empty((12,), np.float64), pmask_c=self.rt.empty((cap,), np.uint8),
+                                         pinfo=self.rt.empty((5,), np.int32))
+        w = dict(c)
+        w["mask"], w["perm"], w["pmask"] = c["mask_c"].view((R, n)), c["perm_c"].view((R, n)), c["pmask_c"].view((n,))
         w["perm"].upload(np.asarray(perms, np.int32))
         self.lib.check(self.lib.dfvo_essential_ransac(kp_cur_buf.ptr, kp_ref_buf.ptr, n, w["perm"].ptr, R,
                                                       self._subset_table(n, max_iters).ptr, max_iters, fx, fy, cx, cy, threshold,
@@ -211,14 +249,15 @@ class Engine:
     def homography_launch(self, kp_cur_buf, kp_ref_buf, n, threshold=1.0, prob=0.99, max_iters=2000):
         """Enqueue cv2.findHomography(kp_cur, kp_ref, RANSAC, confidence, ransacReprojThreshold) + GRIC-H
         (E_tracker.py:199-215) on the device (csrc/homog.cu); returns the buffers (H [9], mask [n], info [4], gric [1])."""
-        key = (n, max_iters)
-        if not hasattr(self, "_h_ws"):
-            self._h_ws = {}
-        if key not in self._h_ws:
-            nb = int(self.lib.dfvo_homography_workspace_bytes(n, max_iters))
-            self._h_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), H=self.rt.empty((9,), np.float64), mask=self.rt.empty((n,), np.uint8),
-                                   info=self.rt.empty((4,), np.int32), gric=self.rt.empty((1,), np.float64))
-        w = self._h_ws[key]
+        c = self._h_ws.get(max_iters)
+        if c is None or c["cap"] < n:
+            cap = self._capacity(n)
+            nb = int(self.lib.dfvo_homography_workspace_bytes(cap, max_iters))
+            c = self._h_ws[max_iters] = dict(cap=cap, ws=self.rt.empty((nb,), np.uint8), H=self.rt.empty((9,), np.float64),
+                                             mask_c=self.rt.empty((cap,), np.uint8), info=self.rt.empty((4,), np.int32),
+                                             gric=self.rt.empty((1,), np.float64))
+        w = dict(c)
+        w["mask"] = c["mask_c"].view((n,))
         # forked onto a side stream so it runs beside the essential-matrix RANSAC (both are short chains of small kernels);
         # whoever reads the result waits on w["done"] first (resolve_validity)
         if not hasattr(self, "_h_stream"):
@@ -239,15 +278,16 @@ class Engine:
         host arrays.  Returns (rt [R,6] = rvec|tvec, info [R,4] = found, inliers, iterations, winning iteration)."""
         cx, cy, fx, fy = K
         n, R = XYZ.shape[0], len(perms)
-        key = (n, R, iters)
-        if not hasattr(self, "_pnp_ws"):
-            self._pnp_ws = {}
-        if key not in self._pnp_ws:
-            nb = int(self.lib.dfvo_pnp_workspace_bytes(n, R, iters))
-            self._pnp_ws[key] = dict(ws=self.rt.empty((nb,), np.uint8), obj=self.rt.empty((n, 3), np.float64),
-                                     img=self.rt.empty((n, 2), np.float64), perm=self.rt.empty((R, n), np.int32),
-                                     rt=self.rt.empty((R, 6), np.float64), info=self.rt.empty((R, 4), np.int32))
-        w = self._pnp_ws[key]
+        key = (R, iters)
+        c = self._pnp_ws.get(key)
+        if c is None or c["cap"] < n:
+            cap = self._capacity(n)
+            nb = int(self.lib.dfvo_pnp_workspace_bytes(cap, R, iters))
+            c = self._pnp_ws[key] = dict(cap=cap, ws=self.rt.empty((nb,), np.uint8), obj_c=self.rt.empty((cap * 3,), np.float64),
+                                         img_c=self.rt.empty((cap * 2,), np.float64), perm_c=self.rt.empty((R * cap,), np.int32),
+                                         rt=self.rt.empty((R, 6), np.float64), info=self.rt.empty((R, 4), np.int32))
+        w = dict(c)
+        w["obj"], w["img"], w["perm"] = c["obj_c"].view((n, 3)), c["img_c"].view((n, 2)), c["perm_c"].view((R, n))
         w["obj"].upload(XYZ); w["img"].upload(kp2); w["perm"].upload(np.asarray(perms, np.int32))
         self.lib.check(self.lib.dfvo_pnp_ransac(w["obj"].ptr, w["img"].ptr, n, w["perm"].ptr, R, self._subset_table(n, iters).ptr,
                                                 iters, fx, fy, cx, cy, float(reproj_thre), prob, w["ws"].ptr, w["ws"].shape[0],
@@ -423,7 +463,14 @@ class DevArray:
         self._host = None
 
     def copy(self):
-        return self
+        """A snapshot, like ``ndarray.copy()``: the engine reuses its flow / mask buffers every frame, and the driver keeps
+        copies across frames (dfvo.py:329-332; ``update_data`` moves ``fb_flow_mask`` / ``rigid_flow_mask`` into ``ref_data``).
+        If the host copy already exists it is the snapshot; else a device-side clone (ordered after the producer kernel)."""
+        if self._host is not None:
+            c = DevArray(self.dev, self.shape, self._view)
+            c._host = self._host.copy()
+            return c
+        return DevArray(self.dev.clone(), self.shape, self._view)
 
     def __array__(self, dtype=None, copy=None):
         if self._host is None:

@@ -49,7 +49,7 @@ static int run_graphed(GraphCache& gc, const std::vector<uintptr_t>& key, cudaSt
     return DFVO_OK;
   }
   if (e.seen < 0 || e.seen++ == 0) return body();
-  const long long l0 = dfvo::g_launch_count;
+  const long long l0 = dfvo::g_launch_count.load();
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e.seen = -1; return body(); }
   const int rc = body();
   cudaGraph_t g = nullptr;
@@ -61,7 +61,7 @@ static int run_graphed(GraphCache& gc, const std::vector<uintptr_t>& key, cudaSt
     dfvo::g_launch_count = l0;
     return body();
   }
-  e.launches = dfvo::g_launch_count - l0;
+  e.launches = dfvo::g_launch_count.load() - l0;
   const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
   cudaGraphDestroy(g);
   if (ie != cudaSuccess) { cudaGetLastError(); e.exec = nullptr; e.seen = -1; dfvo::g_launch_count = l0; return body(); }
@@ -179,7 +179,7 @@ int dfvo_is_device_build(void) {
 #endif
 }
 
-long long dfvo_launch_count(void) { return dfvo::g_launch_count; }
+long long dfvo_launch_count(void) { return dfvo::g_launch_count.load(); }
 void dfvo_profile_enable(int on) { dfvo::conv_tc_profile_enable(on); }
 void dfvo_profile_read(double* tc_ms, long long* tc_launches, double* tc_flops) { dfvo::conv_tc_profile_read(tc_ms, tc_launches, tc_flops); }
 
@@ -217,7 +217,7 @@ int dfvo_load_weight(dfvo_ctx* ctx, int net, const char* key, const float* data,
 
 int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int precision) {
   API_BEGIN
-  DFVO_REQUIRE(ctx && pairs >= 1 && (precision == 0 || precision == 1), DFVO_EINVAL, "dfvo_liteflow_build args");
+  DFVO_REQUIRE(ctx && pairs >= 1 && precision >= 0 && precision <= 2, DFVO_EINVAL, "dfvo_liteflow_build args");
   DFVO_CUDA(cudaSetDevice(ctx->device));
   delete ctx->lfn;
   ctx->lfn = nullptr;
@@ -226,10 +226,16 @@ int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int pre
   API_END
 }
 
-int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs, float* flow_fwd, float* flow_bwd, float* flow_diff,
+int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs, int n_imgs, float* flow_fwd, float* flow_bwd, float* flow_diff,
                           void* stream) {
   API_BEGIN
   DFVO_REQUIRE(ctx && ctx->lfn && imgs, DFVO_ESTATE, "dfvo_liteflow_forward: call dfvo_liteflow_build first");
+  {
+    int th, tw, B;
+    ctx->lfn->geometry(&th, &tw, &B);
+    DFVO_REQUIRE(n_imgs == B, DFVO_EINVAL, "dfvo_liteflow_forward: %d images given, the plan was built for %d (2 per pair)", n_imgs, B);
+    for (int i = 0; i < n_imgs; ++i) DFVO_REQUIRE(imgs[i] != nullptr, DFVO_EINVAL, "dfvo_liteflow_forward: image %d is null", i);
+  }
   // only the body -- the part that touches nothing but the runner's own buffers -- is replayed as a graph, so there is
   // one graph per network no matter which frame / output buffers the caller cycles through
   cudaStream_t st = (cudaStream_t)stream;
@@ -270,6 +276,19 @@ int dfvo_correlation(const float* first, const float* second, float* out, int B,
 }
 
 
+int dfvo_correlation_nhwc_bf16(const void* first, const void* second, void* out, int B, int C, int Cpitch, int H, int W, int stride,
+                               int leaky, int second_nxor, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(first && second && out && B > 0 && C > 0 && Cpitch >= C && Cpitch % 8 == 0 && H > 0 && W > 0 && (stride == 1 || stride == 2),
+               DFVO_EINVAL, "dfvo_correlation_nhwc_bf16 args");
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  Ten<bf16> A = make_ten<bf16>((bf16*)const_cast<void*>(first), B, H, W, C, Cpitch);
+  Ten<bf16> Bn = make_ten<bf16>((bf16*)const_cast<void*>(second), B, H, W, C, Cpitch);
+  Ten<bf16> O = make_ten<bf16>((bf16*)out, B, Ho, Wo, 64, 64);
+  return correlation49<bf16>(cten(A), cten(Bn), second_nxor, stride, leaky, O, (cudaStream_t)stream);
+  API_END
+}
+
 int dfvo_backward_warp(const float* input, const float* flow, float* out, int B, int C, int H, int W, int precision, void* stream) {
   API_BEGIN
   DFVO_REQUIRE(input && flow && out && B > 0 && C > 0 && H > 0 && W > 0, DFVO_EINVAL, "dfvo_backward_warp args");
@@ -304,7 +323,7 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
 
 int dfvo_monodepth2_build(dfvo_ctx* ctx, int feed_h, int feed_w, int precision, float min_depth, float max_depth, float baseline) {
   API_BEGIN
-  DFVO_REQUIRE(ctx && (precision == 0 || precision == 1), DFVO_EINVAL, "dfvo_monodepth2_build args");
+  DFVO_REQUIRE(ctx && precision >= 0 && precision <= 2, DFVO_EINVAL, "dfvo_monodepth2_build args");
   DFVO_CUDA(cudaSetDevice(ctx->device));
   delete ctx->mono;
   ctx->mono = nullptr;
@@ -321,7 +340,7 @@ int dfvo_monodepth2_forward(dfvo_ctx* ctx, const float* img, float* depth_out, v
   API_END
 }
 
-int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1, float crop_x0, float crop_x1,
+int dfvo_depth_post(const float* depth, int h, int w, int H, int W, double crop_y0, double crop_y1, double crop_x0, double crop_x1,
                     float min_depth, float max_depth, float* raw_out, float* depth_out, void* stream) {
   API_BEGIN
   DFVO_REQUIRE(depth && depth_out && h > 0 && w > 0 && H > 0 && W > 0, DFVO_EINVAL, "dfvo_depth_post args");
@@ -392,6 +411,42 @@ int dfvo_gather_depth(const float* depth, int H, int W, const double* kp, int n,
   API_END
 }
 
+int dfvo_backproject(const float* depth, int H, int W, const double* iK9, float* points, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(depth && iK9 && points && H > 0 && W > 0, DFVO_EINVAL, "dfvo_backproject args");
+  return geom_backproject(depth, H, W, iK9, points, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_transform3d(const float* points, long long n, const double* T16, float* out, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(points && T16 && out && n > 0, DFVO_EINVAL, "dfvo_transform3d args");
+  return geom_transform3d(points, (size_t)n, T16, out, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_project(const float* points, int H, int W, const double* K12, float eps, int normalized, float* xy, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(points && K12 && xy && H > 1 && W > 1, DFVO_EINVAL, "dfvo_project args");
+  return geom_project(points, H, W, K12, eps, normalized, xy, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_reproject(const float* depth, int H, int W, const double* T16, const double* K12, const double* iK9, float eps, int normalized,
+                   float* xy, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(depth && T16 && K12 && iK9 && xy && H > 1 && W > 1, DFVO_EINVAL, "dfvo_reproject args");
+  return geom_reproject(depth, H, W, T16, K12, iK9, eps, normalized, 0, xy, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_rigid_flow(const float* depth, int H, int W, const double* T16, const double* K12, const double* iK9, float* flow, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(depth && T16 && K12 && iK9 && flow && H > 1 && W > 1, DFVO_EINVAL, "dfvo_rigid_flow args");
+  return geom_reproject(depth, H, W, T16, K12, iK9, 1e-7f, 0, 1, flow, (cudaStream_t)stream);
+  API_END
+}
+
 int dfvo_five_point(const double* x1, const double* x2, int M, double* E, int32_t* n, void* stream) {
   API_BEGIN
   DFVO_REQUIRE(x1 && x2 && E && n && M > 0, DFVO_EINVAL, "dfvo_five_point args");
@@ -442,6 +497,14 @@ int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const doub
   API_BEGIN
   DFVO_REQUIRE(x1 && x2 && T21 && depth2 && N > 0, DFVO_EINVAL, "dfvo_triangulate_depth args");
   return triangulate_depth(x1, x2, N, T21, depth2, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_triangulate_points(const double* x1, const double* x2, int N, const double* T1w, const double* T2w, double* X, double* X1, double* X2,
+                            void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(x1 && x2 && T1w && T2w && N > 0, DFVO_EINVAL, "dfvo_triangulate_points args");
+  return triangulate_points(x1, x2, N, T1w, T2w, X, X1, X2, (cudaStream_t)stream);
   API_END
 }
 

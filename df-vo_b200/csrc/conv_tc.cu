@@ -389,7 +389,7 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   return DFVO_OK;
 }
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 int g_tc_prof_on = 0;
 static double g_prof_flops = 0.0;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
@@ -462,7 +462,7 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
 // kernel and applies the same TMA semantics (zero fill outside the image / beyond a source's C,
 // virtual concat of sources, tap offsets), so the layer wiring and the weight packer can be
 // validated without a GPU.  Never compiled into the product library.
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 void conv_tc_profile_enable(int) {}
 void conv_tc_profile_read(double* ms, long long* launches, double* flops) { *ms = 0; *launches = 0; *flops = 0; }
 int conv_tc(const ConvTc& c, cudaStream_t) {

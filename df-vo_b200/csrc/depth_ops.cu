@@ -123,11 +123,11 @@ __global__ void k_depth_post(const float* __restrict__ depth, int h, int w, int 
   depth_out[(size_t)y * W + x] = keep ? d : 0.f;
 }
 
-int depth_post(const float* depth, int h, int w, int H, int W, float cy0, float cy1, float cx0, float cx1, float min_depth,
+int depth_post(const float* depth, int h, int w, int H, int W, double cy0, double cy1, double cx0, double cx1, float min_depth,
                float max_depth, float* raw_out, float* depth_out, cudaStream_t s) {
-  // int(h*crop): Python float multiply then truncation
-  int y0 = (int)((double)H * (double)cy0), y1 = (int)((double)H * (double)cy1);
-  int x0 = (int)((double)W * (double)cx0), x1 = (int)((double)W * (double)cx1);
+  // int(h*crop): Python float64 multiply then truncation (utils.py:103-104); the fractions cross the ABI as doubles
+  int y0 = (int)((double)H * cy0), y1 = (int)((double)H * cy1);
+  int x0 = (int)((double)W * cx0), x1 = (int)((double)W * cx1);
   DFVO_LAUNCH(k_depth_post, dim3(cdiv(W, 128), H), dim3(128), 0, s, depth, h, w, H, W, y0, y1, x0, x1, min_depth, max_depth, raw_out,
               depth_out);
   DFVO_CHECK_LAUNCH();

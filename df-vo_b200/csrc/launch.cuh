@@ -5,7 +5,8 @@
 #include "cuda_hostsim.h"
 #else
 #include <cuda_runtime.h>
-namespace dfvo { extern long long g_launch_count; }
+#include <atomic>
+namespace dfvo { extern std::atomic<long long> g_launch_count; }
 #define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { ++dfvo::g_launch_count; kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
 #define DFVO_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _dyn_smem_raw[]; \

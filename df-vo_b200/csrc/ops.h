@@ -125,7 +125,7 @@ int upcat_reflect(Ten<const T> lo, int up, Ten<const T> skip, Ten<T> out, cudaSt
 // sigmoid disparity -> depth (layers.py:16-25, monodepth2.py:111-138): depth = baseline / (min_disp + (max_disp-min_disp)*disp)
 int disp_to_depth(const float* disp, int n, float min_depth, float max_depth, float baseline, float* depth, cudaStream_t s);
 // cv2.resize(INTER_NEAREST) to (W,H) + preprocess_depth (dfvo.py:314-319, utils.py:89-114)
-int depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1, float crop_x0, float crop_x1,
+int depth_post(const float* depth, int h, int w, int H, int W, double crop_y0, double crop_y1, double crop_x0, double crop_x1,
                float min_depth, float max_depth, float* raw_out, float* depth_out, cudaStream_t s);
 
 // PIL-exact LANCZOS resize of a uint8 HWC image (tables from b200/lanczos.py); tmp = uint8 [H][out_w][3]
@@ -147,6 +147,15 @@ int uniform_cells(const float* rigid_diff, const float* flow_diff, int H, int W,
 int rigid_flow_diff(const float* depth, const float* flow, int H, int W, const double* T_host, double fx, double fy, double cx, double cy,
                     float* out, cudaStream_t s);
 int gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, cudaStream_t s);
+
+// ---- geometry layers (geometry.cu): libs/geometry/{backprojection,transformation3d,projection,reprojection,rigid_flow}.py ----
+// host matrices are row-major float64 (cast to float32 like torch.from_numpy(..).float()); points are planar [4][H*W]
+int geom_backproject(const float* depth, int H, int W, const double* iK9, float* points, cudaStream_t s);
+int geom_transform3d(const float* in, size_t n, const double* T16, float* out, cudaStream_t s);
+int geom_project(const float* points, int H, int W, const double* K12, float eps, int normalized, float* xy, cudaStream_t s);
+// mode 0: xy [H][W][2] (Reprojection.forward);  mode 1: planar flow [2][H][W] (RigidFlow.forward)
+int geom_reproject(const float* depth, int H, int W, const double* T16, const double* K12, const double* iK9, float eps, int normalized,
+                   int mode, float* out, cudaStream_t s);
 // idx: [ncells*n_best] slots (cell-major); cell_counts may be null (all slots valid, e.g. bestN with ncells=1)
 int gather_keypoints(const int32_t* idx, const int32_t* cell_counts, int ncells, int n_best, const float* flow_fwd, int H, int W,
                      double* kp1, double* kp2, int32_t* n_out, cudaStream_t s);

@@ -383,6 +383,41 @@ __global__ void k_triangulate_depth(const double* __restrict__ x1, const double*
   depth2[i] = P[2][0] * x + P[2][1] * y + P[2][2] * z + P[2][3];             // X2 = T_2w[:3] @ X
 }
 
+// ops_3d.triangulation (ops_3d.py:44-67) for two general views: cv2.triangulatePoints(T_1w[:3], T_2w[:3], kp1, kp2) (the same 4x4 DLT,
+// smallest singular vector), X /= X[3], X1 = T_1w[:3] @ X, X2 = T_2w[:3] @ X.  Outputs are [3][N] (any may be null).
+__global__ void k_triangulate_points(const double* __restrict__ x1, const double* __restrict__ x2, int N, const double* __restrict__ T1w,
+                                     const double* __restrict__ T2w, double* __restrict__ Xw, double* __restrict__ X1, double* __restrict__ X2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double P0[3][4], P1[3][4];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 4; ++b) { P0[a][b] = T1w[4 * a + b]; P1[a][b] = T2w[4 * a + b]; }
+  const double u0 = x1[2 * i], v0 = x1[2 * i + 1], u1 = x2[2 * i], v1 = x2[2 * i + 1];
+  double A[4][4];
+  for (int k = 0; k < 4; ++k) {
+    A[0][k] = u0 * P0[2][k] - P0[0][k]; A[1][k] = v0 * P0[2][k] - P0[1][k];
+    A[2][k] = u1 * P1[2][k] - P1[0][k]; A[3][k] = v1 * P1[2][k] - P1[1][k];
+  }
+  double AtA[4][4], V[4][4], w[4];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) { double a = 0; for (int k = 0; k < 4; ++k) a += A[k][r] * A[k][c]; AtA[r][c] = a; }
+  sm::jacobi_eig<4>(AtA, V, w);
+  int m = 0;
+  for (int r = 1; r < 4; ++r) if (w[r] < w[m]) m = r;
+  const double X[4] = {V[0][m] / V[3][m], V[1][m] / V[3][m], V[2][m] / V[3][m], 1.0};
+  for (int a = 0; a < 3; ++a) {
+    if (Xw) Xw[(size_t)a * N + i] = X[a];
+    if (X1) X1[(size_t)a * N + i] = P0[a][0] * X[0] + P0[a][1] * X[1] + P0[a][2] * X[2] + P0[a][3];
+    if (X2) X2[(size_t)a * N + i] = P1[a][0] * X[0] + P1[a][1] * X[1] + P1[a][2] * X[2] + P1[a][3];
+  }
+}
+
+int triangulate_points(const double* x1, const double* x2, int N, const double* T1w, const double* T2w, double* Xw, double* X1, double* X2,
+                       cudaStream_t s) {
+  DFVO_LAUNCH(k_triangulate_points, dim3(cdiv(N, 128)), dim3(128), 0, s, x1, x2, N, T1w, T2w, Xw, X1, X2);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s) {
   DFVO_LAUNCH(k_triangulate_depth, dim3(cdiv(N, 128)), dim3(128), 0, s, x1, x2, N, T21, depth2);
   DFVO_CHECK_LAUNCH();

@@ -34,5 +34,8 @@ int homography_ransac(const double* p1, const double* p2, int N, int max_iters, 
 
 // ops_3d.triangulation(kp1n, kp2n, eye(4), T_21) -> z of X2 per point (ops_3d.py:44-67)
 int triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, cudaStream_t s);
+// ops_3d.triangulation for two general views: T1w/T2w device [12] (rows of the 3x4 matrices), outputs [3][N] (nullable)
+int triangulate_points(const double* x1, const double* x2, int N, const double* T1w, const double* T2w, double* Xw, double* X1, double* X2,
+                       cudaStream_t s);
 
 }  // namespace dfvo

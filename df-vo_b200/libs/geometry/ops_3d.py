@@ -16,17 +16,19 @@ def convert_sparse3D_to_depth(kp, XYZ, height, width):
 
 
 def triangulation(kp1, kp2, T_1w, T_2w):
-    """ops_3d.py:44-67 for the configuration the tracker uses (T_1w = identity): returns (X, X1, X2)
-    with only the rows the callers read populated exactly (X2[2] = depth in view 2)."""
-    from b200 import runtime, tracking
-    assert np.allclose(T_1w, np.eye(4)), "triangulation: the device kernel assumes view 1 = [I|0]"
-    eng = tracking.default_engine()
+    """ops_3d.py:44-67: cv2.triangulatePoints(T_1w[:3], T_2w[:3], kp1, kp2) per point on the device (the 4x4 DLT of
+    csrc/ransac.cu), X /= X[3]; returns (X [3,N] world, X1 = T_1w[:3] @ X, X2 = T_2w[:3] @ X)."""
+    from b200 import runtime
+    rt = runtime.get()
     n = kp1.shape[0]
-    z2 = eng.triangulate_depth(runtime.get().from_host(np.ascontiguousarray(kp1, np.float64)),
-                               runtime.get().from_host(np.ascontiguousarray(kp2, np.float64)), n, T_2w)
-    X2 = np.zeros((3, n))
-    X2[2] = z2
-    return None, None, X2
+    k1 = rt.from_host(np.ascontiguousarray(kp1, np.float64))
+    k2 = rt.from_host(np.ascontiguousarray(kp2, np.float64))
+    t1 = rt.from_host(np.ascontiguousarray(np.asarray(T_1w, np.float64)[:3].reshape(-1)))
+    t2 = rt.from_host(np.ascontiguousarray(np.asarray(T_2w, np.float64)[:3].reshape(-1)))
+    out = [rt.empty((3, n), np.float64) for _ in range(3)]
+    rt.lib.check(rt.lib.dfvo_triangulate_points(k1.ptr, k2.ptr, n, t1.ptr, t2.ptr, out[0].ptr, out[1].ptr, out[2].ptr, rt.stream_ptr()))
+    X, X1, X2 = (o.numpy() for o in out)
+    return X, X1, X2
 
 
 def unprojection_kp(kp, kp_depth, cam_intrinsics):

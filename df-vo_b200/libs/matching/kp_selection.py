@@ -64,5 +64,20 @@ def sampled_kp(kp1, kp2, ref_data, kp_list, cfg, outputs):
     return outputs
 
 
-def opt_rigid_flow_kp(*a, **k):
-    raise NotImplementedError("rigid-flow keypoints (kp_selection.py:203-324) are a 'next' row (SURVEY.md 8f rank 1)")
+def opt_rigid_flow_kp(kp1, kp2, ref_data, cfg, outputs, score_method):
+    """kp_selection.py:203-324: per cell the 'uniform' list (every step-th pixel that passes both masks) and the 'best' list
+    (n_best smallest ``score_method`` scores among them) from ``ref_data['rigid_flow_diff']`` [H,W,1] and
+    ``ref_data['flow_diff']`` [H,W,1]; ``kp1``/``kp2`` (the reference's dense grids) are ignored -- the kernels derive the
+    keypoints from ``ref_data['flow']``.  Runs on the device (csrc/select.cu: k_uniform_cells, k_local_bestn)."""
+    assert score_method in ("opt_flow", "rigid_flow"), score_method
+    rk = cfg.kp_selection.rigid_flow_kp
+    eng = tracking.default_engine()
+    h, w = eng.H, eng.W
+    rmap = ref_data["rigid_flow_diff"]
+    rbuf = rmap.dev if isinstance(rmap, tracking.DevArray) else runtime.get().from_host(np.ascontiguousarray(np.asarray(rmap, np.float32).reshape(h, w)))
+    o = eng.opt_rigid_flow_select(rbuf, _dev(ref_data["flow"], np.float32), _dev(ref_data["flow_diff"], np.float32), rk.num_row, rk.num_col,
+                                  rk.num_bestN, float(rk.rigid_flow_thre), float(rk.optical_flow_thre), score_method)
+    outputs["kp1_depth"], outputs["kp2_depth"] = o["kp1_best"][None], o["kp2_best"][None]
+    outputs["kp1_depth_uniform"], outputs["kp2_depth_uniform"] = o["kp1_uniform"][None], o["kp2_uniform"][None]
+    outputs["rigid_flow_mask"] = tracking.DevArray(rbuf, (h, w))
+    return outputs

@@ -36,6 +36,7 @@ extern "C" {
 
 #define DFVO_PREC_FP32 0 /* every conv on CUDA cores in fp32 (parity mode)            */
 #define DFVO_PREC_BF16 1 /* bf16 activations, tcgen05 tensor-core convs, fp32 accum   */
+#define DFVO_PREC_TF32 2 /* fp32 activations, tcgen05 kind::tf32 convs, fp32 accum    */
 
 #define DFVO_ACT_NONE 0
 #define DFVO_ACT_LEAKY 1 /* LeakyReLU(0.1) */
@@ -72,10 +73,10 @@ int dfvo_load_weight(dfvo_ctx* ctx, int net, const char* key, const float* data_
  * Build the plan for `pairs` image pairs of height x width uint8 RGB frames. */
 int dfvo_liteflow_build(dfvo_ctx* ctx, int height, int width, int pairs, int precision);
 /* imgs: 2*pairs device pointers (host array of device pointers) to HWC uint8 frames ordered
- * [ref0, cur0, ref1, cur1, ...].  Outputs (any may be NULL): flow_fwd / flow_bwd
+ * [ref0, cur0, ref1, cur1, ...]; n_imgs must equal 2*pairs of the built plan.  Outputs (any may be NULL): flow_fwd / flow_bwd
  * [pairs][2][H][W] fp32 (= flows[(ref,cur)], flows[(cur,ref)]), flow_diff [pairs][H][W] fp32
  * (= flows[(ref,cur,'diff')], deep_flow.py:171-196). */
-int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs_host_array, float* flow_fwd,
+int dfvo_liteflow_forward(dfvo_ctx* ctx, const uint8_t* const* imgs_host_array, int n_imgs, float* flow_fwd,
                           float* flow_bwd, float* flow_diff, void* stream);
 /* parity helper: regularised flow of pyramid level (2..6), NHWC [2*pairs][h][w][2] fp32 */
 int dfvo_liteflow_level_flow(dfvo_ctx* ctx, int level, float* out);
@@ -98,8 +99,8 @@ int dfvo_lanczos_resize_u8(const uint8_t* img, int H, int W, const int32_t* boun
                            int out_w, uint8_t* tmp, uint8_t* out_u8, float* out_nchw, void* stream);
 /* cv2.resize(raw_depth, (W,H), INTER_NEAREST) + utils.preprocess_depth (dfvo.py:314-319, utils.py:89-114):
  * depth [h,w] -> raw_out [H,W] (may be NULL), depth_out [H,W]; crop = [[y0,y1],[x0,x1]] normalised. */
-int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y0, float crop_y1,
-                    float crop_x0, float crop_x1, float min_depth, float max_depth, float* raw_out,
+int dfvo_depth_post(const float* depth, int h, int w, int H, int W, double crop_y0, double crop_y1,
+                    double crop_x0, double crop_x1, float min_depth, float max_depth, float* raw_out,
                     float* depth_out, void* stream);
 
 /* ---- stage-level entry points (parity tests; NCHW fp32 at the boundary like the reference) -----
@@ -107,6 +108,12 @@ int dfvo_depth_post(const float* depth, int h, int w, int H, int W, float crop_y
  * -> out [B,49,ceil(H/s),ceil(W/s)].  precision selects the fp32 or bf16 kernel. */
 int dfvo_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W,
                      int stride, int leaky, int precision, void* stream);
+/* The correlation kernel of the product path on its own layout (BASELINE configs[2] bench): first/second/out are NHWC
+ * bf16 device tensors, first/second [B][H][W][Cpitch] (C real channels, Cpitch % 8 == 0), out [B][ceil(H/s)][ceil(W/s)][64]
+ * (49 real channels, the rest zero).  second_nxor: the second operand of batch entry n is read at index n ^ second_nxor
+ * (1 = the "other image of the pair" addressing LiteFlowNet's level 6 uses, 0 = plain). */
+int dfvo_correlation_nhwc_bf16(const void* first, const void* second, void* out, int B, int C, int Cpitch, int H, int W,
+                               int stride, int leaky, int second_nxor, void* stream);
 /* Backward (lite_flow_net.py:10-28): input [B,C,H,W], flow [B,2,H,W] (already scaled) -> [B,C,H,W] */
 int dfvo_backward_warp(const float* input, const float* flow, float* out, int B, int C, int H, int W,
                        int precision, void* stream);
@@ -152,6 +159,21 @@ int dfvo_rigid_flow_diff(const float* raw_depth, const float* flow_fwd, int H, i
 int dfvo_uniform_cells(const float* rigid_flow_diff, const float* flow_diff, int H, int W, int rows, int cols, int num_bestN,
                        float rigid_flow_thre, float optical_flow_thre, int32_t* idx_out, int32_t* cell_counts, void* stream);
 
+/* ---- geometry layers (libs/geometry; float32 like the torch modules; matrices are row-major float64 on the HOST) ----------
+ * Backprojection.forward (backprojection.py:45-63): depth [H,W] -> points [4][H*W] = (inv_K[:3,:3] @ (x,y,1)) * depth, 1. */
+int dfvo_backproject(const float* depth, int H, int W, const double* inv_K9_host, float* points, void* stream);
+/* Transformation3D.forward (transformation3d.py:21-31): out [4][n] = T (4x4) @ points [4][n]. */
+int dfvo_transform3d(const float* points, long long n, const double* T16_host, float* out, void* stream);
+/* Projection.forward (projection.py:31-52): points [4][H*W] -> xy [H][W][2] = (K[:3,:] @ p)[:2] / ((K[:3,:] @ p)[2] + eps),
+ * normalized != 0: x/(W-1), y/(H-1), then (xy-0.5)*2.  K12 = the 3x4 matrix K[:3,:]. */
+int dfvo_project(const float* points, int H, int W, const double* K12_host, float eps, int normalized, float* xy, void* stream);
+/* Reprojection.forward (reprojection.py:37-56) fused: depth [H,W] -> xy [H][W][2]. */
+int dfvo_reproject(const float* depth, int H, int W, const double* T16_host, const double* K12_host, const double* inv_K9_host,
+                   float eps, int normalized, float* xy, void* stream);
+/* RigidFlow.forward (rigid_flow.py:38-58; PixToFlow layers.py:252-266): depth [H,W] -> flow [2][H][W] = reprojected pixel - pixel. */
+int dfvo_rigid_flow(const float* depth, int H, int W, const double* T16_host, const double* K12_host, const double* inv_K9_host,
+                    float* flow, void* stream);
+
 /* depth[int(kp_y), int(kp_x)] for n keypoints (ops_3d.py:29, pnp_tracker.py:72-73); 0 outside the image. */
 int dfvo_gather_depth(const float* depth, int H, int W, const double* kp, int n, float* out, void* stream);
 
@@ -180,6 +202,10 @@ int dfvo_cv_subset_stream_host(int count, int model_points, int n_subsets, int32
 /* cv::triangulatePoints([I|0], T_21[:3], x1, x2) followed by X2 = T_21[:3] X / X_w (ops_3d.py:44-67): x1, x2
  * [N][2] normalised (float64), T21 [12] row-major 3x4 -> depth2 [N] = z of the point in view 2. */
 int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, void* stream);
+/* ops_3d.triangulation(kp1, kp2, T_1w, T_2w) (ops_3d.py:44-67) for two general views: x1, x2 [N][2] normalised float64, T1w / T2w
+ * [12] = the 3x4 matrices (device memory) -> X, X1, X2 [3][N] (world / view-1 / view-2 coordinates; any may be NULL). */
+int dfvo_triangulate_points(const double* x1, const double* x2, int N, const double* T1w, const double* T2w, double* X, double* X1,
+                            double* X2, void* stream);
 /* cv2.recoverPose(E, p1, p2, focal, pp) (E_tracker.py:292-295): Rt_out[12] = R row-major then t, mask [N],
  * info[5] = {cheirality count, counts of the four (R,t) candidates}. */
 int dfvo_recover_pose(const double* E, const double* p1, const double* p2, int N, double focal, double cx,

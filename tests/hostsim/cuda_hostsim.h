@@ -135,6 +135,7 @@ inline void __threadfence() {}
 
 // dynamic shared memory: kernels declare it through DFVO_DYN_SMEM(type, name)
 #define DFVO_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(hostsim_dyn_smem)
-namespace dfvo { extern long long g_launch_count; }
+#include <atomic>
+namespace dfvo { extern std::atomic<long long> g_launch_count; }
 #define DFVO_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { ++dfvo::g_launch_count; hostsim::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)

@@ -32,6 +32,13 @@ class HostsimRuntime:
     def to_host(self, buf):
         return buf.t.copy()
 
+    def view(self, buf, shape):
+        n = int(np.prod(shape)) if len(shape) else 1
+        return rt_mod.Buf(buf.t.reshape(-1)[:n].reshape(tuple(shape)), shape, buf.dtype, self)
+
+    def clone(self, buf):
+        return rt_mod.Buf(buf.t.copy(), buf.shape, buf.dtype, self)
+
     def ptr_of(self, t):
         return t.ctypes.data_as(ctypes.c_void_p)
 

@@ -41,13 +41,14 @@ def check_maps_and_selection(engine, name):
     assert err.max() < 2e-3 * max(1.0, float(np.abs(want_map).max()) / 30), err.max()
     assert np.abs(dev_map[::9, ::9] - g[key + "_rigid_flow_diff_s9"]).max() < 5e-3
     # selection on the oracle's map (uploaded over the device map) -> exact lists
-    engine._rf["map"].upload(want_map)
+    rf = engine._rf[(10, 10, 20)]
+    rf["map"].upload(want_map)
     cells, quota = 100, 20
-    u, b = engine._rf["u"], engine._rf["b"]
+    u, b = rf["u"], rf["b"]
     lib, st = engine.lib, rt.stream_ptr()
-    lib.check(lib.dfvo_uniform_cells(engine._rf["map"].ptr, d_diff.ptr, H, W, 10, 10, 2000, 5.0, 0.1, u["idx"].ptr, u["cc"].ptr, st))
-    lib.check(lib.dfvo_local_bestn(d_diff.ptr, engine._rf["map"].ptr, H, W, 10, 10, 2000, 0.1, 5.0, b["idx"].ptr, b["cc"].ptr,
-                                   engine._rf["st"].ptr, st))
+    lib.check(lib.dfvo_uniform_cells(rf["map"].ptr, d_diff.ptr, H, W, 10, 10, 2000, 5.0, 0.1, u["idx"].ptr, u["cc"].ptr, st))
+    lib.check(lib.dfvo_local_bestn(d_diff.ptr, rf["map"].ptr, H, W, 10, 10, 2000, 0.1, 5.0, b["idx"].ptr, b["cc"].ptr,
+                                   rf["st"].ptr, st))
     best, uniform = vo.opt_rigid_flow_kp(want_map, fr["flow_diff"][:, :, 0], score_method="opt_flow")
     iu, cu = u["idx"].numpy().reshape(cells, quota), u["cc"].numpy()
     ib, cb = b["idx"].numpy().reshape(cells, quota), b["cc"].numpy()
