@@ -21,13 +21,22 @@ def _wrap(d):
 
 def default_cfg(height=376, width=1241):
     return _wrap({
-        "dataset": "kitti_odom", "seed": 4869,
+        "dataset": "kitti_odom", "seed": 4869, "frame_step": 1,
         "image": {"height": height, "width": width},
-        "depth": {"max_depth": 50, "min_depth": 0},
+        "depth": {"max_depth": 50, "min_depth": 0, "depth_src": None, "deep_depth": {"network": "monodepth2", "pretrained_model": None}},
+        "deep_flow": {"network": "liteflow", "flow_net_weight": None, "forward_backward": True},
+        "deep_pose": {"enable": False},
+        "online_finetune": {"enable": False, "lr": 0.00001, "num_frames": 200,
+                            "flow": {"enable": False, "scales": [1, 2, 3, 4, 5], "loss": {"flow_consistency": 0.005, "flow_smoothness": 0.1}},
+                            "depth": {"enable": False, "scales": [0, 1, 2, 3], "pose_src": "DF-VO",
+                                      "loss": {"apperance_loss": 1, "disparity_smoothness": 0.001, "depth_consistency": 0.001}},
+                            "pose": {"enable": False}},
         "crop": {"depth_crop": [[0.3, 1], [0, 1]], "flow_crop": [[0, 1], [0, 1]]},
         "kp_selection": {
             "local_bestN": {"enable": True, "num_bestN": 2000, "num_row": 10, "num_col": 10, "score_method": "flow", "thre": 0.1},
             "bestN": {"enable": False, "num_bestN": 2000},
+            "sampled_kp": {"enable": False, "num_kp": 2000},
+            "depth_consistency": {"enable": False, "thre": 0.05},
             "rigid_flow_kp": {"enable": False, "num_bestN": 2000, "num_row": 10, "num_col": 10, "score_method": "opt_flow",
                               "rigid_flow_thre": 5, "optical_flow_thre": 0.1},
         },
