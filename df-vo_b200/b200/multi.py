@@ -79,3 +79,62 @@ def gather_trajectories(poses, dst=0):
     out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
     dist.gather_object(poses, out, dst=dst)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# pair-level sharding: the "batched many-frames mode" (independent image pairs split over the GPUs)
+# ---------------------------------------------------------------------------------------------
+class PairShard:
+    """Contiguous block of the `total` independent image pairs owned by `rank` ("contiguous block of 64/G pairs per
+    GPU").  The first `total % world` ranks take one extra pair, so every pair has exactly one owner for any world size."""
+
+    def __init__(self, total, rank, world):
+        base, rem = divmod(int(total), int(world))
+        self.total, self.rank, self.world = int(total), int(rank), int(world)
+        self.count = base + (1 if rank < rem else 0)
+        self.first = rank * base + min(rank, rem)
+
+    def owner_table(self):
+        """[(first, count)] for every rank."""
+        return [(PairShard(self.total, r, self.world).first, PairShard(self.total, r, self.world).count) for r in range(self.world)]
+
+
+class PairBatchRunner:
+    """LiteFlowNet forward+backward flow and the consistency map for a rank's block of pairs in ONE batched forward
+    (``dfvo_liteflow_build(pairs=count)``; the reference itself is hard-wired to one pair per call, deep_flow.py:34).  Frames
+    and outputs stay on the device; per pair only the mean inconsistency and the fraction of consistent pixels leave it."""
+
+    def __init__(self, rt, height, width, pairs, flow_weights, precision=1, thre=0.1):
+        from . import tracking
+        self.rt, self.pairs, self.thre = rt, int(pairs), float(thre)
+        self.eng = tracking.Engine(height, width, rt)
+        self.eng.build_flow(flow_weights, pairs=self.pairs, precision=precision)
+
+    def forward(self, img_bufs):
+        """img_bufs: 2*pairs uint8 HWC device buffers [ref0, cur0, ref1, cur1, ...] -> float64 [pairs, 2] =
+        (mean flow_diff, fraction of pixels with flow_diff < thre)."""
+        assert len(img_bufs) == 2 * self.pairs
+        fwd, bwd, diff = self.eng.flow(img_bufs)
+        d = diff.t.reshape(self.pairs, -1) if hasattr(diff.t, "reshape") else diff.t
+        if hasattr(d, "mean") and not isinstance(d, np.ndarray):          # torch tensor on the device: two tiny reductions
+            stats = self.rt.torch.stack([d.double().mean(1), (d < self.thre).double().mean(1)], 1)
+            return stats.cpu().numpy()
+        d = np.asarray(d)
+        return np.stack([d.astype(np.float64).mean(1), (d < self.thre).mean(1)], 1)
+
+
+def gather_pair_stats(stats, shard, world, device=None):
+    """all_gather of the per-pair statistics ([count, 2] per rank, ragged blocks padded to the largest) -> [total, 2] in
+    global pair order on every rank."""
+    import torch
+    import torch.distributed as dist
+    stats = np.asarray(stats, np.float64).reshape(-1, 2)
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        return stats
+    table = shard.owner_table()
+    cap = max(c for _, c in table)
+    mine = torch.zeros((cap, 2), dtype=torch.float64, device=device or "cpu")
+    mine[:stats.shape[0]] = torch.from_numpy(stats).to(mine.device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return np.concatenate([parts[r][:table[r][1]].cpu().numpy() for r in range(world)], 0)

@@ -11,6 +11,8 @@ kilobytes (keypoints, masks, scores) instead of the reference's ~9.8 MB of dense
 This is the object ``bench.py`` times; ``df-vo_b200/libs`` exposes the same kernels behind the reference's
 class API for the unmodified driver.
 """
+import time
+
 import numpy as np
 
 from . import config as cfg_mod
@@ -47,8 +49,13 @@ class _ForkJoin:
 
 class FramePipeline:
     def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
-                 overlap=False, engine=None, inflight=1):
+                 overlap=False, engine=None, inflight=1, inject=None):
         """K = [cx, cy, fx, fy].
+
+        inject: optional ``callable(pipeline, frame_state)`` run by ``infer`` right after the two networks of a frame were
+        enqueued (on the frame's network stream).  Without trained weights a benchmark / test uses it to copy analytic
+        flow / depth over the network outputs on the device; it is the one official hook for that -- nothing else of the
+        pipeline needs replacing.
 
         overlap=False: ``step(img)`` returns the pose of ``img`` (one stream, in order).
         overlap=True : two CUDA streams; ``step(img)`` enqueues the networks of ``img`` and then tracks the
@@ -65,11 +72,13 @@ class FramePipeline:
         self.eng = engine or tracking.Engine(height, width, self.rt)      # `engine`: share built networks with another pipeline
         self.precision = precision
         self.rng = rng
+        self.inject = inject
         self.ref = None
         self.stage = 0
         self.global_pose = np.eye(4)
         self.motion = np.eye(4)
         self.poses = {}
+        self.track_ms = {}
         self.modes = {}              # frame id -> branch taken by the tracker ('E', 'PnP', 'const'; None for the first frame)
         self.last = {}
         self._bufs = {}
@@ -125,13 +134,17 @@ class FramePipeline:
         return np.ascontiguousarray(np.transpose(np.asarray(im, np.uint8), (2, 0, 1))[None].astype(np.float32) / np.float32(255))
 
     def infer(self, img, fid):
-        """Upload + both networks for one new frame; returns its FrameState (device buffers)."""
+        """Upload + both networks for one new frame; returns its FrameState (device buffers).  `img`: uint8 HWC frame as a
+        host ndarray, a pinned host tensor (asynchronous H2D) or an already device-resident ``runtime.Buf``."""
         st = FrameState()
         st.id = fid
         # multi-buffer images / depths / flows so the previous frame's stay valid as 'ref'
         slot = self.slot(fid)
         eng = self.engine_for(fid)
-        st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
+        if isinstance(img, rt_mod.Buf):
+            st.img = img
+        else:
+            st.img = self._buf("img%d" % slot, (self.H, self.W, 3), np.uint8).upload(img)
         self.mark_image_ready(st)
         st.raw_depth = self._buf("raw%d" % slot, (self.H, self.W), np.float32)
         st.depth = self._buf("dep%d" % slot, (self.H, self.W), np.float32)
@@ -143,6 +156,8 @@ class FramePipeline:
             self.wait_reference_image()
             st.fwd, st.bwd, st.diff = self.flow_slot(slot)
             eng.flow([self.ref.img, st.img], out=(st.fwd, st.bwd, st.diff))
+        if self.inject is not None:
+            self.inject(self, st)
         return st
 
     def mark_image_ready(self, st):
@@ -285,7 +300,9 @@ class FramePipeline:
             self.global_pose = np.eye(4)
             self.motion = np.eye(4)
         else:
+            t0 = time.perf_counter()
             rel = self.track(cur, ref)
+            self.track_ms[fid] = (time.perf_counter() - t0) * 1e3      # host time of the tracker path (includes its device waits)
             self.motion = rel.copy()
             # update_global_pose (dfvo.py:109-119): t_w += R_w t ; R_w = R_w R
             self.global_pose[:3, 3:] = self.global_pose[:3, :3] @ rel[:3, 3:] + self.global_pose[:3, 3:]

@@ -95,7 +95,10 @@ class CudaRuntime:
         return Buf(t, arr.shape, arr.dtype, self)
 
     def upload(self, buf, arr):
-        buf.t.copy_(self.torch.from_numpy(np.ascontiguousarray(arr, dtype=buf.dtype).reshape(buf.shape)))
+        if self.torch.is_tensor(arr):                 # e.g. a pinned host tensor: asynchronous H2D on the current stream
+            buf.t.copy_(arr.reshape(buf.shape), non_blocking=True)
+        else:
+            buf.t.copy_(self.torch.from_numpy(np.ascontiguousarray(arr, dtype=buf.dtype).reshape(buf.shape)))
 
     def to_host(self, buf):
         return buf.t.cpu().numpy()

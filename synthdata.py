@@ -328,10 +328,12 @@ def correspondences(seed, n=2000, outlier_frac=0.3, noise=0.05, h=376, w=1241, z
 # ----------------------------------------------------------------------------------------
 # per-frame analytic network outputs of the synthetic drive (driver golden, bench)
 # ----------------------------------------------------------------------------------------
-def frame_inputs(t, h, w, K, mode="normal"):
+def frame_inputs(t, h, w, K, mode="normal", outlier_frac=0.0):
     """Analytic network outputs for the pair (t-1, t): forward/backward flow [2,h,w] f32, inconsistency
     [h,w,1] f32 and the CNN depth [h,w] f32 of frame t.  mode 'still' has zero translation (forces the
-    GRIC check to prefer the homography -> PnP fallback); 'blind' has no consistent flow at all."""
+    GRIC check to prefer the homography -> PnP fallback); 'blind' has no consistent flow at all.
+    outlier_frac > 0 replaces that fraction of the flow vectors by U(-30, 30) px without touching the
+    inconsistency map (the E-RANSAC then needs ~28 / ~410 iterations at 0.3 / 0.6)."""
     rs = np.random.RandomState(1000 + t)
     depth = scene_depth(h, w, K, 7).astype(np.float32) * np.float32(1.0 + 0.05 * np.sin(t))
     rvec, tr = default_motion(rs)
@@ -339,6 +341,10 @@ def frame_inputs(t, h, w, K, mode="normal"):
         tr = tr * 0.0
     flow = rigid_flow(depth.astype(np.float64), K, rodrigues(rvec), tr) + rs.standard_normal((2, h, w)) * 0.05
     diff = np.abs(rs.standard_normal((h, w)) * (0.08 if mode != "blind" else 50.0))
+    if outlier_frac > 0:
+        ro = np.random.RandomState(5000 + t)
+        m = ro.uniform(0, 1, (h, w)) < outlier_frac
+        flow = np.where(m[None], ro.uniform(-30, 30, (2, h, w)), flow)
     return dict(fwd=flow.astype(np.float32), bwd=(-flow).astype(np.float32), diff=diff.astype(np.float32)[..., None],
                 depth=depth, rvec=rvec, t=tr)
 

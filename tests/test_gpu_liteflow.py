@@ -89,3 +89,19 @@ def test_liteflow_two_pairs_batched(dev_lib):
     for p in range(2):
         f1, b1, d1 = run(1, imgs[2 * p:2 * p + 2])
         assert np.array_equal(f2[p], f1[0]) and np.array_equal(b2[p], b1[0]) and np.array_equal(d2[p], d1[0]), p
+
+
+def test_pair_batch_runner_matches_single_pairs(dev_lib):
+    """b200.multi.PairBatchRunner (the per-rank unit of the sharded many-frames mode): its per-pair statistics equal those of
+    the same pairs run one at a time."""
+    from b200 import multi, runtime as rt_mod
+    rt = rt_mod.CudaRuntime(0)
+    rt_mod.set_runtime(rt)
+    H, W = 128, 416
+    w = synth.liteflownet_weights()
+    imgs = [rt.from_host(synth.value_noise_image(H, W, s)) for s in (1, 2, 3, 4, 5, 6)]
+    all3 = multi.PairBatchRunner(rt, H, W, 3, w).forward(imgs)
+    one = multi.PairBatchRunner(rt, H, W, 1, w)
+    for p in range(3):
+        assert np.array_equal(one.forward(imgs[2 * p:2 * p + 2])[0], all3[p]), p
+    assert all3.shape == (3, 2) and (all3[:, 0] > 0).all()

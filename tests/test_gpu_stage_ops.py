@@ -23,7 +23,7 @@ def cu(a):
 
 
 @pytest.mark.parametrize("B,C,H,W,s", [(2, 192, 11, 38, 1), (2, 128, 22, 76, 1), (2, 96, 44, 152, 1),
-                                       (2, 64, 88, 304, 2), (1, 64, 35, 51, 2), (1, 32, 9, 13, 1)])
+                                       (2, 64, 88, 304, 2), (2, 64, 176, 608, 2), (1, 64, 35, 51, 2), (1, 32, 9, 13, 1)])
 @pytest.mark.parametrize("prec", [0, 1])
 def test_correlation(dev_lib, B, C, H, W, s, prec):
     rs = np.random.RandomState(C + H)
@@ -178,6 +178,16 @@ TC_CASES = [
     (3, 16, 9, 130, 16, 3, 3, 1, 1, 3),        # odd sizes, elu, minimum channels
 ]
 
+# the level-2 layers that carry 69 % of the frame's FLOPs (176x608x2, multi-wave persistent CTAs, S = 2 / 4 sub-tiles)
+TC_BIG_CASES = [
+    (2, 128, 176, 608, 128, 3, 3, 1, 1, 1),    # S = 2, block_n 128, 836 tiles over 148 CTAs
+    (2, 130, 176, 608, 128, 3, 3, 1, 1, 1),    # Subpixel Main.0: 144-channel input with a partial last chunk
+    (2, 128, 176, 608, 64, 3, 3, 1, 1, 1),     # S = 4, block_n 64
+    (2, 64, 176, 608, 32, 3, 3, 1, 1, 1),      # S = 4, block_n 32
+    (2, 32, 176, 608, 64, 1, 1, 0, 0, 1),      # 1x1, store-bound
+    (2, 32, 176, 608, 49, 7, 1, 3, 0, 0),      # distance conv 7x1 -> 49 (zero-padded to 64)
+]
+
 TC_S2_CASES = [
     # B, Cin, H, W, Cout, k, pad, act -- stride-2 convs (5-D tensor map over the 2x2 pixel phases)
     (2, 32, 64, 96, 32, 3, 1, 1), (2, 64, 44, 152, 96, 3, 1, 1), (1, 128, 22, 76, 192, 3, 1, 1),
@@ -204,22 +214,49 @@ def test_conv2d_tcgen05_stride2(dev_lib, case):
 
 
 
-@pytest.mark.parametrize("case", TC_CASES)
-def test_conv2d_tcgen05(dev_lib, case):
+def tf32_round(x):
+    """Round float32 to the 10-bit-mantissa tf32 grid (round to nearest, ties away: cvt.rna.tf32.f32)."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def _tc_conv_check(dev_lib, case, prec, stride=1):
+    """tcgen05 conv (prec 1: kind::f16 on bf16 operands; prec 2: kind::tf32 on fp32 operands) vs an fp64 convolution of the
+    operands rounded to the tensor core's input format.  Tolerances: bf16 output rounding 2^-9; tf32 mode stores fp32
+    rounded to tf32 (2^-11) and the activations are rounded once more on the way in."""
     B, Cin, H, W, Cout, kh, kw, py, px, act = case
     rs = np.random.RandomState(Cin + 13 * Cout + kh)
-    x = bf16_round(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
-    w = bf16_round((rs.standard_normal((Cout, Cin, kh, kw)) / np.sqrt(Cin * kh * kw)).astype(np.float32))
+    rnd = bf16_round if prec == 1 else tf32_round
+    x = rnd(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
+    w = rnd((rs.standard_normal((Cout, Cin, kh, kw)) / np.sqrt(Cin * kh * kw)).astype(np.float32))
     b = (rs.standard_normal(Cout) * 0.1).astype(np.float32)
-    y = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=(py, px))
+    y = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), stride=stride, padding=(py, px))
     y = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.1), 2: F.relu, 3: F.elu}[act](y).float().numpy()
     dx = cu(x)
     out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
     dev_lib.check(dev_lib.dfvo_conv2d(dptr(dx), w.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
-                                      dptr(out), B, Cin, H, W, Cout, kh, kw, 1, py, px, 0, act, 1, None))
+                                      dptr(out), B, Cin, H, W, Cout, kh, kw, stride, py, px, 0, act, prec, None))
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     err = np.abs(got - y)
-    tol = 8e-3 * np.abs(y) + 4e-3          # bf16 output rounding (2^-9 rel) + fp32 accumulation order
+    tol = (8e-3 * np.abs(y) + 4e-3) if prec == 1 else (1e-3 * np.abs(y) + 5e-4)
     assert (err <= tol).all(), "max err %g at %s (ref %g got %g)" % (
         err.max(), np.unravel_index(err.argmax(), err.shape), y.flat[err.argmax()], got.flat[err.argmax()])
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tcgen05(dev_lib, case, prec):
+    _tc_conv_check(dev_lib, case, prec)
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("case", TC_BIG_CASES)
+def test_conv2d_tcgen05_level2_shapes(dev_lib, case, prec):
+    _tc_conv_check(dev_lib, case, prec)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 64, 96, 32, 3, 3, 1, 1, 1), (1, 128, 22, 76, 192, 3, 3, 1, 1, 1), (2, 32, 352, 1216, 32, 3, 3, 1, 1, 1)])
+def test_conv2d_tcgen05_stride2_tf32(dev_lib, case):
+    _tc_conv_check(dev_lib, case, 2, stride=2)

@@ -69,6 +69,11 @@ def _worker(rank, world, port, out_dir):
     ms = multi.max_over_ranks(10.0 + rank)
     assert ms == 10.0 + world - 1
     allp = multi.gather_trajectories(poses, dst=0)
+    # ---- pair-level sharding (batched many-frames mode): ragged contiguous blocks, one all_gather of per-pair statistics
+    sh = multi.PairShard(5, rank, world)
+    stats = np.stack([np.arange(sh.first, sh.first + sh.count, dtype=np.float64), 0.5 + np.arange(sh.first, sh.first + sh.count)], 1)
+    allstats = multi.gather_pair_stats(stats, sh, world)
+    assert allstats.shape == (5, 2) and np.array_equal(allstats[:, 0], np.arange(5.0)) and np.array_equal(allstats[:, 1], 0.5 + np.arange(5.0))
     if rank == 0:
         np.save(os.path.join(out_dir, "owned.npy"), np.array([multi.rank_sequences(5, r, world) for r in range(world)], dtype=object),
                 allow_pickle=True)
@@ -102,4 +107,13 @@ def test_layout_roundtrip():
     a2, b2 = multi.unpack_weights(flat * 2, table, [dict(a), dict(b)])
     assert np.array_equal(a2["w"], a["w"] * 2) and a2["n"] == 3 and np.array_equal(b2["b"], 2 * b["b"])
     assert multi.rank_sequences(7, 1, 3) == [1, 4]
+    # pair shards: contiguous, disjoint, covering, for every world size that does or does not divide the total
+    for total, world in ((64, 1), (64, 2), (64, 8), (64, 3), (5, 8)):
+        cover = []
+        for r in range(world):
+            sh = multi.PairShard(total, r, world)
+            cover += list(range(sh.first, sh.first + sh.count))
+            assert sh.owner_table()[r] == (sh.first, sh.count)
+        assert cover == list(range(total))
+    assert np.array_equal(multi.gather_pair_stats([[1.0, 2.0]], multi.PairShard(1, 0, 1), 1), [[1.0, 2.0]])
     assert multi.max_over_ranks(3.5) == 3.5
