@@ -373,7 +373,7 @@ def bench_ransac10k(rt, iters=10):
     M, N = 10000, 2048
     # hypotheses: 5-point solutions of random minimal samples (first root of each) -- generated on the device, not timed
     rs = np.random.RandomState(0)
-    ms_ = 4000
+    ms_ = 6000
     sub = np.stack([rs.choice(N, 5, replace=False) for _ in range(ms_)])
     d1, d2 = rt.from_host(np.ascontiguousarray(x1[sub])), rt.from_host(np.ascontiguousarray(x2[sub]))
     dE, dn = rt.empty((ms_, 10, 9), np.float64), rt.empty((ms_,), np.int32)

@@ -143,14 +143,14 @@ static int stage_warp(const float* input, const float* flow, float* out, int B, 
 
 template <typename T>
 static int stage_conv(const float* x, const HostTensor& w, const HostTensor* b, float* y, int B, int Cin, int H, int W, int Cout,
-                      int kh, int kw, int stride, int pad_y, int pad_x, int reflect, int act, cudaStream_t s) {
+                      int kh, int kw, int stride, int pad_y, int pad_x, int reflect, int act, cudaStream_t s, bool tf32 = false) {
   Arena a;
-  const bool is_bf16 = sizeof(T) == 2;
+  const bool is_bf16 = sizeof(T) == 2 || tf32;          // "tensor-core layer": bf16 operands, or fp32 operands read as tf32
   const int Cp = (Cin + 15) / 16 * 16, Cop = (Cout + 15) / 16 * 16;
   const int Ho = (H + 2 * pad_y - kh) / stride + 1, Wo = (W + 2 * pad_x - kw) / stride + 1;
   ConvLayer L;
   int rc;
-  if ((rc = build_conv_layer(a, w, b, {{Cin, Cp}}, stride, pad_y, pad_x, reflect, is_bf16, !is_bf16, nullptr, nullptr, &L))) return rc;
+  if ((rc = build_conv_layer(a, w, b, {{Cin, Cp}}, stride, pad_y, pad_x, reflect, is_bf16, !is_bf16, nullptr, nullptr, &L, sizeof(T) == 2 ? 2 : 4))) return rc;
   float* f32 = a.alloc_t<float>((size_t)B * H * W * Cp);
   T* ti = a.alloc_t<T>((size_t)B * H * W * Cp);
   T* to = a.alloc_t<T>((size_t)B * Ho * Wo * Cop);
@@ -317,6 +317,8 @@ int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, flo
     return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
   DFVO_REQUIRE((stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0 && kh % 2 == 1 && pad_y == kh / 2 && pad_x == kw / 2)) && !reflect,
                DFVO_EINVAL, "dfvo_conv2d: the tcgen05 path needs stride 1, or stride 2 on even sizes with 'same' padding; zero padding");
+  if (precision == DFVO_PREC_TF32)
+    return stage_conv<float>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream, true);
   return stage_conv<bf16>(x, w, bias_host ? &b : nullptr, y, B, Cin, H, W, Cout, kh, kw, stride, pad_y, pad_x, reflect, act, (cudaStream_t)stream);
   API_END
 }

@@ -34,6 +34,8 @@ struct ConvHaloK {
   int HW, HH;                    // halo box, pixels
   int block_n, a_stages, b_stages, a_stage_bytes, acc_cols, tmem_cols;
   int Cout, Cout_pad, act, out_f32, zero_pad_to;
+  int chunk;                     // channels per 128-byte operand row: 64 (bf16) or 32 (fp32 read as tf32)
+  int esize, round_tf32;
   const float* bias;
   void* out; long long oN, oH, oW;
   const void* res; long long rN, rH, rW;
@@ -42,7 +44,7 @@ struct ConvHaloK {
 #define HALO_THREADS 352
 #define HALO_TH 16
 
-template <int S>
+template <int S, int TF32>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -102,7 +104,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int x0 = tx * 8 * S + p.dx0, y0 = ty * HALO_TH + p.dy0;
       for (int s = 0; s < p.nsrc; ++s) {
         const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
-        for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+        for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
           mbar_wait(a_empty(stage), phase ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(a_full(stage), a_bytes);
@@ -120,7 +122,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int nb = tile / (p.tiles_x * p.tiles_y * p.N);
       int kofs = 0;
       for (int s = 0; s < p.nsrc; ++s) {
-        for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+        for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
           for (int tap = 0; tap < ntaps; ++tap) {
             mbar_wait(b_empty(stage), phase ^ 1u);
             if (elect_one()) {
@@ -141,8 +143,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     // loop invariant lives in a register, descriptors advance by adds): a single thread issues dependent instructions
     // ~4-8 clk apart, and an N = 64 MMA is only 32 tensor clocks long, so a fat loop body starves the tensor pipe
     // (measured: 50 % tensor-pipe activity with ~130 instructions per tap, MMA warp never waiting for data).
-    // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = tc_idesc(TF32, p.block_n);
     // descriptor words: lo = start>>4 [0,14) | LBO (unused for swizzled K-major, 1) [16,30);
     //                   hi = SBO>>4 [0,14) | version 1 [14,16) | SWIZZLE_128B (2) [29,32).  A: SBO = one halo row; B: 1024 B
     const uint32_t a_hi = (((uint32_t)p.HW * 128u) >> 4) | (1u << 14) | (2u << 29);
@@ -165,12 +166,12 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_cols);
       uint32_t fresh = 0;                         // 0 for the first (chunk, tap) of the tile: its ks = 0 MMAs overwrite
       for (int s = 0; s < p.nsrc; ++s) {
-        for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+        for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
           mbar_wait(a_full(astage), aphase);
           tc_fence_after();
           const uint32_t a_lo0 = (((a_base + (uint32_t)astage * (uint32_t)p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           const int rem = p.srcC[s] - c0;
-          const int nks = (rem >= 64 ? 64 : rem) >> 4;       // K=16 steps with real channels
+          const int nks = ((rem >= p.chunk ? p.chunk : rem) * p.esize) >> 5;       // 32-byte K steps (16 bf16 / 8 tf32) with real channels
           if (elect_one()) {
             uint32_t a_lo = a_lo0;                             // + (ky * HW + kx) pixels * 128 B, in 16-B units
             uint32_t b_lo = b_lo_base + (uint32_t)bstage * b_lo_step;
@@ -184,17 +185,17 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 #pragma unroll
                   for (int sub = 0; sub < S; ++sub) {
                     const uint32_t d = tmem_d + (uint32_t)sub * bn, al = a_lo + (uint32_t)sub * 64u;            // +8 pixels
-                    tc_mma_bf16_lohi(d, al, a_hi, b_lo, b_hi, idesc, fresh);
-                    tc_mma_bf16_lohi(d, al + 2u, a_hi, b_lo + 2u, b_hi, idesc, 1u);       // +32 B inside the swizzle atom
-                    tc_mma_bf16_lohi(d, al + 4u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
-                    tc_mma_bf16_lohi(d, al + 6u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
+                    tc_mma_lohi<TF32>(d, al, a_hi, b_lo, b_hi, idesc, fresh);
+                    tc_mma_lohi<TF32>(d, al + 2u, a_hi, b_lo + 2u, b_hi, idesc, 1u);       // +32 B inside the swizzle atom
+                    tc_mma_lohi<TF32>(d, al + 4u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
+                    tc_mma_lohi<TF32>(d, al + 6u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
                   }
                 } else {
 #pragma unroll
                   for (int sub = 0; sub < S; ++sub) {
                     const uint32_t d = tmem_d + (uint32_t)sub * bn, al = a_lo + (uint32_t)sub * 64u;
                     for (int ks = 0; ks < nks; ++ks)
-                      tc_mma_bf16_lohi(d, al + 2u * ks, a_hi, b_lo + 2u * ks, b_hi, idesc, ks == 0 ? fresh : 1u);
+                      tc_mma_lohi<TF32>(d, al + 2u * ks, a_hi, b_lo + 2u * ks, b_hi, idesc, ks == 0 ? fresh : 1u);
                   }
                 }
                 tc_commit(be);
@@ -233,7 +234,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     for (int i = threadIdx.x - 96; i < p.Cout_pad; i += 256) bias_s[i] = p.bias ? p.bias[i] : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
-    TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.out = p.out; ep.res = p.res;
+    TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.round_tf32 = p.round_tf32; ep.out = p.out; ep.res = p.res;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
@@ -330,8 +331,9 @@ static bool halo_fit(int S, int bn, int kh, int kw, int Cout_pad, HaloCfg* out) 
 // MMA time per K=16 step = max(block_n/2, 32 + block_n/4) clk (tensor floor vs shared-memory operand reads),
 // L2->SM ~ 43 B/clk per SM when every SM streams (chip cap 6.3 KB/clk), up to ~3x that for a lone CTA.
 static bool halo_choose(const ConvTc& c, int kh, int kw, HaloCfg* best) {
-  int ktot16 = 0, kbytes = 0;
-  for (int s = 0; s < c.nsrc; ++s) { ktot16 += (c.src[s].C + 15) / 16; kbytes += c.src[s].C * 2; }
+  int ktot16 = 0, kbytes = 0;                       // 32-byte K steps and bytes per pixel over all sources
+  const int es = c.esize == 4 ? 4 : 2;
+  for (int s = 0; s < c.nsrc; ++s) { ktot16 += (c.src[s].C * es + 31) / 32; kbytes += c.src[s].C * es; }
   const int nsm = tc_num_sms();
   const int fS = env_int("DFVO_HALO_S", 0), fN = env_int("DFVO_HALO_BN", 0);
   bool found = false;
@@ -386,10 +388,12 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
   int cols = 32; while (cols < 2 * k.acc_cols) cols <<= 1;
   k.tmem_cols = cols;
   k.nsrc = c.nsrc;
+  const int es = c.esize == 4 ? 4 : 2;
+  k.esize = es; k.chunk = 128 / es; k.round_tf32 = c.round_out_tf32;
   int ktot = 0;
   for (int i = 0; i < c.nsrc; ++i) {
     DFVO_REQUIRE(c.src[i].C % 16 == 0 && c.src[i].C > 0, DFVO_EINVAL, "conv_halo: source %d channels %d not a multiple of 16", i, c.src[i].C);
-    DFVO_REQUIRE(((uintptr_t)c.src[i].p & 15) == 0 && c.src[i].sW % 8 == 0 && c.src[i].sH % 8 == 0 && c.src[i].sN % 8 == 0,
+    DFVO_REQUIRE(((uintptr_t)c.src[i].p & 15) == 0 && (c.src[i].sW * es) % 16 == 0 && (c.src[i].sH * es) % 16 == 0 && (c.src[i].sN * es) % 16 == 0,
                  DFVO_EINVAL, "conv_halo: source %d not 16-byte aligned/strided", i);
     k.srcC[i] = c.src[i].C; ktot += c.src[i].C;
   }
@@ -403,23 +407,26 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
     const ConvTcSource& src = c.src[i < c.nsrc ? i : 0];
     const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
     unsigned long long dims[4] = {(unsigned long long)src.C, (unsigned long long)inW, (unsigned long long)inH, (unsigned long long)c.N};
-    unsigned long long str[3] = {(unsigned long long)src.sW * 2, (unsigned long long)src.sH * 2, (unsigned long long)src.sN * 2};
-    unsigned box[4] = {64, (unsigned)k.HW, (unsigned)k.HH, 1};
-    int rc = tc_encode_map(&tmA[i], src.p, 4, dims, str, box);
+    unsigned long long str[3] = {(unsigned long long)src.sW * es, (unsigned long long)src.sH * es, (unsigned long long)src.sN * es};
+    unsigned box[4] = {(unsigned)k.chunk, (unsigned)k.HW, (unsigned)k.HH, 1};
+    int rc = tc_encode_map(&tmA[i], src.p, 4, dims, str, box, es);
     if (rc) return rc;
   }
   {
     unsigned long long dims[3] = {(unsigned long long)ktot, (unsigned long long)c.Cout_pad, (unsigned long long)c.ntaps};
-    unsigned long long str[2] = {(unsigned long long)ktot * 2, (unsigned long long)ktot * 2 * (unsigned long long)c.Cout_pad};
-    unsigned box[3] = {64, (unsigned)k.block_n, 1};
-    int rc = tc_encode_map(&tmB, c.w, 3, dims, str, box);
+    unsigned long long str[2] = {(unsigned long long)ktot * es, (unsigned long long)ktot * es * (unsigned long long)c.Cout_pad};
+    unsigned box[3] = {(unsigned)k.chunk, (unsigned)k.block_n, 1};
+    int rc = tc_encode_map(&tmB, c.w, 3, dims, str, box, es);
     if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_halo<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = k.ntiles < tc_num_sms() ? k.ntiles : tc_num_sms();
@@ -428,12 +435,18 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
   const bool prof = tc_prof_begin(s, &pr);
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
   tc_launch_config(&cfg, &attr, grid, HALO_THREADS, h.smem, s);
-  if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1>, tmA[0], tmA[1], tmA[2], tmB, k));
-  else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2>, tmA[0], tmA[1], tmA[2], tmB, k));
-  else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4>, tmA[0], tmA[1], tmA[2], tmB, k));
+  if (es == 2) {
+    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
+    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
+    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
+  } else {
+    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
+    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
+    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
+  }
   if (prof) {
     char d[256];
-    snprintf(d, sizeof(d), "halo N%d %dx%d k%dx%d src[%d,%d,%d] cout%d/%d bn%d S%d stages%d/%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,
+    snprintf(d, sizeof(d), "halo%s N%d %dx%d k%dx%d src[%d,%d,%d] cout%d/%d bn%d S%d stages%d/%d grid%d tiles%d gflop %.3f", es == 4 ? "-tf32" : "", c.N, c.H, c.W,
              k.kh, k.kw, c.src[0].C, c.nsrc > 1 ? c.src[1].C : 0, c.nsrc > 2 ? c.src[2].C : 0, c.Cout, c.Cout_pad, k.block_n,
              k.S, k.a_stages, k.b_stages, grid, k.ntiles, c.flops * 1e-9);
     tc_prof_end(s, pr, c.flops, d);

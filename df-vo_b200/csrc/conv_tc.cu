@@ -49,6 +49,7 @@ struct ConvTcK {
   int stride, src_pitch;        // src_pitch (elements) = channel offset of the odd pixel inside a double-pixel
   int block_n, stages, acc_stride, tmem_cols;
   int Cout, Cout_pad, act, out_f32, zero_pad_to;
+  int chunk, esize, round_tf32;   // channels per 128-byte operand row (64 bf16 / 32 tf32), operand element size
   const float* bias;
   void* out; long long oN, oH, oW;
   const void* res; long long rN, rH, rW;
@@ -61,6 +62,7 @@ struct ConvTcK {
 #define TC_THREADS 320
 #define TC_A_BYTES 16384
 
+template <int TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -101,7 +103,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   pdl_wait();                                  // from here on: activations of the previous kernel / our output buffers
 
   int chunks_total = 0;
-  for (int s = 0; s < p.nsrc; ++s) chunks_total += (p.srcC[s] + 63) >> 6;
+  for (int s = 0; s < p.nsrc; ++s) chunks_total += (p.srcC[s] + p.chunk - 1) / p.chunk;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -117,7 +119,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         int kofs = 0;
         for (int s = 0; s < p.nsrc; ++s) {
           const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
-          for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+          for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
@@ -137,8 +139,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
-    // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = tc_idesc(TF32, p.block_n);
     const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -149,22 +150,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       uint32_t fresh = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int s = 0; s < p.nsrc; ++s) {
-          for (int c0 = 0; c0 < p.srcC[s]; c0 += 64) {
+          for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = (((sa + TC_A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
               const int rem = p.srcC[s] - c0;
-              const int nks = (rem >= 64 ? 64 : rem) >> 4;       // K=16 steps with real channels
+              const int nks = ((rem >= p.chunk ? p.chunk : rem) * p.esize) >> 5;       // 32-byte K steps with real channels
               if (nks == 4) {
-                tc_mma_bf16_lohi(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, fresh);
-                tc_mma_bf16_lohi(tmem_d, a_lo + 2u, d_hi, b_lo + 2u, d_hi, idesc, 1u);   // +32 B inside the 128-B swizzle atom
-                tc_mma_bf16_lohi(tmem_d, a_lo + 4u, d_hi, b_lo + 4u, d_hi, idesc, 1u);
-                tc_mma_bf16_lohi(tmem_d, a_lo + 6u, d_hi, b_lo + 6u, d_hi, idesc, 1u);
+                tc_mma_lohi<TF32>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, fresh);
+                tc_mma_lohi<TF32>(tmem_d, a_lo + 2u, d_hi, b_lo + 2u, d_hi, idesc, 1u);   // +32 B inside the 128-B swizzle atom
+                tc_mma_lohi<TF32>(tmem_d, a_lo + 4u, d_hi, b_lo + 4u, d_hi, idesc, 1u);
+                tc_mma_lohi<TF32>(tmem_d, a_lo + 6u, d_hi, b_lo + 6u, d_hi, idesc, 1u);
               } else {
                 for (int ks = 0; ks < nks; ++ks)
-                  tc_mma_bf16_lohi(tmem_d, a_lo + 2u * ks, d_hi, b_lo + 2u * ks, d_hi, idesc, ks == 0 ? fresh : 1u);
+                  tc_mma_lohi<TF32>(tmem_d, a_lo + 2u * ks, d_hi, b_lo + 2u * ks, d_hi, idesc, ks == 0 ? fresh : 1u);
               }
               tc_commit(empty_bar(stage));
             }
@@ -208,7 +209,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
 
-      TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.out = p.out; ep.res = p.res;
+      TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.round_tf32 = p.round_tf32; ep.out = p.out; ep.res = p.res;
       auto process = [&](const uint32_t* v, int col) {
         const int c = cbase + col;
         if (inb && c < p.zero_pad_to) tc_epilogue16(ep, v, bias4, c, opix, rpix);
@@ -259,7 +260,8 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims_, const unsigned long long* strides_, const unsigned* box_) {
+int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims_, const unsigned long long* strides_, const unsigned* box_,
+                  int esize) {
   cuuint64_t dims[5], str[5];
   cuuint32_t box[5];
   for (int i = 0; i < rank; ++i) { dims[i] = dims_[i]; box[i] = box_[i]; if (i < rank - 1) str[i] = strides_[i]; }
@@ -268,7 +270,7 @@ int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long
   PFN_encodeTiled enc = get_encode();
   DFVO_REQUIRE(enc != nullptr, DFVO_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
+  CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DFVO_REQUIRE(r == CUDA_SUCCESS, DFVO_ECUDA, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r,
@@ -301,10 +303,11 @@ int tc_num_sms() {
   }
   return g_num_sms;
 }
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                      int esize) {
   unsigned long long d[5], st[5]; unsigned b[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i < rank - 1) st[i] = strides_bytes[i]; }
-  return tc_encode_map(m, ptr, rank, d, st, b);
+  return tc_encode_map(m, ptr, rank, d, st, b, esize);
 }
 
 static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
@@ -321,10 +324,12 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
   k.n_blocks = c.Cout_pad / k.block_n;
   k.ntiles = k.tiles_x * k.tiles_y * c.N * k.n_blocks;
   k.nsrc = c.nsrc; k.ntaps = c.ntaps;
+  const int es = c.esize == 4 ? 4 : 2;
+  k.esize = es; k.chunk = 128 / es; k.round_tf32 = c.round_out_tf32;
   int ktot = 0;
   for (int s = 0; s < c.nsrc; ++s) {
     DFVO_REQUIRE(c.src[s].C % 16 == 0 && c.src[s].C > 0, DFVO_EINVAL, "conv_tc: source %d channels %d not a multiple of 16", s, c.src[s].C);
-    DFVO_REQUIRE(((uintptr_t)c.src[s].p & 15) == 0 && c.src[s].sW % 8 == 0 && c.src[s].sH % 8 == 0 && c.src[s].sN % 8 == 0,
+    DFVO_REQUIRE(((uintptr_t)c.src[s].p & 15) == 0 && (c.src[s].sW * es) % 16 == 0 && (c.src[s].sH * es) % 16 == 0 && (c.src[s].sN * es) % 16 == 0,
                  DFVO_EINVAL, "conv_tc: source %d not 16-byte aligned/strided", s);
     k.srcC[s] = c.src[s].C; ktot += c.src[s].C;
   }
@@ -366,24 +371,24 @@ static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {
       // at [pitch, pitch+C); (py, px) of a tap select the phase, the box walks W/2 x H/2 cells of the output tile
       const int inW2 = c.W, inH2 = c.H;
       cuuint64_t dims[5] = {(cuuint64_t)(src.sW + src.C), (cuuint64_t)inW2, 2, (cuuint64_t)inH2, (cuuint64_t)c.N};
-      cuuint64_t str[4] = {(cuuint64_t)src.sW * 4, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sH * 4, (cuuint64_t)src.sN * 2};
-      cuuint32_t box[5] = {64, (cuuint32_t)k.tw, 1, (cuuint32_t)k.th, 1};
-      int rc = encode_map(&pl->tmA[s], src.p, 5, dims, str, box);
+      cuuint64_t str[4] = {(cuuint64_t)src.sW * 2 * es, (cuuint64_t)src.sH * es, (cuuint64_t)src.sH * 2 * es, (cuuint64_t)src.sN * es};
+      cuuint32_t box[5] = {(cuuint32_t)k.chunk, (cuuint32_t)k.tw, 1, (cuuint32_t)k.th, 1};
+      int rc = encode_map(&pl->tmA[s], src.p, 5, dims, str, box, es);
       if (rc) return rc;
       continue;
     }
     const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
     cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)inW, (cuuint64_t)inH, (cuuint64_t)c.N};
-    cuuint64_t str[3] = {(cuuint64_t)src.sW * 2, (cuuint64_t)src.sH * 2, (cuuint64_t)src.sN * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)k.tw, (cuuint32_t)k.th, 1};
-    int rc = encode_map(&pl->tmA[s], src.p, 4, dims, str, box);
+    cuuint64_t str[3] = {(cuuint64_t)src.sW * es, (cuuint64_t)src.sH * es, (cuuint64_t)src.sN * es};
+    cuuint32_t box[4] = {(cuuint32_t)k.chunk, (cuuint32_t)k.tw, (cuuint32_t)k.th, 1};
+    int rc = encode_map(&pl->tmA[s], src.p, 4, dims, str, box, es);
     if (rc) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)c.Cout_pad, (cuuint64_t)c.ntaps};
-    cuuint64_t str[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * 2 * (cuuint64_t)c.Cout_pad};
-    cuuint32_t box[3] = {64, (cuuint32_t)k.block_n, 1};
-    int rc = encode_map(&pl->tmB, c.w, 3, dims, str, box);
+    cuuint64_t str[2] = {(cuuint64_t)ktot * es, (cuuint64_t)ktot * es * (cuuint64_t)c.Cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)k.chunk, (cuuint32_t)k.block_n, 1};
+    int rc = encode_map(&pl->tmB, c.w, 3, dims, str, box, es);
     if (rc) return rc;
   }
   return DFVO_OK;
@@ -437,7 +442,8 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    DFVO_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   ++g_launch_count;
@@ -445,7 +451,8 @@ int conv_tc(const ConvTc& c, cudaStream_t s) {
   const bool prof = tc_prof_begin(s, &pr);
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
   tc_launch_config(&cfg, &attr, pl.grid, TC_THREADS, pl.smem, s);
-  DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc, pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k));
+  if (pl.k.esize == 4) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<1>, pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k));
+  else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<0>, pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmB, pl.k));
   if (prof) {
     char d[256];
     snprintf(d, sizeof(d), "tap  N%d %dx%d s%d taps%d src[%d,%d,%d] cout%d/%d bn%d tile%dx%d stages%d grid%d tiles%d gflop %.3f", c.N, c.H, c.W,
@@ -481,12 +488,13 @@ int conv_tc(const ConvTc& c, cudaStream_t) {
           if (iy < 0 || iy >= inH || ix < 0 || ix >= inW) continue;
           int kofs = 0;
           for (int s = 0; s < c.nsrc; ++s) {
-            const bf16* a = c.src[s].p + n * c.src[s].sN + iy * c.src[s].sH + ix * c.src[s].sW;
+            const size_t eoff = n * c.src[s].sN + iy * c.src[s].sH + ix * c.src[s].sW;
             for (int ci = 0; ci < c.src[s].C; ++ci) {
-              float av = __bfloat162float(a[ci]);
+              const float av = c.esize == 4 ? ((const float*)c.src[s].p)[eoff + ci] : __bfloat162float(((const bf16*)c.src[s].p)[eoff + ci]);
               if (av == 0.f) continue;
-              const bf16* w = c.w + ((size_t)t * c.Cout_pad) * ktot + kofs + ci;
-              for (int co = 0; co < c.Cout_pad; ++co) acc[co] += av * __bfloat162float(w[(size_t)co * ktot]);
+              const size_t woff = ((size_t)t * c.Cout_pad) * ktot + kofs + ci;
+              for (int co = 0; co < c.Cout_pad; ++co)
+                acc[co] += av * (c.esize == 4 ? ((const float*)c.w)[woff + (size_t)co * ktot] : __bfloat162float(((const bf16*)c.w)[woff + (size_t)co * ktot]));
             }
             kofs += c.src[s].C;
           }

@@ -48,6 +48,7 @@ template <> struct IsBf16<bf16> { enum { v = 1 }; };
 template <typename T>
 struct LfnImpl : public LiteFlowNetBase {
   Arena arena;
+  bool tf32 = false;          // T = float only: convs on tcgen05 kind::tf32 (DFVO_PREC_TF32) instead of the CUDA-core kernel
   int H0 = 0, W0 = 0, th = 0, tw = 0, B = 0, P = 0;
   int lh[7], lw[7];
   // weights
@@ -89,8 +90,10 @@ struct LfnImpl : public LiteFlowNetBase {
     const HostTensor* w = find_weight(ws, name + ".weight");
     const HostTensor* b = find_weight(ws, name + ".bias");
     DFVO_REQUIRE(w != nullptr, DFVO_ESTATE, "missing weight %s.weight", name.c_str());
-    bool want_tc = IsBf16<T>::v && tc_ok;
-    return build_conv_layer(arena, *w, b, segs, stride, pad_y, pad_x, 0, want_tc, !want_tc, nullptr, nullptr, L);
+    const bool want_tc = (IsBf16<T>::v || tf32) && tc_ok;
+    // fp32 / tf32 modes keep the CUDA-core weights as well (2-channel heads, debugging)
+    return build_conv_layer(arena, *w, b, segs, stride, pad_y, pad_x, 0, want_tc, !want_tc || !IsBf16<T>::v, nullptr, nullptr, L,
+                            IsBf16<T>::v ? 2 : 4);
   }
   int raw_weight(const WeightStore& ws, const std::string& key, size_t n, float** out) {
     const HostTensor* w = find_weight(ws, key);
@@ -110,7 +113,7 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 1; L <= 6; ++L) { lh[L] = th >> (L - 1); lw[L] = tw >> (L - 1); }
     // ---------------- weights ----------------
     const std::string F = "moduleFeatures.";
-    if (IsBf16<T>::v) {
+    if (IsBf16<T>::v || tf32) {
       // stem on tensor cores: 7x7x3 -> 7x1 over a horizontal window of pixels.
       //   window mode (default): K = 64 = 8 pixels x 8 channels read straight from the column-padded image through an
       //     overlapping-box tensor map (flow_ops.cu::pad_image8), w'[co][px*8+c][ky] = w[co][c][ky][px], px < 7, c < 3;
@@ -119,7 +122,7 @@ struct LfnImpl : public LiteFlowNetBase {
       const HostTensor* b7 = find_weight(ws, F + "moduleOne.0.bias");
       DFVO_REQUIRE(w7 && w7->shape.size() == 4 && w7->shape[1] == 3 && w7->shape[2] == 7 && w7->shape[3] == 7, DFVO_ESTATE, "moduleOne weight");
       const char* env = getenv("DFVO_STEM_WINDOW");
-      stem_window = !(env && atoi(env) == 0);
+      stem_window = IsBf16<T>::v && !(env && atoi(env) == 0);          // the 64-element window needs 2-byte elements (128-byte box rows)
       const int kk = stem_window ? 64 : 21, cs = stem_window ? 8 : 3;
       HostTensor wr;
       wr.shape = {w7->shape[0], kk, 7, 1};
@@ -133,7 +136,7 @@ struct LfnImpl : public LiteFlowNetBase {
         TRY(build_conv_layer(arena, wr, b7, {{64, 64}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
         fOne.Cin_ref = 21;                       // algorithmic FLOPs of the layer: 7 x 7 x 3 real taps per output channel
       } else {
-        TRY(build_conv_layer(arena, wr, b7, {{21, 32}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne));
+        TRY(build_conv_layer(arena, wr, b7, {{21, 32}}, 1, 3, 0, 0, true, false, nullptr, nullptr, &fOne, IsBf16<T>::v ? 2 : 4));
       }
     } else {
       TRY(conv_layer(ws, F + "moduleOne.0", {{3, 3}}, 1, 3, 3, false, &fOne));
@@ -195,7 +198,7 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 1; L <= 6; ++L) { img[L] = arena.alloc_t<float>(px(L) * 4); if (!img[L]) return DFVO_ENOMEM; }
 #define ALLOC(ptr, type, count) do { ptr = arena.alloc_t<type>(count); if (!ptr) return DFVO_ENOMEM; } while (0)
     ALLOC(f1buf, T, px(1) * 32);
-    ALLOC(rowbuf, T, (IsBf16<T>::v && !stem_window) ? px(1) * 32 : 64);
+    ALLOC(rowbuf, T, ((IsBf16<T>::v || tf32) && !stem_window) ? px(1) * 32 : 64);
     ALLOC(imgpad, T, (IsBf16<T>::v && stem_window) ? (size_t)B * lh[1] * (lw[1] + 8) * 8 + 64 : 64);
     ALLOC(t2a, T, px(2) * 32); ALLOC(t2b, T, px(2) * 32); ALLOC(feat2, T, px(2) * 32);
     ALLOC(t3a, T, px(3) * 64); ALLOC(t4a, T, px(4) * 96);
@@ -252,7 +255,7 @@ struct LfnImpl : public LiteFlowNetBase {
       Ten<const T> win; win.p = imgpad; win.N = B; win.H = lh[1]; win.W = lw[1]; win.C = 64;
       win.sW = 8; win.sH = (long long)(lw[1] + 8) * 8; win.sN = (long long)lh[1] * (lw[1] + 8) * 8;
       TRY(run_conv<T>(fOne, win, view(f1buf, 1, 32, 32), ACT_LEAKY, none, 0, s));
-    } else if (IsBf16<T>::v) {
+    } else if (IsBf16<T>::v || tf32) {
       TRY(im2row7<T>(cfview(img[1], 1, 3, 4), view(rowbuf, 1, 32, 32), s));
       TRY(run_conv<T>(fOne, cview(rowbuf, 1, 32, 32), view(f1buf, 1, 32, 32), ACT_LEAKY, none, 0, s));
     } else {
@@ -397,8 +400,9 @@ struct LfnImpl : public LiteFlowNetBase {
 
 int liteflownet_create(const WeightStore& ws, int H0, int W0, int pairs, int precision, LiteFlowNetBase** out) {
   *out = nullptr;
-  if (precision == 0) {
+  if (precision == 0 || precision == 2) {
     auto* p = new LfnImpl<float>();
+    p->tf32 = precision == 2;
     int rc = p->build(ws, H0, W0, pairs);
     if (rc) { delete p; return rc; }
     *out = p;

@@ -23,6 +23,7 @@ template <> struct IsBf16m<bf16> { enum { v = 1 }; };
 template <typename T>
 struct MonoImpl : public Monodepth2Base {
   Arena arena;
+  bool tf32 = false;          // T = float only: tcgen05 kind::tf32 convs (DFVO_PREC_TF32)
   int h = 0, w = 0;
   float min_depth = 0.1f, max_depth = 100.f, baseline = 5.4f;
   ConvLayer conv1;
@@ -57,16 +58,17 @@ struct MonoImpl : public Monodepth2Base {
       shift[c] = b->data[c] - m->data[c] * scale[c];
     }
     const int cp = cin == 3 ? 3 : cin;
-    bool want_tc = IsBf16m<T>::v && tc_ok;
-    return build_conv_layer(arena, *wgt, nullptr, {{cin, cp}}, stride, pad, pad, 0, want_tc, !want_tc, scale.data(), shift.data(), L);
+    const bool want_tc = (IsBf16m<T>::v || tf32) && tc_ok;
+    return build_conv_layer(arena, *wgt, nullptr, {{cin, cp}}, stride, pad, pad, 0, want_tc, !want_tc || !IsBf16m<T>::v, scale.data(), shift.data(), L,
+                            IsBf16m<T>::v ? 2 : 4);
   }
   int plain_conv(const WeightStore& ws, const std::string& name, int cin, bool tc_ok, ConvLayer* L) {
     const HostTensor* wgt = find_weight(ws, name + ".weight");
     const HostTensor* b = find_weight(ws, name + ".bias");
     DFVO_REQUIRE(wgt && b, DFVO_ESTATE, "missing weights for %s", name.c_str());
-    bool want_tc = IsBf16m<T>::v && tc_ok;
+    const bool want_tc = (IsBf16m<T>::v || tf32) && tc_ok;
     // input is pre-padded by upcat_reflect -> the conv itself has no padding
-    return build_conv_layer(arena, *wgt, b, {{cin, cin}}, 1, 0, 0, 0, want_tc, !want_tc, nullptr, nullptr, L);
+    return build_conv_layer(arena, *wgt, b, {{cin, cin}}, 1, 0, 0, 0, want_tc, !want_tc || !IsBf16m<T>::v, nullptr, nullptr, L, IsBf16m<T>::v ? 2 : 4);
   }
 
   int build(const WeightStore& ws, int feed_h, int feed_w, float mind, float maxd, float base) {
@@ -196,8 +198,9 @@ struct MonoImpl : public Monodepth2Base {
 int monodepth2_create(const WeightStore& ws, int feed_h, int feed_w, int precision, float min_depth, float max_depth,
                       float baseline, Monodepth2Base** out) {
   *out = nullptr;
-  if (precision == 0) {
+  if (precision == 0 || precision == 2) {
     auto* p = new MonoImpl<float>();
+    p->tf32 = precision == 2;
     int rc = p->build(ws, feed_h, feed_w, min_depth, max_depth, baseline);
     if (rc) { delete p; return rc; }
     *out = p;

@@ -44,6 +44,17 @@ const HostTensor* find_weight(const WeightStore& ws, const std::string& key) {
   return it == ws.end() ? nullptr : &it->second;
 }
 
+// fp32 -> tf32 grid (10-bit mantissa), round to nearest, ties away from zero (= cvt.rna.tf32.f32); the tensor core reads
+// the upper 19 bits of an fp32 operand, so pre-rounded weights make its truncation a no-op
+static float f2tf32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 static uint16_t f2bf(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -54,7 +65,7 @@ static uint16_t f2bf(float f) {
 
 int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, const std::vector<Seg>& segs,
                      int stride, int pad_y, int pad_x, int reflect, bool want_tc, bool want_direct,
-                     const float* scale, const float* shift, ConvLayer* L) {
+                     const float* scale, const float* shift, ConvLayer* L, int tc_esize) {
   DFVO_REQUIRE(w.shape.size() == 4, DFVO_ESHAPE, "conv weight must be 4-D");
   const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], kh = (int)w.shape[2], kw = (int)w.shape[3];
   int real = 0, ktot = 0;
@@ -64,6 +75,7 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
   L->pad_y = pad_y; L->pad_x = pad_x; L->reflect = reflect; L->Ktot = ktot;
   L->Cout_pad = (Cout + 15) / 16 * 16;
   L->tc = want_tc;
+  L->tc_esize = tc_esize;
   // padded-k -> reference channel (or -1)
   std::vector<int> kmap(ktot, -1);
   {
@@ -116,7 +128,20 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
     if (!L->w_head) return DFVO_ENOMEM;
     DFVO_CUDA(cudaMemcpy(L->w_head, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   }
-  if (want_tc) {
+  if (want_tc && tc_esize == 4) {
+    DFVO_REQUIRE((stride == 1 || stride == 2) && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1|2, zero pad, K %% 16 == 0");
+    std::vector<float> h((size_t)kh * kw * L->Cout_pad * ktot, 0.f);
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int co = 0; co < Cout; ++co) {
+          float* dst = &h[(((size_t)ky * kw + kx) * L->Cout_pad + co) * ktot];
+          for (int k = 0; k < ktot; ++k)
+            if (kmap[k] >= 0) dst[k] = f2tf32(W(co, kmap[k], ky, kx));
+        }
+    L->w_tc = arena.alloc(h.size() * 4);
+    if (!L->w_tc) return DFVO_ENOMEM;
+    DFVO_CUDA(cudaMemcpy(L->w_tc, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  } else if (want_tc) {
     DFVO_REQUIRE((stride == 1 || stride == 2) && !reflect && ktot % 16 == 0, DFVO_EINVAL, "tc conv needs stride 1|2, zero pad, K %% 16 == 0");
     std::vector<uint16_t> h((size_t)kh * kw * L->Cout_pad * ktot, 0);
     for (int ky = 0; ky < kh; ++ky)
@@ -126,7 +151,7 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
           for (int k = 0; k < ktot; ++k)
             if (kmap[k] >= 0) dst[k] = f2bf(W(co, kmap[k], ky, kx));
         }
-    L->w_tc = reinterpret_cast<bf16*>(arena.alloc(h.size() * 2));
+    L->w_tc = arena.alloc(h.size() * 2);
     if (!L->w_tc) return DFVO_ENOMEM;
     DFVO_CUDA(cudaMemcpy(L->w_tc, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -150,9 +175,38 @@ static ConvDirect to_direct(const ConvLayer& L, int act) {
   return d;
 }
 
+// common description of a tensor-core launch for either operand type
+template <typename T, typename TO>
+static int launch_tc(const ConvLayer& L, Ten<const T> in, Ten<TO> out, int act, Ten<const TO> residual, int zero_pad_to, int round_out,
+                     cudaStream_t s) {
+  DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc conv: input view has %d channels, layer expects %d", in.C, L.Ktot);
+  DFVO_REQUIRE((int)sizeof(T) == L.tc_esize, DFVO_ESTATE, "tc conv: layer packed for %d-byte operands, input has %d", L.tc_esize, (int)sizeof(T));
+  ConvTc c;
+  memset(&c, 0, sizeof(c));
+  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W; c.stride = L.stride;
+  if (L.stride == 2) {
+    DFVO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W, DFVO_ESHAPE, "tc conv stride 2: in %dx%d out %dx%d", in.H, in.W, out.H, out.W);
+  } else {
+    DFVO_REQUIRE(in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
+                 "tc conv: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
+  }
+  c.nsrc = 1;
+  c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
+  fill_taps(L, &c);
+  c.esize = L.tc_esize; c.round_out_tf32 = round_out;
+  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = sizeof(TO) == 4;
+  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
+  c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
+  c.zero_pad_to = zero_pad_to;
+  c.flops = 2.0 * (double)in.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
+  return conv_tc(c, s);
+}
+
 template <>
 int run_conv<float>(const ConvLayer& L, Ten<const float> in, Ten<float> out, int act, Ten<const float> residual,
                     int zero_pad_to, cudaStream_t s) {
+  // tf32 mode: fp32 activations, tcgen05 kind::tf32; stored activations are rounded to tf32 (the next conv's operand)
+  if (L.tc && L.tc_esize == 4) return launch_tc<float, float>(L, in, out, act, residual, zero_pad_to, 1, s);
   DFVO_REQUIRE(L.w_direct, DFVO_ESTATE, "conv layer has no fp32 weights");
   // pad channels of fp32 buffers are zero from allocation and never written; nothing to do for zero_pad_to
   (void)zero_pad_to;
@@ -166,25 +220,7 @@ int run_conv<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<bf16> out, int ac
     DFVO_REQUIRE(L.w_direct, DFVO_ESTATE, "conv layer has no direct weights");
     return conv_direct<bf16, bf16>(to_direct(L, act), in, out, residual, s);
   }
-  DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc conv: input view has %d channels, layer expects %d", in.C, L.Ktot);
-  ConvTc c;
-  memset(&c, 0, sizeof(c));
-  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W; c.stride = L.stride;
-  if (L.stride == 2) {
-    DFVO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W, DFVO_ESHAPE, "tc conv stride 2: in %dx%d out %dx%d", in.H, in.W, out.H, out.W);
-  } else {
-    DFVO_REQUIRE(in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
-                 "tc conv: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
-  }
-  c.nsrc = 1;
-  c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
-  fill_taps(L, &c);
-  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = 0;
-  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
-  c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
-  c.zero_pad_to = zero_pad_to;
-  c.flops = 2.0 * (double)in.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
-  return conv_tc(c, s);
+  return launch_tc<bf16, bf16>(L, in, out, act, residual, zero_pad_to, 0, s);
 }
 
 template <>
@@ -207,21 +243,7 @@ int run_conv_f32out<bf16>(const ConvLayer& L, Ten<const bf16> in, Ten<float> out
   if (L.w_head && !(head_tc && big) && act == ACT_NONE && in.C == 32 && (L.kh == 3 || L.kh == 5 || L.kh == 7) &&
       L.pad_y == L.kh / 2 && L.pad_x == L.kw / 2)
     return flow_head(in, L.w_head, L.bias_h[0], L.bias_h[1], L.kh, residual, out, s);
-  DFVO_REQUIRE(in.C == L.Ktot, DFVO_ESHAPE, "tc head: input view has %d channels, layer expects %d", in.C, L.Ktot);
-  DFVO_REQUIRE(L.stride == 1 && in.H == out.H + L.kh - 1 - 2 * L.pad_y && in.W == out.W + L.kw - 1 - 2 * L.pad_x, DFVO_ESHAPE,
-               "tc head: in %dx%d out %dx%d k %dx%d pad %d,%d", in.H, in.W, out.H, out.W, L.kh, L.kw, L.pad_y, L.pad_x);
-  ConvTc c;
-  memset(&c, 0, sizeof(c));
-  c.N = in.N; c.H = out.H; c.W = out.W; c.inH = in.H; c.inW = in.W; c.stride = 1;
-  c.nsrc = 1;
-  c.src[0].p = in.p; c.src[0].C = in.C; c.src[0].sN = in.sN; c.src[0].sH = in.sH; c.src[0].sW = in.sW;
-  fill_taps(L, &c);
-  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = 1;
-  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
-  c.residual = residual.p; c.rN = residual.sN; c.rH = residual.sH; c.rW = residual.sW;
-  c.zero_pad_to = 0;
-  c.flops = 2.0 * (double)in.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
-  return conv_tc(c, s);
+  return launch_tc<bf16, float>(L, in, out, act, residual, 0, 0, s);
 }
 
 }  // namespace dfvo

@@ -39,7 +39,8 @@ struct ConvLayer {
   int Cout_pad = 0;        // multiple of 16
   float* w_direct = nullptr;   // device [kh*kw*Ktot][w_pitch] fp32
   int w_pitch = 0;
-  bf16* w_tc = nullptr;        // device [kh*kw][Cout_pad][Ktot] bf16 (only if tc requested)
+  void* w_tc = nullptr;        // device [kh*kw][Cout_pad][Ktot] bf16 (tc_esize 2) or tf32-rounded float (tc_esize 4), if tc requested
+  int tc_esize = 2;
   float* w_head = nullptr;     // device [kh*kw][Ktot][2] fp32, only for 2-channel heads (flow_head kernel)
   float* bias = nullptr;       // device [Cout_pad] fp32 (zero padded; zeros if the conv has no bias)
   float bias_h[4] = {0.f, 0.f, 0.f, 0.f};   // host copy of the first biases (kernel arguments of the head kernel)
@@ -50,7 +51,7 @@ struct ConvLayer {
 // `scale`/`shift` (optional, per Cout) fold an eval-mode BatchNorm: y = conv*scale + shift.
 int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, const std::vector<Seg>& segs,
                      int stride, int pad_y, int pad_x, int reflect, bool want_tc, bool want_direct,
-                     const float* scale, const float* shift, ConvLayer* out);
+                     const float* scale, const float* shift, ConvLayer* out, int tc_esize = 2);
 
 template <typename T>
 int run_conv(const ConvLayer& L, Ten<const T> in, Ten<T> out, int act, Ten<const T> residual, int zero_pad_to,

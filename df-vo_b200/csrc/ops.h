@@ -77,7 +77,7 @@ int flow_head(Ten<const __nv_bfloat16> in, const float* w, float bias0, float bi
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) -------------------------------------------
 struct ConvTcSource {
-  const bf16* p;          // NHWC bf16 view (channel slice allowed)
+  const void* p;          // NHWC view (channel slice allowed) of bf16 (esize 2) or float (esize 4, kind::tf32) elements
   int C;                  // channels in this source (multiple of 16; zero-padded by the producer)
   long long sN, sH, sW;   // strides in elements
 };
@@ -91,7 +91,9 @@ struct ConvTc {
                           // 5-D tensor map (pitch+C, W/2, 2, H/2, N) -- see conv_tc.cu)
   int ntaps;              // kh*kw
   int8_t dy[49], dx[49];  // tap offsets in INPUT pixels (already include -pad): iy = oy*stride + dy
-  const bf16* w;          // packed [ntaps][Cout_pad][Ktot] bf16, Ktot = sum(src[i].C)
+  int esize;              // operand element size: 2 = bf16 (tcgen05 kind::f16), 4 = fp32 storage read as tf32 (kind::tf32)
+  int round_out_tf32;     // esize 4: round the stored fp32 activations to tf32 (cvt.rna) so the next conv's operand is unbiased
+  const void* w;          // packed [ntaps][Cout_pad][Ktot] (bf16 or tf32-rounded float), Ktot = sum(src[i].C)
   int Cout_pad;           // multiple of 16
   int Cout;               // real output channels written
   const float* bias;      // [Cout_pad] fp32

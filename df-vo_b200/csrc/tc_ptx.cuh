@@ -8,6 +8,7 @@ namespace dfvo {
 // what the epilogue needs to turn 16 accumulator columns of one output pixel into stored channels
 struct TcEpi {
   int Cout, zero_pad_to, act, out_f32;
+  int round_tf32;          // fp32 output rounded to the tf32 grid (tf32 mode activations)
   void* out;
   const void* res;
 };
@@ -73,6 +74,35 @@ __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo,
       "mov.b64 db, {%3, %4};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::tf32: fp32 operands in shared memory read as tf32 (upper 19 bits), K = 8 per instruction (32 bytes per row, like bf16's
+// K = 16), fp32 accumulation.  Same descriptors, same 128-byte swizzle.
+__device__ __forceinline__ void tc_mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int TF32>
+__device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if (TF32) tc_mma_tf32_lohi(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else tc_mma_bf16_lohi(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 @ bit 4), A / B format @ bits 7 / 10 (kind::f16: bf16 = 1;
+// kind::tf32: tf32 = 2), K-major A and B, N >> 3 @ 17, M >> 4 @ 24
+__device__ __forceinline__ uint32_t tc_idesc(int tf32, int block_n) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ float tc_round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
 }
 // Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
 // while its predecessor in the stream is still running; it must not touch data the predecessor produces (or overwrite
@@ -186,6 +216,42 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v,
   // still two vector stores: channels >= Cout are written as zeros
   const int cend = p.Cout > p.zero_pad_to ? p.Cout : p.zero_pad_to;
   const bool tail = c + 16 > p.Cout;
+  if (p.out_f32 && (c + 16 <= cend)) {
+    // fp32 activations (tf32 mode): four 16-byte stores; pad channels of a straddling group are written as zeros
+    float* of = reinterpret_cast<float*>(p.out) + opix + c;
+    const float* rf = p.res ? reinterpret_cast<const float*>(p.res) + rpix + c : nullptr;
+    if ((reinterpret_cast<uintptr_t>(of) & 15u) == 0 && (!rf || (!tail && (reinterpret_cast<uintptr_t>(rf) & 15u) == 0))) {
+      if (rf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 rv = *reinterpret_cast<const float4*>(rf + 4 * j);
+          f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
+        }
+      }
+      if (p.act <= ACT_RELU) {
+        const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope * f[j]);
+      } else if (p.act == ACT_ELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+      }
+      if (tail) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (c + j < p.Cout) ? f[j] : 0.f;
+      }
+      if (p.round_tf32) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = tc::tc_round_tf32(f[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(of + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      return;
+    }
+  }
   const bool full = !p.out_f32 && (c + 16 <= cend) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) &&
                     (!r || (!tail && (reinterpret_cast<uintptr_t>(r) & 15u) == 0));
   if (!full) {
@@ -236,7 +302,7 @@ struct TcProf { cudaEvent_t e0, e1; };
 bool tc_prof_begin(cudaStream_t s, TcProf* p);                       // false (and no events) when profiling is off
 void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc);
 int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                  const unsigned* box);                              // bf16, SWIZZLE_128B, zero OOB fill
+                  const unsigned* box, int esize = 2);               // bf16 (esize 2) or fp32 (4), SWIZZLE_128B, zero OOB fill
 int tc_num_sms();
 // launch config with the PDL attribute set unless DFVO_PDL=0 (attr must outlive the cudaLaunchKernelEx call)
 #ifndef DFVO_HOSTSIM

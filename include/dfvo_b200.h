@@ -122,7 +122,8 @@ int dfvo_backward_warp(const float* input, const float* flow, float* out, int B,
 int dfvo_fb_consistency(const float* flow_fwd, const float* flow_bwd, float* diff, int H, int W,
                         void* stream);
 /* torch.nn.Conv2d (+ activation): x [B,Cin,H,W], w_host [Cout,Cin,kh,kw], bias_host [Cout] or NULL
- * -> y [B,Cout,Ho,Wo].  precision DFVO_PREC_BF16 runs the tcgen05 kernel (stride must be 1). */
+ * -> y [B,Cout,Ho,Wo].  precision DFVO_PREC_BF16 / DFVO_PREC_TF32 run the tcgen05 kernels (kind::f16 on bf16 operands /
+ * kind::tf32 on fp32 operands; stride 1, or stride 2 on even sizes with 'same' padding). */
 int dfvo_conv2d(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin,
                 int H, int W, int Cout, int kh, int kw, int stride, int pad_y, int pad_x, int reflect,
                 int act, int precision, void* stream);

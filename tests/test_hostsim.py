@@ -97,6 +97,29 @@ def test_liteflownet_bf16_plumbing(hostsim_lib):
     assert epe.mean() < 0.05 and epe.max() < 0.5
 
 
+def test_tf32_mode_plumbing(hostsim_lib):
+    """DFVO_PREC_TF32 wiring (fp32 activations, layers packed for 4-byte tensor-core operands, im2row stem, CUDA-core heads):
+    in the CPU emulation the tcgen05 kind::tf32 convs are exact fp32 arithmetic on tf32-rounded weights, so both networks must
+    land within tf32 weight-rounding distance of the reference goldens."""
+    g = np.load(os.path.join(G, "deep_models_70x150.npz"))
+    H, W = 70, 150
+    ref, cur = synth.value_noise_image(H, W, 1), synth.value_noise_image(H, W, 2)
+    ctx = native.Context(hostsim_lib)
+    ctx.load_weights(native.NET_LITEFLOWNET, synth.liteflownet_weights())
+    ctx.liteflow_build(H, W, 1, native.PREC_TF32)
+    fwd, bwd, diff = np.zeros((2, H, W), np.float32), np.zeros((2, H, W), np.float32), np.zeros((H, W), np.float32)
+    ctx.liteflow_forward([ref.ctypes.data, cur.ctypes.data], hptr(fwd), hptr(bwd), hptr(diff))
+    epe = np.sqrt(((fwd - g["flow_fwd"]) ** 2).sum(0))
+    assert epe.mean() < 5e-3 and epe.max() < 5e-2, (epe.mean(), epe.max())
+    fh, fw = [int(x) for x in g["feed_hw"]]
+    enc, dec = synth.monodepth2_weights(4869, fh, fw)
+    ctx.load_weights(native.NET_MONODEPTH2, enc); ctx.load_weights(native.NET_MONODEPTH2, dec)
+    ctx.monodepth2_build(fh, fw, native.PREC_TF32)
+    out = np.zeros((fh, fw), np.float32)
+    ctx.monodepth2_forward(hptr(np.ascontiguousarray(g["depth_feed"][None])), hptr(out))
+    assert (np.abs(out - g["depth"]) / g["depth"]).max() < 2e-3
+
+
 def test_liteflownet_two_pairs_batched(hostsim_lib):
     """The batched many-pairs mode (BASELINE configs[2] / SURVEY 8e pair-level sharding): two independent frame pairs in one
     forward (batch of 4 images, 'second image' = n ^ 1 inside each pair) give, pair by pair, exactly what each pair gives
