@@ -249,30 +249,48 @@ def torch_gpu_baseline(frames, iters=8):
     out = {}
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
     torch.backends.cudnn.benchmark = True
+
+    class Bf16Convs:
+        """torch.nn.functional with conv2d / conv_transpose2d running on bf16 channels_last operands (weights converted once),
+        results returned as fp32: the same split as the product (bf16 conv operands, fp32 flows / coordinates)."""
+        def __init__(self):
+            self.cache = {}
+
+        def __getattr__(self, k):
+            return getattr(F, k)
+
+        def _w(self, t):
+            if t is None:
+                return None
+            c = self.cache.get(id(t))
+            if c is None:
+                c = t.to(torch.bfloat16)
+                c = c.contiguous(memory_format=torch.channels_last) if c.dim() == 4 else c
+                self.cache[id(t)] = c
+            return c
+
+        def conv2d(self, x, w, b=None, **kw):
+            return F.conv2d(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), self._w(w), self._w(b), **kw).float()
+
+        def conv_transpose2d(self, x, w, b=None, **kw):
+            return F.conv_transpose2d(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), self._w(w), self._w(b), **kw).float()
+
     try:
         with torch.no_grad(), torch.device(dev):
-            for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast_channels_last", True, True)):
+            for name, tf32, bf16 in (("fp32", False, False), ("tf32", True, False), ("bf16_convs_channels_last", True, True)):
                 torch.backends.cudnn.allow_tf32 = tf32
                 torch.backends.cuda.matmul.allow_tf32 = tf32
-                if amp:
-                    cl = lambda d: {k: (v.contiguous(memory_format=torch.channels_last) if hasattr(v, "dim") and v.dim() == 4 else v) for k, v in d.items()}
-                    pf, pe, pd = cl(p_flow), cl(p_enc), cl(p_dec)
-                    ctx = lambda: torch.autocast("cuda", dtype=torch.bfloat16)
-                else:
-                    pf, pe, pd = p_flow, p_enc, p_dec
-                    import contextlib
-                    ctx = contextlib.nullcontext
+                nets.F = Bf16Convs() if bf16 else F
 
                 def flow():
-                    with ctx():
-                        return nets.liteflow_inference_flow(pf, a, b)
+                    return nets.liteflow_inference_flow(p_flow, a, b)
 
                 def depth():
-                    with ctx():
-                        return nets.monodepth2_inference_depth(pe, pd, feed)
+                    return nets.monodepth2_inference_depth(p_enc, p_dec, feed)
                 ms_f, ms_d = timed(flow), timed(depth)
                 out[name] = dict(flow_net_ms=ms_f, depth_net_ms=ms_d, networks_fps=1e3 / (ms_f + ms_d))
     finally:
+        nets.F = F
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
     out["what"] = ("reference graph (oracle/nets.py restatement of lite_flow_net.py:31-325, resnet_encoder.py:87-98, depth_decoder.py:50-65) "
                    "through torch %s / cuDNN on this GPU, networks only (no tracker); %d iterations after 3 warm-ups" % (torch.__version__, iters))

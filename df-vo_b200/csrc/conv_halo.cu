@@ -36,6 +36,10 @@ struct ConvHaloK {
   int Cout, Cout_pad, act, out_f32, zero_pad_to;
   int chunk;                     // channels per 128-byte operand row: 64 (bf16) or 32 (fp32 read as tf32)
   int esize, round_tf32;
+  int tma_out;                   // bf16 output through shared-memory staging + cp.async.bulk.tensor stores (full-line writes)
+  int cw;                        // channels per store box: min(block_n, 64)
+  uint32_t stage_out_off;        // byte offset of the two staging buffers from the 1024-B aligned base
+  long long* dbg;                // optional per-phase clock stamps of CTA 0 (DFVO_HALO_DBG)
   const float* bias;
   void* out; long long oN, oH, oW;
   const void* res; long long rN, rH, rW;
@@ -48,7 +52,7 @@ template <int S, int TF32>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ ConvHaloK p) {
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvHaloK p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -57,7 +61,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)p.a_stages * (uint32_t)p.a_stage_bytes;
-  const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
+  // [A ring][B ring][2 store-staging boxes (tma_out)][barriers, TMEM slot, bias]
+  const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes + (p.tma_out ? 2u * 128u * (uint32_t)p.cw * 2u : 0u);
   // barriers: a_full[A], a_empty[A], b_full[B], b_empty[B], tmem_full[2], tmem_empty[2]
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(p.a_stages + s); };
@@ -71,11 +76,18 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // phase stamps (debug): 0 entry, 1 after set-up sync, 2 after the PDL wait, 3 first A box landed, 4 first accumulator complete,
+  // 5 first tile stored, 6 last tile stored (CTA 0 only; %globaltimer ns)
+  auto stamp = [&](int i) {
+    if (p.dbg && blockIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[i] = (long long)t; }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmB);
+    if (p.tma_out) prefetch_tmap(&tmO);
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
@@ -90,7 +102,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ntaps = p.kh * p.kw;
+  if (threadIdx.x == 0) stamp(1);
   pdl_wait();                                  // from here on: activations of the previous kernel / our output buffers
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ===================================== A producer: one halo box per (tile, source, 64-channel chunk)
@@ -169,6 +183,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         for (int c0 = 0; c0 < p.srcC[s]; c0 += p.chunk) {
           mbar_wait(a_full(astage), aphase);
           tc_fence_after();
+          if (p.dbg && tile == (int)blockIdx.x && s == 0 && c0 == 0 && lane == 0) stamp(3);
           const uint32_t a_lo0 = (((a_base + (uint32_t)astage * (uint32_t)p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           const int rem = p.srcC[s] - c0;
           const int nks = ((rem >= p.chunk ? p.chunk : rem) * p.esize) >> 5;       // 32-byte K steps (16 bf16 / 8 tf32) with real channels
@@ -236,6 +251,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
     TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.round_tf32 = p.round_tf32; ep.out = p.out; ep.res = p.res;
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t store_seq = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -247,6 +263,53 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
 
+      if (p.dbg && tile == (int)blockIdx.x && threadIdx.x == 96) stamp(4);
+      if (p.tma_out) {
+        // ---- staged stores: per (sub-tile, cw-channel group) the 8 warps write their 16-column chunks of the 128 pixels into a
+        // swizzled [16 rows][8 px][cw ch] box in shared memory; one thread hands it to TMA, which writes whole lines and clips the
+        // box at the image / channel borders.  Two boxes in flight (double-buffered staging).
+        const int cw = p.cw, groups_per_sub = p.block_n / cw, ngroups = S * groups_per_sub;
+        const int chunks_per_group = cw >> 4;                              // 16-column chunks of a group: 4, 2 or 1
+        const uint32_t row_bytes = (uint32_t)cw * 2u, box_bytes = 128u * row_bytes;
+        const int sw_shift = cw == 64 ? 0 : (cw == 32 ? 1 : 2), sw_mask = cw == 64 ? 7 : (cw == 32 ? 3 : 1);
+        const int row = (4 * q + (lane >> 3)) * 8 + (lane & 7);             // this lane's pixel inside the 8 x 16 box
+        for (int g = 0; g < ngroups; ++g) {
+          const int sub = g / groups_per_sub, cg = g - sub * groups_per_sub;
+          const uint32_t buf = base + p.stage_out_off + (uint32_t)(store_seq & 1) * box_bytes;
+          if (threadIdx.x == 96) bulk_wait_read<1>();                       // the box that used this buffer two stores ago was read
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int x = xs + 8 * sub;
+          const bool inside = x < p.W && y < p.H;
+          const long long rpix = n * p.rN + (long long)y * p.rH + (long long)x * p.rW;
+          // the two warps of a quadrant split the group's chunks
+          const int ch0 = (ew < 4) ? 0 : ((chunks_per_group + 1) >> 1), ch1 = (ew < 4) ? ((chunks_per_group + 1) >> 1) : chunks_per_group;
+          for (int ch = ch0; ch < ch1; ++ch) {
+            uint32_t v[16], w[8];
+            __syncwarp();
+            tc_ld16(taddr0 + (uint32_t)(sub * p.block_n + cg * cw + ch * 16), v);
+            tc_epilogue16_pack(ep, v, bias4, cbase + cg * cw + ch * 16, rpix, p.res != nullptr && inside, w);
+            const uint32_t a0 = buf + (uint32_t)row * row_bytes;
+            const int k0 = 2 * ch, sx = (row >> sw_shift) & sw_mask;       // 16-byte units inside the row, XOR-swizzled like the tensor map
+            st_shared_v4(a0 + (uint32_t)(((k0) ^ sx) << 4), w[0], w[1], w[2], w[3]);
+            st_shared_v4(a0 + (uint32_t)(((k0 + 1) ^ sx) << 4), w[4], w[5], w[6], w[7]);
+          }
+          if (g == ngroups - 1) {                                           // accumulator fully read: give it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 96) {
+            tma_store_4d(&tmO, buf, cbase + cg * cw, tx * 8 * S + 8 * sub, ty * HALO_TH, n);
+            bulk_commit();
+          }
+          ++store_seq;
+        }
+        if (p.dbg && threadIdx.x == 96) stamp(tile == (int)blockIdx.x ? 5 : 6);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       auto process = [&](const uint32_t* v, int item) {
         const int sub = item / nchunks, ch = item - sub * nchunks;
         const int x = xs + 8 * sub;
@@ -268,8 +331,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (p.dbg && threadIdx.x == 96) stamp(tile == (int)blockIdx.x ? 5 : 6);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_out && threadIdx.x == 96) bulk_wait_all();                  // global writes of every box performed before the grid ends
   }
 
   tc_fence_before();
@@ -308,12 +373,13 @@ static bool rect_taps(const ConvTc& c, int* kh, int* kw, int* dy0, int* dx0) {
 struct HaloCfg { int S, block_n, a_stages, b_stages, a_stage_bytes; size_t smem; double cost; };
 
 // shared memory: A ring + B ring + barriers + TMEM slot + bias (+ 1 KB alignment slack)
-static bool halo_fit(int S, int bn, int kh, int kw, int Cout_pad, HaloCfg* out) {
+static bool halo_fit(int S, int bn, int kh, int kw, int Cout_pad, bool tma_out, HaloCfg* out) {
   const int HW = 8 * S + kw - 1, HH = HALO_TH + kh - 1;
   if (HW > 256 || HH > 256) return false;
   const int a_stage = (HW * HH * 128 + 1023) & ~1023;
   const int b_stage = bn * 128;
-  const size_t fixed = 1024 + 8 * 64 + 64 + (size_t)Cout_pad * 4;      // alignment slack, <= 34 barriers, TMEM slot, bias
+  const size_t staging = tma_out ? 2 * 128 * (size_t)(bn < 64 ? bn : 64) * 2 : 0;      // two store boxes of 128 px x min(bn, 64) bf16
+  const size_t fixed = 1024 + 8 * 64 + 64 + (size_t)Cout_pad * 4 + staging;      // alignment slack, <= 34 barriers, TMEM slot, bias
   const size_t budget = 220 * 1024;
   int a_stages = 2, b_stages = 2;
   if (fixed + (size_t)a_stages * a_stage + (size_t)b_stages * b_stage > budget) return false;
@@ -330,6 +396,12 @@ static bool halo_fit(int S, int bn, int kh, int kw, int Cout_pad, HaloCfg* out) 
 // Pick (S, block_n): minimise  waves x max(MMA time, L2->SM time)  per tile + a fixed per-tile overhead.
 // MMA time per K=16 step = max(block_n/2, 32 + block_n/4) clk (tensor floor vs shared-memory operand reads),
 // L2->SM ~ 43 B/clk per SM when every SM streams (chip cap 6.3 KB/clk), up to ~3x that for a lone CTA.
+static bool halo_tma_out(const ConvTc& c) {
+  static int on = -1;
+  if (on < 0) on = env_int("DFVO_TMA_STORE", 1);
+  return on && !c.out_f32 && ((uintptr_t)c.out & 15) == 0 && (c.oW * 2) % 16 == 0 && (c.oH * 2) % 16 == 0 && (c.oN * 2) % 16 == 0;
+}
+
 static bool halo_choose(const ConvTc& c, int kh, int kw, HaloCfg* best) {
   int ktot16 = 0, kbytes = 0;                       // 32-byte K steps and bytes per pixel over all sources
   const int es = c.esize == 4 ? 4 : 2;
@@ -343,7 +415,7 @@ static bool halo_choose(const ConvTc& c, int kh, int kw, HaloCfg* best) {
       if (c.Cout_pad % bn || S * bn > 256) continue;
       if (fN && bn != fN) continue;
       HaloCfg h;
-      if (!halo_fit(S, bn, kh, kw, c.Cout_pad, &h)) continue;
+      if (!halo_fit(S, bn, kh, kw, c.Cout_pad, halo_tma_out(c), &h)) continue;
       const long long tiles = (long long)cdiv(c.W, 8 * S) * cdiv(c.H, HALO_TH) * c.N * (c.Cout_pad / bn);
       const long long waves = (tiles + nsm - 1) / nsm;
       const int active = (int)(tiles < nsm ? tiles : nsm);
@@ -401,8 +473,17 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
   k.zero_pad_to = c.zero_pad_to > c.Cout ? c.zero_pad_to : c.Cout;
   k.bias = c.bias; k.out = c.out; k.oN = c.oN; k.oH = c.oH; k.oW = c.oW;
   k.res = c.residual; k.rN = c.rN; k.rH = c.rH; k.rW = c.rW;
+  k.tma_out = halo_tma_out(c) ? 1 : 0;
+  k.cw = k.block_n < 64 ? k.block_n : 64;
+  k.stage_out_off = (uint32_t)k.a_stages * (uint32_t)k.a_stage_bytes + (uint32_t)k.b_stages * (uint32_t)k.block_n * 128u;
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = env_int("DFVO_HALO_DBG", 0);
+  if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8 * sizeof(long long)); }
+  k.dbg = dbg_on ? dbg_buf : nullptr;
+  if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), s);
 
-  CUtensorMap tmA[3], tmB;
+  CUtensorMap tmA[3], tmB, tmO;
   for (int i = 0; i < 3; ++i) {
     const ConvTcSource& src = c.src[i < c.nsrc ? i : 0];
     const int inW = c.inW > 0 ? c.inW : c.W, inH = c.inH > 0 ? c.inH : c.H;
@@ -418,6 +499,16 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
     unsigned box[3] = {(unsigned)k.chunk, (unsigned)k.block_n, 1};
     int rc = tc_encode_map(&tmB, c.w, 3, dims, str, box, es);
     if (rc) return rc;
+  }
+  if (k.tma_out) {
+    // store view: channels [0, max(Cout, zero_pad_to)) of the output slot; boxes are clipped there and at the image border
+    unsigned long long dims[4] = {(unsigned long long)k.zero_pad_to, (unsigned long long)c.W, (unsigned long long)c.H, (unsigned long long)c.N};
+    unsigned long long str[3] = {(unsigned long long)c.oW * 2, (unsigned long long)c.oH * 2, (unsigned long long)c.oN * 2};
+    unsigned box[4] = {(unsigned)k.cw, 8, HALO_TH, 1};
+    int rc = tc_encode_map(&tmO, c.out, 4, dims, str, box, 2, k.cw * 2);
+    if (rc) return rc;
+  } else {
+    tmO = tmB;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -436,19 +527,27 @@ int conv_halo(const ConvTc& c, cudaStream_t s) {
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
   tc_launch_config(&cfg, &attr, grid, HALO_THREADS, h.smem, s);
   if (es == 2) {
-    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
-    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
-    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 0>, tmA[0], tmA[1], tmA[2], tmB, k));
+    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 0>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
+    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 0>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
+    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 0>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
   } else {
-    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
-    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
-    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 1>, tmA[0], tmA[1], tmA[2], tmB, k));
+    if (k.S == 1) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<1, 1>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
+    else if (k.S == 2) DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<2, 1>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
+    else DFVO_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, 1>, tmA[0], tmA[1], tmA[2], tmB, tmO, k));
+  }
+  if (dbg_on) {
+    long long t[8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(t, dbg_buf, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "halo_dbg N%d %dx%d k%dx%d cin%d cout%d bn%d S%d tiles%d grid%d tma%d | setup %.2f pdl %.2f firstA %.2f acc %.2f store1 %.2f last %.2f us\n",
+            c.N, c.H, c.W, k.kh, k.kw, ktot, c.Cout, k.block_n, k.S, k.ntiles, grid, k.tma_out, (t[1] - t[0]) * 1e-3, (t[2] - t[0]) * 1e-3,
+            (t[3] - t[0]) * 1e-3, (t[4] - t[0]) * 1e-3, (t[5] - t[0]) * 1e-3, ((t[6] ? t[6] : t[5]) - t[0]) * 1e-3);
   }
   if (prof) {
     char d[256];
-    snprintf(d, sizeof(d), "halo%s N%d %dx%d k%dx%d src[%d,%d,%d] cout%d/%d bn%d S%d stages%d/%d grid%d tiles%d gflop %.3f", es == 4 ? "-tf32" : "", c.N, c.H, c.W,
+    snprintf(d, sizeof(d), "halo%s N%d %dx%d k%dx%d src[%d,%d,%d] cout%d/%d bn%d S%d stages%d/%d grid%d tiles%d tma%d gflop %.3f", es == 4 ? "-tf32" : "", c.N, c.H, c.W,
              k.kh, k.kw, c.src[0].C, c.nsrc > 1 ? c.src[1].C : 0, c.nsrc > 2 ? c.src[2].C : 0, c.Cout, c.Cout_pad, k.block_n,
-             k.S, k.a_stages, k.b_stages, grid, k.ntiles, c.flops * 1e-9);
+             k.S, k.a_stages, k.b_stages, grid, k.ntiles, k.tma_out, c.flops * 1e-9);
     tc_prof_end(s, pr, c.flops, d);
   }
   DFVO_CHECK_LAUNCH();

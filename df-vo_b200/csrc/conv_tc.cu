@@ -261,7 +261,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims_, const unsigned long long* strides_, const unsigned* box_,
-                  int esize) {
+                  int esize, int swizzle_bytes) {
   cuuint64_t dims[5], str[5];
   cuuint32_t box[5];
   for (int i = 0; i < rank; ++i) { dims[i] = dims_[i]; box[i] = box_[i]; if (i < rank - 1) str[i] = strides_[i]; }
@@ -271,7 +271,9 @@ int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long
   DFVO_REQUIRE(enc != nullptr, DFVO_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DFVO_REQUIRE(r == CUDA_SUCCESS, DFVO_ECUDA, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r,
                rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
@@ -307,7 +309,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
                       int esize) {
   unsigned long long d[5], st[5]; unsigned b[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i < rank - 1) st[i] = strides_bytes[i]; }
-  return tc_encode_map(m, ptr, rank, d, st, b, esize);
+  return tc_encode_map(m, ptr, rank, d, st, b, esize, 128);
 }
 
 static int build_plan(const ConvTc& c, ConvTcPlanImpl* pl) {

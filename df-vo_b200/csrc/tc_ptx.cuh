@@ -51,6 +51,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// ---- TMA store (shared -> global) of one tile box; bulk-group completion tracking
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest `N` bulk groups have finished READING shared memory (their staging buffers may be overwritten)
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// all bulk groups are complete (global writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) before the store is issued
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -196,6 +213,58 @@ static __device__ __noinline__ void tc_epilogue16_slow(TcEpi p, float4 f0, float
   }
 }
 
+// bias + optional bf16 residual + activation of 16 consecutive output channels [c, c+16) of one pixel, packed to 8 bf16x2 words
+// (channels >= Cout are zero).  The TMA-store epilogue stages these in shared memory; `have_res` must be false for pixels outside
+// the image.
+__device__ __forceinline__ void tc_epilogue16_pack(const TcEpi& p, const uint32_t* v, const float4* bias4, int c, long long rpix, bool have_res,
+                                                   uint32_t* w) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b = bias4[(c >> 2) + j];
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+  }
+  if (have_res) {
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c;
+    if (c + 16 <= p.Cout && (reinterpret_cast<uintptr_t>(r) & 15u) == 0) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[2 * j] += __uint_as_float(rw[j] << 16);
+        f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 16; ++j)
+        if (c + j < p.Cout) f[j] += __bfloat162float(r[j]);
+    }
+  }
+  if (p.act <= ACT_RELU) {
+    const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);      // max(f, f) = f for ACT_NONE
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope * f[j]);
+  } else if (p.act == ACT_ELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
+  }
+  if (c + 16 > p.Cout) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = (c + j < p.Cout) ? f[j] : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
 // bias + optional residual + activation + store of 16 consecutive output channels [c, c+16) of one pixel.
 // v = 16 fp32 accumulator words (tcgen05.ld), bias4 = shared-memory bias, opix/rpix = element offsets of the pixel.
 // Fast path (bf16 output, full aligned group): two 16-byte stores; LeakyReLU / ReLU / identity are one fmaxf with a
@@ -302,7 +371,7 @@ struct TcProf { cudaEvent_t e0, e1; };
 bool tc_prof_begin(cudaStream_t s, TcProf* p);                       // false (and no events) when profiling is off
 void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc);
 int tc_encode_map(void* map, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                  const unsigned* box, int esize = 2);               // bf16 (esize 2) or fp32 (4), SWIZZLE_128B, zero OOB fill
+                  const unsigned* box, int esize = 2, int swizzle_bytes = 128);   // bf16 (esize 2) or fp32 (4); swizzle 128 / 64 / 32 B; zero OOB fill
 int tc_num_sms();
 // launch config with the PDL attribute set unless DFVO_PDL=0 (attr must outlive the cudaLaunchKernelEx call)
 #ifndef DFVO_HOSTSIM

@@ -58,8 +58,8 @@ def analytic_hooks(h, w, K, seen=None):
         f = seqdata.frame_inputs(cur_id, h, w, K, seqdata.MODES[cur_id % len(seqdata.MODES)])
         for key, val in (((ref_id, cur_id), f["fwd"]), ((cur_id, ref_id), f["bwd"]), ((ref_id, cur_id, "diff"), f["diff"])):
             a = flows[key]
-            if seen is not None:
-                seen.setdefault("flow", {})[(cur_id,) + key[2:]] = np.array(np.asarray(a)) if key[0] == ref_id else None
+            if seen is not None and key[0] == ref_id:          # the forward flow and the inconsistency map
+                seen.setdefault("flow", {})[(cur_id,) + key[2:]] = np.array(np.asarray(a))
             if hasattr(a, "dev"):                              # device-backed array of the mirror: overwrite in place
                 a.dev.upload(np.ascontiguousarray(val, np.float32).reshape(a.dev.shape))
                 a._host = None
