@@ -252,6 +252,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.round_tf32 = p.round_tf32; ep.out = p.out; ep.res = p.res;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t store_seq = 0;
+    // lean path: bf16 output, no residual, LeakyReLU / ReLU / identity, 16-byte aligned pixels (uniform per launch)
+    const bool fast_launch = !p.out_f32 && p.res == nullptr && p.act <= ACT_RELU && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 &&
+                             (p.oW & 7) == 0 && (p.oH & 7) == 0 && (p.oN & 7) == 0;
+    const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);      // max(f, slope * f); identity: max(f, f)
+    const int sub_begin = it_begin / nchunks, ch_begin = it_begin - sub_begin * nchunks;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -278,16 +283,23 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           const uint32_t buf = base + p.stage_out_off + (uint32_t)(store_seq & 1) * box_bytes;
           if (threadIdx.x == 96) bulk_wait_read<1>();                       // the box that used this buffer two stores ago was read
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int x = xs + 8 * sub;
-          const bool inside = x < p.W && y < p.H;
-          const long long rpix = n * p.rN + (long long)y * p.rH + (long long)x * p.rW;
           // the two warps of a quadrant split the group's chunks
           const int ch0 = (ew < 4) ? 0 : ((chunks_per_group + 1) >> 1), ch1 = (ew < 4) ? ((chunks_per_group + 1) >> 1) : chunks_per_group;
           for (int ch = ch0; ch < ch1; ++ch) {
             uint32_t v[16], w[8];
             __syncwarp();
             tc_ld16(taddr0 + (uint32_t)(sub * p.block_n + cg * cw + ch * 16), v);
-            tc_epilogue16_pack(ep, v, bias4, cbase + cg * cw + ch * 16, rpix, p.res != nullptr && inside, w);
+            {
+              const int c = cbase + cg * cw + ch * 16;
+              tc_epilogue16_fast_pack(v, bias_s + c, slope, w);                 // bias is zero-padded to Cout_pad
+              if (c + 16 > p.Cout) {                                             // channel tail: zeros beyond Cout
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int c2 = c + 2 * j;
+                  w[j] = c2 + 1 < p.Cout ? w[j] : (c2 < p.Cout ? (w[j] & 0xffffu) : 0u);
+                }
+              }
+            }
             const uint32_t a0 = buf + (uint32_t)row * row_bytes;
             const int k0 = 2 * ch, sx = (row >> sw_shift) & sw_mask;       // 16-byte units inside the row, XOR-swizzled like the tensor map
             st_shared_v4(a0 + (uint32_t)(((k0) ^ sx) << 4), w[0], w[1], w[2], w[3]);
@@ -310,23 +322,38 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
-      auto process = [&](const uint32_t* v, int item) {
-        const int sub = item / nchunks, ch = item - sub * nchunks;
-        const int x = xs + 8 * sub;
-        const int c = cbase + ch * 16;
-        if (x < p.W && y < p.H && c < p.zero_pad_to)
-          tc_epilogue16(ep, v, bias4, c, n * p.oN + y * p.oH + x * p.oW, n * p.rN + y * p.rH + x * p.rW);
-      };
+      // two items (sub-tile, 16-column chunk) in flight; (sub, ch) advance without divisions
+      const bool yin = y < p.H;
+      const long long opix0 = n * p.oN + (long long)y * p.oH + (long long)xs * p.oW, rpix0 = n * p.rN + (long long)y * p.rH + (long long)xs * p.rW;
+      int sub = sub_begin, ch = ch_begin;
       for (int it = it_begin; it < it_end; it += 2) {
         uint32_t v0[16], v1[16];
         const bool two = it + 1 < it_end;
+        const int sub_a = sub, ch_a = ch;
+        if (++ch == nchunks) { ch = 0; ++sub; }
+        const int sub_b = sub, ch_b = ch;
+        if (++ch == nchunks) { ch = 0; ++sub; }
         __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
-        tc_ld16_nowait(taddr0 + (uint32_t)((it / nchunks) * p.block_n + (it % nchunks) * 16), v0);
-        if (two) tc_ld16_nowait(taddr0 + (uint32_t)(((it + 1) / nchunks) * p.block_n + ((it + 1) % nchunks) * 16), v1);
+        tc_ld16_nowait(taddr0 + (uint32_t)(sub_a * p.block_n + ch_a * 16), v0);
+        if (two) tc_ld16_nowait(taddr0 + (uint32_t)(sub_b * p.block_n + ch_b * 16), v1);
         tc_ld_wait16(v0);
         if (two) tc_ld_wait16(v1);
-        process(v0, it);
-        if (two) process(v1, it + 1);
+        {
+          const int c = cbase + ch_a * 16;
+          const bool ok = yin && xs + 8 * sub_a < p.W;
+          if (fast_launch && c + 16 <= p.Cout)
+            tc_epilogue16_fast(v0, bias_s + c, slope, reinterpret_cast<__nv_bfloat16*>(p.out) + opix0 + (long long)(8 * sub_a) * p.oW + c, ok);
+          else if (ok && c < p.zero_pad_to)
+            tc_epilogue16_call(ep, v0, bias4, c, opix0 + (long long)(8 * sub_a) * p.oW, rpix0 + (long long)(8 * sub_a) * p.rW);
+        }
+        if (two) {
+          const int c = cbase + ch_b * 16;
+          const bool ok = yin && xs + 8 * sub_b < p.W;
+          if (fast_launch && c + 16 <= p.Cout)
+            tc_epilogue16_fast(v1, bias_s + c, slope, reinterpret_cast<__nv_bfloat16*>(p.out) + opix0 + (long long)(8 * sub_b) * p.oW + c, ok);
+          else if (ok && c < p.zero_pad_to)
+            tc_epilogue16_call(ep, v1, bias4, c, opix0 + (long long)(8 * sub_b) * p.oW, rpix0 + (long long)(8 * sub_b) * p.rW);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -398,8 +425,11 @@ static bool halo_fit(int S, int bn, int kh, int kw, int Cout_pad, bool tma_out, 
 // L2->SM ~ 43 B/clk per SM when every SM streams (chip cap 6.3 KB/clk), up to ~3x that for a lone CTA.
 static bool halo_tma_out(const ConvTc& c) {
   static int on = -1;
-  if (on < 0) on = env_int("DFVO_TMA_STORE", 1);
-  return on && !c.out_f32 && ((uintptr_t)c.out & 15) == 0 && (c.oW * 2) % 16 == 0 && (c.oH * 2) % 16 == 0 && (c.oN * 2) % 16 == 0;
+  // opt-in: measured on B200 (profiles/r02_trace_tma_store.txt) the staged TMA-store epilogue is SLOWER than direct 2 x 16-byte stores on
+  // every full-channel layer (1x1 32->64 @176x608: 26.8 vs 22.7 us; the epilogue is instruction-issue bound, not store bound, and the
+  // staging adds two named barriers + a proxy fence per box); it only wins on the 9 / 25-channel distance maps (11 vs 13 us)
+  if (on < 0) on = env_int("DFVO_TMA_STORE", 0);
+  return on && !c.out_f32 && c.residual == nullptr && c.act <= ACT_RELU && ((uintptr_t)c.out & 15) == 0 && (c.oW * 2) % 16 == 0 && (c.oH * 2) % 16 == 0 && (c.oN * 2) % 16 == 0;
 }
 
 static bool halo_choose(const ConvTc& c, int kh, int kw, HaloCfg* best) {

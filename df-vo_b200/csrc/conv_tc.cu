@@ -210,9 +210,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
 
       TcEpi ep; ep.Cout = p.Cout; ep.zero_pad_to = p.zero_pad_to; ep.act = p.act; ep.out_f32 = p.out_f32; ep.round_tf32 = p.round_tf32; ep.out = p.out; ep.res = p.res;
+      // lean path (tc_ptx.cuh::tc_epilogue16_fast): bf16 output, no residual, LeakyReLU / ReLU / identity, aligned pixels
+      const bool fast_launch = !p.out_f32 && p.res == nullptr && p.act <= ACT_RELU && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 &&
+                               (p.oW & 7) == 0 && (p.oH & 7) == 0 && (p.oN & 7) == 0;
+      const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);
       auto process = [&](const uint32_t* v, int col) {
         const int c = cbase + col;
-        if (inb && c < p.zero_pad_to) tc_epilogue16(ep, v, bias4, c, opix, rpix);
+        if (fast_launch && c + 16 <= p.Cout) tc_epilogue16_fast(v, bias_s + c, slope, reinterpret_cast<__nv_bfloat16*>(p.out) + opix + c, inb);
+        else if (inb && c < p.zero_pad_to) tc_epilogue16_call(ep, v, bias4, c, opix, rpix);
       };
 
       for (int ch = ch_begin; ch < ch_end; ch += 2) {

@@ -21,7 +21,11 @@
 
 namespace dfvo {
 
-struct HState { int niters, best_good, best_iter, it, done, n_subsets; };
+struct HState {
+  int niters, best_good, best_iter, it, done, n_subsets;
+  int pos, ndraws, failed, pad;      // stream offset of the next attempt, raw draws generated so far
+  uint64_t rng;                      // generator state after `ndraws` draws
+};
 
 namespace hmg {
 
@@ -116,35 +120,71 @@ __global__ void k_h_prepare(const double* __restrict__ p1, const double* __restr
   dst[2 * i] = (float)p2[2 * i]; dst[2 * i + 1] = (float)p2[2 * i + 1];
 }
 
-// thread 0 of the block: subsets [i0, i1) of the RANSAC loop (RANSACPointSetRegistrator::getSubset with the homography
-// checkSubset); the generator state is carried between rounds.  Returns the number of subsets available so far.
-DFVO_D int h_make_subsets(const float* __restrict__ src, const float* __restrict__ dst, int N, int i0, int i1, uint64_t* state_io,
-                          int32_t* __restrict__ subsets) {
-  uint64_t state = *state_io;
-  int made = i0;
-  for (int it = i0; it < i1; ++it) {
-    int idx[4];
-    float s[8], d[8];
-    bool found = false;
-    for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
-      for (int i = 0; i < 4;) {
-        state = (uint64_t)(uint32_t)state * 4164903690u + (uint32_t)(state >> 32);
-        const int v = (int)((uint32_t)state % (uint32_t)N);
-        bool dup = false;
-        for (int j = 0; j < i; ++j) dup = dup || idx[j] == v;
-        if (dup) continue;
-        idx[i] = v;
-        s[2 * i] = src[2 * v]; s[2 * i + 1] = src[2 * v + 1]; d[2 * i] = dst[2 * v]; d[2 * i + 1] = dst[2 * v + 1];
-        ++i;
-      }
-      found = hmg::check_subset(s, d);
-    }
-    if (!found) break;                                          // OpenCV stops the loop here
-    for (int i = 0; i < 4; ++i) subsets[it * 4 + i] = idx[i];
-    made = it + 1;
+// ---- subset stream: "parallel-evaluate / sequential-replay" --------------------------------------------------------------------
+// OpenCV draws its 4-point subsets with rejection (checkSubset), so the stream depends on the data and is sequential -- but only
+// through HOW MANY raw draws each attempt consumes.  So: (1) one thread extends the raw uniform stream U[k] = next() % N (a few
+// clocks per draw); (2) every stream offset k is evaluated IN PARALLEL as if an attempt started there: the four distinct indices,
+// the number of draws consumed, checkSubset's verdict; (3) one thread walks the offsets from the current position -- a table
+// look-up per attempt from shared memory -- and emits the subsets OpenCV would have produced.  A sequential generator reading
+// the points from global memory took 2.5 us per subset (5 ms for the 2000 iterations a non-planar scene needs).
+struct HAttempt { int32_t idx[4]; };
+
+DFVO_D uint32_t h_rng_next(uint64_t* state) {
+  *state = (uint64_t)(uint32_t)*state * 4164903690u + (uint32_t)(*state >> 32);      // cv::RNG::next (multiply-with-carry)
+  return (uint32_t)*state;
+}
+
+// Jump-ahead.  cv::RNG is a multiply-with-carry generator: with b = 2^32, S = c*b + x  ->  S' = a*x + c, hence S'*b = S (mod m),
+// m = a*b - 1: the state sequence is S_n = S_2 * r^(n-2) mod m for n >= 2 (r = b^-1 mod m; S_1 of the seed 2^64-1 is not yet a
+// canonical residue, S_2 is).  Any thread can therefore start the stream at any draw index, and the raw stream of a whole RANSAC
+// round is generated in parallel instead of by one thread (64 000 sequential draws were 0.4 ms).
+#define H_RNG_M 0xf83f6309ffffffffull          // 4164903690 * 2^32 - 1
+#define H_RNG_R 0x00000000f83f630aull          // (2^32)^-1 mod m
+#define H_RNG_S1 0xf83f630a07c09cf5ull         // state after the first draw from the seed (uint64)-1
+#define H_RNG_S2 0x07848374bac3439cull         // ... after the second
+DFVO_D uint64_t h_addmod(uint64_t x, uint64_t y) {            // x, y < m
+  const uint64_t s = x + y;
+  return (s < x || s >= H_RNG_M) ? s - H_RNG_M : s;
+}
+DFVO_D uint64_t h_mulmod(uint64_t x, uint64_t y) {            // binary double-and-add (m is within 3 % of 2^64)
+  uint64_t r = 0;
+  for (int i = 63; i >= 0; --i) {
+    r = h_addmod(r, r);
+    if ((y >> i) & 1ull) r = h_addmod(r, x);
   }
-  *state_io = state;
-  return made;
+  return r;
+}
+// generator state after n draws (n >= 0) from the seed cv::RNG((uint64)-1)
+DFVO_D uint64_t h_rng_state_after(uint32_t n) {
+  if (n == 0) return 0xFFFFFFFFFFFFFFFFull;
+  if (n == 1) return H_RNG_S1;
+  uint64_t acc = H_RNG_S2, base = H_RNG_R;
+  for (uint32_t e = n - 2; e; e >>= 1) {
+    if (e & 1u) acc = h_mulmod(acc, base);
+    base = h_mulmod(base, base);
+  }
+  return acc;
+}
+
+// attempt starting at stream offset k: consumed draws (0 if the stream is too short), accepted flag, indices
+DFVO_D uint16_t h_eval_attempt(const uint32_t* __restrict__ U, int k, int ndraws, const float* __restrict__ src, const float* __restrict__ dst,
+                               HAttempt* __restrict__ out) {
+  int idx[4], c = 0;
+  float sp[8], dp[8];
+  for (int i = 0; i < 4;) {
+    if (k + c >= ndraws) return 0;
+    const int v = (int)U[k + c];
+    ++c;
+    bool dup = false;
+    for (int j = 0; j < i; ++j) dup = dup || idx[j] == v;
+    if (dup) continue;
+    idx[i] = v;
+    sp[2 * i] = src[2 * v]; sp[2 * i + 1] = src[2 * v + 1]; dp[2 * i] = dst[2 * v]; dp[2 * i + 1] = dst[2 * v + 1];
+    ++i;
+  }
+  const bool found = hmg::check_subset(sp, dp);
+  for (int i = 0; i < 4; ++i) out->idx[i] = idx[i];
+  return (uint16_t)(c | (found ? 0x8000 : 0));
 }
 
 // one thread per iteration: 4-point normalised DLT -> hyp [max_iters][9], ok [max_iters]
@@ -197,76 +237,164 @@ DFVO_HD int h_update_num_iters(double p, double ep, int model_points, int max_it
   return (int)rint(num / denom);
 }
 
-// ONE block runs the whole estimation: RANSAC rounds (thread 0 draws the subsets, one thread per minimal solve, one warp
-// per hypothesis score, thread 0 replays the acceptance rule; later rounds only if the adaptive iteration count asks
-// for them), then the inlier mask of the winner, the DLT over the inliers, the LM refinement and GRIC-H.  A single
-// launch matters: the tracker's kernels run beside the next frame's persistent convolution kernels, and every
-// dependent launch waits for an SM to take it.
+
+// acceptance rule of RANSACPointSetRegistrator::run over iterations [st.it, min(niters, i1))
+DFVO_D void h_replay(HState* st, const int32_t* __restrict__ ok, const int32_t* __restrict__ counts, int N, int i1, double prob) {
+  HState s2 = *st;
+  if (s2.done) return;
+  int it = s2.it;
+  while (it < s2.niters && it < i1) {
+    if (it >= s2.n_subsets) { s2.done = 1; break; }       // getSubset failed: the loop ends
+    if (ok[it]) {
+      const int good = counts[it];
+      const int lim = s2.best_good > 3 ? s2.best_good : 3;
+      if (good > lim) {
+        s2.best_good = good; s2.best_iter = it;
+        s2.niters = h_update_num_iters(prob, (double)(N - good) / (double)N, 4, s2.niters);
+      }
+    }
+    ++it;
+  }
+  s2.it = it;
+  if (it >= s2.niters) s2.done = 1;
+  *st = s2;
+}
+
+__global__ void k_h_init(HState* st, int max_iters) {
+  if (threadIdx.x == 0) {
+    st->niters = max_iters; st->best_good = -1; st->best_iter = -1; st->it = 0; st->done = 0; st->n_subsets = 0;
+    st->pos = 0; st->ndraws = 0; st->failed = 0; st->rng = 0;
+  }
+}
+
+#define H_DRAWS_PER_SUBSET 40     // window of raw draws per subset: ~4 when nothing is rejected, ~32 with 60 % gross outliers
+#define H_DRAW_CHUNK 32
+
+// round start (one thread): replay of the previous round, then the window of raw draws the coming round may need
+__global__ void k_h_round_begin(HState* st, const int32_t* __restrict__ ok, const int32_t* __restrict__ counts, int N, int prev_i1, int i0, int i1,
+                                double prob, int max_draws) {
+  if (threadIdx.x != 0) return;
+  if (prev_i1 > 0) h_replay(st, ok, counts, N, prev_i1, prob);
+  if (st->done) return;
+  int target = st->pos + (i1 - i0) * H_DRAWS_PER_SUBSET + 1024;
+  if (target > max_draws) target = max_draws;
+  if (target > st->ndraws) st->ndraws = target;
+}
+
+// raw stream U[k] = draw k % N for the window [pos, ndraws): each thread jumps to its chunk and runs the generator from there
+__global__ void __launch_bounds__(128)
+k_h_draws(const HState* __restrict__ st, int N, uint32_t* __restrict__ U) {
+  if (st->done) return;
+  const int k0 = st->pos + (blockIdx.x * blockDim.x + threadIdx.x) * H_DRAW_CHUNK;
+  if (k0 >= st->ndraws) return;
+  uint64_t state = h_rng_state_after((uint32_t)k0);
+  const int k1 = k0 + H_DRAW_CHUNK < st->ndraws ? k0 + H_DRAW_CHUNK : st->ndraws;
+  for (int k = k0; k < k1; ++k) U[k] = h_rng_next(&state) % (uint32_t)N;
+}
+
+// every stream offset of the window as a potential attempt start
+__global__ void __launch_bounds__(128)
+k_h_attempts(const HState* __restrict__ st, const uint32_t* __restrict__ U, const float* __restrict__ src, const float* __restrict__ dst,
+             uint16_t* __restrict__ att, HAttempt* __restrict__ atti) {
+  if (st->done) return;
+  const int k = st->pos + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st->ndraws) return;
+  att[k] = h_eval_attempt(U, k, st->ndraws, src, dst, &atti[k]);
+}
+
+// the sequential walk: subsets [i0, i1) from the attempt table (thread 0, table staged in shared memory), then the copy-out
+__global__ void __launch_bounds__(256)
+k_h_walk(HState* st, uint32_t* __restrict__ U, int max_draws, const float* __restrict__ src, const float* __restrict__ dst, int N,
+         uint16_t* __restrict__ att, HAttempt* __restrict__ atti, int i0, int i1, int32_t* __restrict__ acc_off, int32_t* __restrict__ subsets, int cap) {
+  DFVO_DYN_SMEM(uint16_t, tab);
+  __shared__ int made_s;
+  if (st->done) return;
+  const int t = threadIdx.x, p0 = st->pos;
+  int span = st->ndraws - p0;
+  if (span > cap) span = cap;
+  for (int k = t; k < span; k += 256) tab[k] = att[p0 + k];
+  __syncthreads();
+  if (t == 0) {
+    int p = p0, made = i0, ndraws = st->ndraws;
+    bool failed = false;
+    for (int it = i0; it < i1 && !failed; ++it) {
+      bool found = false;
+      for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
+        uint16_t a = (p - p0 < span) ? tab[p - p0] : (p < ndraws ? att[p] : (uint16_t)0);
+        if ((a & 0x7fff) == 0) {
+          // the pre-evaluated window is exhausted (more rejections than H_DRAWS_PER_SUBSET allows for): extend the stream from
+          // this offset and evaluate the attempt here, sequentially
+          if (ndraws < p + 64) {
+            int to = p + 64 < max_draws ? p + 64 : max_draws;
+            uint64_t state = h_rng_state_after((uint32_t)ndraws);
+            for (int k = ndraws; k < to; ++k) U[k] = h_rng_next(&state) % (uint32_t)N;
+            ndraws = to > ndraws ? to : ndraws;
+          }
+          a = h_eval_attempt(U, p, ndraws, src, dst, &atti[p]);
+          if ((a & 0x7fff) == 0) { failed = true; break; }            // stream capacity exhausted
+        }
+        if (a & 0x8000) { acc_off[it] = p; found = true; }
+        p += a & 0x7fff;
+      }
+      if (!found) break;                                          // OpenCV stops the loop here
+      made = it + 1;
+    }
+    st->pos = p; st->ndraws = ndraws; st->n_subsets = made;
+    made_s = made;
+  }
+  __syncthreads();
+  for (int it = i0 + t; it < made_s; it += 256) {
+    const HAttempt a = atti[acc_off[it]];
+    for (int i = 0; i < 4; ++i) subsets[it * 4 + i] = a.idx[i];
+  }
+}
+
+__global__ void __launch_bounds__(64)
+k_h_hyp(const HState* __restrict__ st, const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ subsets, int i0,
+        int i1, double* __restrict__ hyp, int32_t* __restrict__ ok) {
+  if (st->done) return;
+  const int it = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= i1) return;
+  if (it < st->n_subsets) h_hypothesis(src, dst, subsets, it, hyp, ok);
+  else ok[it] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_h_score(const HState* __restrict__ st, const float* __restrict__ src, const float* __restrict__ dst, int N, int i0, int i1, float thr2,
+          const double* __restrict__ hyp, const int32_t* __restrict__ ok, int32_t* __restrict__ counts) {
+  if (st->done) return;
+  const int it = i0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (it >= i1) return;
+  int c = 0;
+  if (ok[it]) {
+    float Hf[8];
+    for (int q = 0; q < 8; ++q) Hf[q] = (float)hyp[(size_t)it * 9 + q];
+    for (int j = lane; j < N; j += 32) c += (h_err(Hf, src[2 * j], src[2 * j + 1], dst[2 * j], dst[2 * j + 1]) <= thr2) ? 1 : 0;
+  }
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if (lane == 0) counts[it] = c;
+}
+
+// ONE block finishes the estimation: replay of the last round, the inlier mask of the winner, the DLT over the inliers, the LM
+// refinement and GRIC-H.
 // out: H_out [9], mask [N] (inliers of the refined H), info [4] = {found, inliers, iterations, winning iteration}, gric [1]
 __global__ void __launch_bounds__(256)
-k_h_ransac(const float* __restrict__ src, const float* __restrict__ dst, const double* __restrict__ p1, const double* __restrict__ p2, int N,
-           int max_iters, double prob, float thr2, double* __restrict__ hyp, int32_t* __restrict__ subsets, int32_t* __restrict__ ok,
-           int32_t* __restrict__ counts, double* __restrict__ H_out, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
-           double* __restrict__ gric) {
+k_h_finalize(HState* st, const float* __restrict__ src, const float* __restrict__ dst, const double* __restrict__ p1, const double* __restrict__ p2,
+             int N, int max_iters, double prob, float thr2, const double* __restrict__ hyp, const int32_t* __restrict__ ok,
+             const int32_t* __restrict__ counts, double* __restrict__ H_out, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
+             double* __restrict__ gric) {
   __shared__ double part[8][48];
   __shared__ double acc[48];
   __shared__ double Hs[9], xs[8], xd[8], dvec[8], Amat[8][8], vvec[8];
   __shared__ double S_cur, S_new, lambda, lc;
   __shared__ int stop, ninl;
   __shared__ HState sst;
-  __shared__ uint64_t rng_state;
   const int t = threadIdx.x;
   if (t == 0) {
-    sst.niters = max_iters; sst.best_good = -1; sst.best_iter = -1; sst.it = 0; sst.done = 0; sst.n_subsets = 0;
-    rng_state = 0xFFFFFFFFFFFFFFFFull;                          // cv::RNG((uint64)-1)
+    h_replay(st, ok, counts, N, max_iters, prob);
+    sst = *st;
   }
   __syncthreads();
-  {
-    const int bounds[5] = {0, 64, 320, 1088, max_iters};
-    for (int rd = 0; rd < 4; ++rd) {
-      const int i0 = bounds[rd] < max_iters ? bounds[rd] : max_iters, i1 = bounds[rd + 1] < max_iters ? bounds[rd + 1] : max_iters;
-      if (i1 <= i0) continue;
-      if (t == 0) sst.n_subsets = h_make_subsets(src, dst, N, i0, i1, &rng_state, subsets);
-      __syncthreads();
-      for (int it = i0 + t; it < i1; it += 256) {
-        if (it < sst.n_subsets) h_hypothesis(src, dst, subsets, it, hyp, ok);
-        else ok[it] = 0;
-      }
-      __syncthreads();
-      for (int it = i0 + (t >> 5); it < i1; it += 8) {          // one warp per hypothesis
-        int c = 0;
-        if (ok[it]) {
-          float Hf[8];
-          for (int q = 0; q < 8; ++q) Hf[q] = (float)hyp[(size_t)it * 9 + q];
-          for (int j = (t & 31); j < N; j += 32) c += (h_err(Hf, src[2 * j], src[2 * j + 1], dst[2 * j], dst[2 * j + 1]) <= thr2) ? 1 : 0;
-        }
-        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if ((t & 31) == 0) counts[it] = c;
-      }
-      __syncthreads();
-      if (t == 0) {                                             // acceptance rule of RANSACPointSetRegistrator::run
-        HState s2 = sst;
-        int it = s2.it;
-        while (it < s2.niters && it < i1) {
-          if (it >= s2.n_subsets) { s2.done = 1; break; }       // getSubset failed: the loop ends
-          if (ok[it]) {
-            const int good = counts[it];
-            const int lim = s2.best_good > 3 ? s2.best_good : 3;
-            if (good > lim) {
-              s2.best_good = good; s2.best_iter = it;
-              s2.niters = h_update_num_iters(prob, (double)(N - good) / (double)N, 4, s2.niters);
-            }
-          }
-          ++it;
-        }
-        s2.it = it;
-        if (it >= s2.niters) s2.done = 1;
-        sst = s2;
-      }
-      __syncthreads();
-      if (sst.done) break;
-    }
-  }
   const HState s = sst;
   auto block_sum_vec = [&](const double* a, int n) {            // sums of n <= 48 per-thread values -> acc[0..n)
     for (int k = 0; k < n; ++k) {
@@ -497,8 +625,11 @@ k_h_ransac(const float* __restrict__ src, const float* __restrict__ dst, const d
   }
 }
 
+static int h_max_draws(int max_iters) { return max_iters * (H_DRAWS_PER_SUBSET + 8) + 8192; }
+
 size_t homography_workspace_bytes(int N, int max_iters) {
-  return (size_t)N * 4 * 4 + (size_t)max_iters * (9 * 8 + 4 * 4 + 4 + 4) + sizeof(HState) + 8 + 2048;
+  const size_t nd = (size_t)h_max_draws(max_iters);
+  return (size_t)N * 4 * 4 + (size_t)max_iters * (9 * 8 + 4 * 4 + 4 + 4 + 4) + nd * (4 + 2 + sizeof(HAttempt)) + sizeof(HState) + 4096;
 }
 
 int homography_ransac(const double* p1, const double* p2, int N, int max_iters, double threshold, double prob, void* workspace, size_t ws_bytes,
@@ -507,16 +638,42 @@ int homography_ransac(const double* p1, const double* p2, int N, int max_iters, 
   DFVO_REQUIRE(ws_bytes >= homography_workspace_bytes(N, max_iters), DFVO_EINVAL, "homography_ransac workspace too small");
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   auto take = [&](size_t bytes) { uint8_t* p = w; w += (bytes + 127) & ~(size_t)127; return p; };
+  const int nd = h_max_draws(max_iters);
   float* src = (float*)take((size_t)N * 2 * 4);
   float* dst = (float*)take((size_t)N * 2 * 4);
   double* hyp = (double*)take((size_t)max_iters * 9 * 8);
   int32_t* subsets = (int32_t*)take((size_t)max_iters * 4 * 4);
   int32_t* ok = (int32_t*)take((size_t)max_iters * 4);
   int32_t* counts = (int32_t*)take((size_t)max_iters * 4);
+  int32_t* acc_off = (int32_t*)take((size_t)max_iters * 4);
+  uint32_t* U = (uint32_t*)take((size_t)nd * 4);
+  uint16_t* att = (uint16_t*)take((size_t)nd * 2);
+  HAttempt* atti = (HAttempt*)take((size_t)nd * sizeof(HAttempt));
+  HState* st = (HState*)take(sizeof(HState));
   const float thr2 = (float)(threshold * threshold);
   DFVO_LAUNCH(k_h_prepare, dim3(cdiv(N, 128)), dim3(128), 0, s, p1, p2, N, src, dst);
-  DFVO_LAUNCH(k_h_ransac, dim3(1), dim3(256), 0, s, src, dst, p1, p2, N, max_iters, prob, thr2, hyp, subsets, ok, counts, H_out, mask_out,
-              info, gric);
+  DFVO_LAUNCH(k_h_init, dim3(1), dim3(32), 0, s, st, max_iters);
+  // rounds: a scene with a dominant plane stops inside the first; a general scene (no homography fits most points) runs all max_iters
+  const int bounds[3] = {0, 256, max_iters};
+  int prev_i1 = 0;
+#ifndef DFVO_HOSTSIM
+  static bool attr_set = false;
+  if (!attr_set) { DFVO_CUDA(cudaFuncSetAttribute(k_h_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+#endif
+  for (int rd = 0; rd < 2; ++rd) {
+    const int i0 = bounds[rd] < max_iters ? bounds[rd] : max_iters, i1 = bounds[rd + 1] < max_iters ? bounds[rd + 1] : max_iters;
+    if (i1 <= i0) continue;
+    DFVO_LAUNCH(k_h_round_begin, dim3(1), dim3(32), 0, s, st, ok, counts, N, prev_i1, i0, i1, prob, nd);
+    const int window = (i1 - i0) * H_DRAWS_PER_SUBSET + 1024;
+    DFVO_LAUNCH(k_h_draws, dim3(cdiv(cdiv(window, H_DRAW_CHUNK), 128)), dim3(128), 0, s, st, N, U);
+    DFVO_LAUNCH(k_h_attempts, dim3(cdiv(window, 128)), dim3(128), 0, s, st, U, src, dst, att, atti);
+    const int cap = window < 80 * 1024 ? window : 80 * 1024;         // table entries staged in shared memory (2 B each)
+    DFVO_LAUNCH(k_h_walk, dim3(1), dim3(256), (size_t)cap * 2, s, st, U, nd, src, dst, N, att, atti, i0, i1, acc_off, subsets, cap);
+    DFVO_LAUNCH(k_h_hyp, dim3(cdiv(i1 - i0, 64)), dim3(64), 0, s, st, src, dst, subsets, i0, i1, hyp, ok);
+    DFVO_LAUNCH(k_h_score, dim3(cdiv((i1 - i0) * 32, 256)), dim3(256), 0, s, st, src, dst, N, i0, i1, thr2, hyp, ok, counts);
+    prev_i1 = i1;
+  }
+  DFVO_LAUNCH(k_h_finalize, dim3(1), dim3(256), 0, s, st, src, dst, p1, p2, N, max_iters, prob, thr2, hyp, ok, counts, H_out, mask_out, info, gric);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }

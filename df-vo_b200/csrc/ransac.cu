@@ -11,6 +11,8 @@
 //   5. k_finalize: inlier mask + GRIC-E residual sum (gric.py:14-37,94-132) of each repeat's winner;
 //   6. k_recover_pose_vote / _pick: decomposeEssentialMat + 4 x triangulation + cheirality vote.
 // All arithmetic is FP64 (inlier decisions are threshold tests).
+#include <stdlib.h>
+
 #include "fivept.cuh"
 #include "ops.h"
 #include "ransac.h"
@@ -115,6 +117,36 @@ __global__ void k_hypotheses(const double* __restrict__ x1n, const double* __res
   size_t h = (size_t)r * max_iters + i;
   ncand[h] = c;
   for (int k = 0; k < 9 * c; ++k) Ecand[h * 90 + k] = e[k];
+}
+
+// Warp-cooperative hypothesis generation (fivept::solve_coop): ten lanes per minimal sample, three samples per warp.
+#ifdef DFVO_HOSTSIM
+#define HYP_WARPS 1          // the CPU emulation pays per shuffle and per thread of the block
+#else
+#define HYP_WARPS 4
+#endif
+__global__ void __launch_bounds__(HYP_WARPS * 32)
+k_hypotheses_coop(const double* __restrict__ x1n, const double* __restrict__ x2n, const int32_t* __restrict__ subsets, int N, int i0, int i1,
+                  const EssState* __restrict__ st, double* __restrict__ Ecand, int32_t* __restrict__ ncand, int max_iters) {
+  __shared__ fivept::CoopShared sm[HYP_WARPS * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = blockIdx.y;
+  if (st[r].done) return;                                  // uniform per block
+  int g = lane / 10, l = lane - 10 * g;
+  if (g == 3) { g = 2; l += 10; }                           // lanes 30, 31 ride along with the third group
+  int i = i0 + (blockIdx.x * HYP_WARPS + warp) * 3 + g;
+  const bool live = i < i1;
+  if (!live) i = i1 - 1;                                    // duplicate work on a valid sample, results discarded
+  double a[10], b[10];
+  for (int k = 0; k < 5; ++k) {
+    const int s = subsets[i * 5 + k];
+    const size_t o = ((size_t)r * N + s) * 2;
+    a[2 * k] = x1n[o]; a[2 * k + 1] = x1n[o + 1];
+    b[2 * k] = x2n[o]; b[2 * k + 1] = x2n[o + 1];
+  }
+  const size_t h = (size_t)r * max_iters + i;
+  // dead groups write nowhere: E_out is only dereferenced by lanes whose candidate exists (live is folded into `ok`)
+  const int c = fivept::solve_coop(a, b, &sm[warp * 3 + g], l, 10 * g, live, Ecand + h * 90);
+  if (live && l == 0) ncand[h] = c;
 }
 
 __global__ void __launch_bounds__(256)
@@ -261,7 +293,13 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
   for (int rd = 0; rd < 3; ++rd) {
     const int i0 = bounds[rd], i1 = bounds[rd + 1];
     if (i1 <= i0) continue;
-    DFVO_LAUNCH(k_hypotheses, dim3(cdiv(i1 - i0, 32), R), dim3(32), 0, s, x1n, x2n, subsets, N, i0, i1, st, Ecand, ncand, max_iters);
+    static int coop = -1;
+    if (coop < 0) { const char* e = getenv("DFVO_HYP_COOP"); coop = !(e && atoi(e) == 0); }
+    if (coop)
+      DFVO_LAUNCH(k_hypotheses_coop, dim3(cdiv(i1 - i0, HYP_WARPS * 3), R), dim3(HYP_WARPS * 32), 0, s, x1n, x2n, subsets, N, i0, i1, st, Ecand,
+                  ncand, max_iters);
+    else
+      DFVO_LAUNCH(k_hypotheses, dim3(cdiv(i1 - i0, 32), R), dim3(32), 0, s, x1n, x2n, subsets, N, i0, i1, st, Ecand, ncand, max_iters);
     DFVO_LAUNCH(k_score_round, dim3(cdiv((i1 - i0) * 10 * 32, 256), R), dim3(256), 0, s, Ecand, ncand, x1n, x2n, N, i0, i1, thr2, st,
                 counts, max_iters);
     DFVO_LAUNCH(k_replay, dim3(1), dim3(32), 0, s, ncand, counts, N, i1, prob, st, max_iters, R);

@@ -213,55 +213,44 @@ static __device__ __noinline__ void tc_epilogue16_slow(TcEpi p, float4 f0, float
   }
 }
 
-// bias + optional bf16 residual + activation of 16 consecutive output channels [c, c+16) of one pixel, packed to 8 bf16x2 words
-// (channels >= Cout are zero).  The TMA-store epilogue stages these in shared memory; `have_res` must be false for pixels outside
-// the image.
-__device__ __forceinline__ void tc_epilogue16_pack(const TcEpi& p, const uint32_t* v, const float4* bias4, int c, long long rpix, bool have_res,
-                                                   uint32_t* w) {
-  float f[16];
+// Lean epilogue for the common case (bf16 output, no residual, LeakyReLU / ReLU / identity, all 16 channels real, 16-byte aligned
+// pixel): v = 16 fp32 accumulator words, bias = 16 floats in shared memory.  ncu showed the generic path costing 374 instructions per
+// two chunks (integer divisions, per-chunk alignment / tail / slow-path tests, scalar FADD / FMUL) and the epilogue warps -- two
+// per scheduler -- issue-bound at ~20 %: 7.7 us per 256 x 128 tile against 4.8 us of MMAs.  Here: 8 FADD2 + 8 FMUL2 (packed fp32x2,
+// sm_100) + 16 FMNMX + 8 F2FP + 2 STG.128.
+__device__ __forceinline__ void tc_epilogue16_fast_pack(const uint32_t* v, const float* bias, float slope, uint32_t* w) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+  unsigned long long sl;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(sl) : "f"(slope));
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 b = bias4[(c >> 2) + j];
-    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    const float4 b = b4[j];
+    unsigned long long a0, a1, b0, b1, x0, x1, y0, y1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "r"(v[4 * j]), "r"(v[4 * j + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "r"(v[4 * j + 2]), "r"(v[4 * j + 3]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b0) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b1) : "f"(b.z), "f"(b.w));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x0) : "l"(a0), "l"(b0));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x1) : "l"(a1), "l"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(y0) : "l"(x0), "l"(sl));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(y1) : "l"(x1), "l"(sl));
+    float xa, xb, xc, xd, ya, yb, yc, yd;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(xa), "=f"(xb) : "l"(x0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(xc), "=f"(xd) : "l"(x1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ya), "=f"(yb) : "l"(y0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(yc), "=f"(yd) : "l"(y1));
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(xa, ya), fmaxf(xb, yb));
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(xc, yc), fmaxf(xd, yd));
+    w[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+    w[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
   }
-  if (have_res) {
-    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix + c;
-    if (c + 16 <= p.Cout && (reinterpret_cast<uintptr_t>(r) & 15u) == 0) {
-      const uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
-      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        f[2 * j] += __uint_as_float(rw[j] << 16);
-        f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-      }
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < 16; ++j)
-        if (c + j < p.Cout) f[j] += __bfloat162float(r[j]);
-    }
-  }
-  if (p.act <= ACT_RELU) {
-    const float slope = p.act == ACT_LEAKY ? 0.1f : (p.act == ACT_RELU ? 0.f : 1.f);      // max(f, f) = f for ACT_NONE
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope * f[j]);
-  } else if (p.act == ACT_ELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + expf(-f[j]));
-  }
-  if (c + 16 > p.Cout) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = (c + j < p.Cout) ? f[j] : 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    w[j] = *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void tc_epilogue16_fast(const uint32_t* v, const float* bias, float slope, __nv_bfloat16* o, bool valid) {
+  uint32_t w[8];
+  tc_epilogue16_fast_pack(v, bias, slope, w);
+  if (valid) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -360,6 +349,19 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& p, const uint32_t* v,
   }
   *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
   *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+// Out-of-line instance of the general epilogue for the conv kernels' rare chunks (residual / ELU / sigmoid / fp32 output / channel
+// tails): one copy of the ~15 KB of unrolled activation code per kernel instead of one per call site (the kernels were 128 KB of
+// SASS; ncu showed `no_instruction` stalls in the epilogue warps).  The accumulator words travel by value (registers).
+struct TcAcc16 { uint32_t v[16]; };
+static __device__ __noinline__ void tc_epilogue16_general(TcEpi p, TcAcc16 a, const float4* bias4, int c, long long opix, long long rpix) {
+  tc_epilogue16(p, a.v, bias4, c, opix, rpix);
+}
+__device__ __forceinline__ void tc_epilogue16_call(const TcEpi& p, const uint32_t* v, const float4* bias4, int c, long long opix, long long rpix) {
+  TcAcc16 a;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a.v[j] = v[j];
+  tc_epilogue16_general(p, a, bias4, c, opix, rpix);
 }
 #endif  // !DFVO_HOSTSIM
 

@@ -37,7 +37,7 @@ class DeepModel:
     def __init__(self, cfg):
         self.cfg = cfg
         self.finetune_cfg = cfg.online_finetune
-        self.precision = native.PREC_FP32 if os.environ.get("DFVO_B200_PRECISION", "bf16") == "fp32" else native.PREC_BF16
+        self.precision = native.PREC_NAMES[os.environ.get("DFVO_B200_PRECISION", "bf16")]          # bf16 | tf32 | fp32
         self.engine = tracking.default_engine(cfg.image.height, cfg.image.width)
         self.rt = self.engine.rt
 

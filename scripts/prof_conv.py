@@ -6,7 +6,8 @@ import numpy as np, torch
 from b200 import native
 from util import dptr
 lib = native.load()
-shapes = [(2, 128, 176, 608, 128, 3, 3, 1, 1), (2, 32, 176, 608, 128, 1, 1, 0, 0), (2, 128, 176, 608, 64, 3, 3, 1, 1)]
+shapes = [(2, 128, 176, 608, 128, 3, 3, 1, 1), (2, 32, 176, 608, 128, 1, 1, 0, 0), (2, 128, 176, 608, 64, 3, 3, 1, 1),
+          (2, 32, 176, 608, 64, 1, 1, 0, 0), (2, 64, 176, 608, 128, 3, 3, 1, 1), (2, 64, 176, 608, 32, 3, 3, 1, 1)]
 if len(sys.argv) > 1:
     shapes = [shapes[int(a)] for a in sys.argv[1:]]
 for (B, Cin, H, W, Cout, kh, kw, py, px) in shapes:
