@@ -442,7 +442,15 @@ void tc_prof_end(cudaStream_t s, const TcProf& p, double flops, const char* desc
   g_prof_desc.push_back(desc);
 }
 
+int conv_tc_single(const ConvTc& c, cudaStream_t s);
 int conv_tc(const ConvTc& c, cudaStream_t s) {
+  int rc = DFVO_OK;
+  if (conv_chain_take(c, s, &rc)) return rc;              // deferred into the open layer chain (conv_chain.cu)
+  if (rc) return rc;
+  return conv_tc_single(c, s);
+}
+
+int conv_tc_single(const ConvTc& c, cudaStream_t s) {
   if (conv_halo_supported(c)) return conv_halo(c, s);
   ConvTcPlanImpl pl;
   int rc = build_plan(c, &pl);

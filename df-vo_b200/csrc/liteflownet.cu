@@ -68,6 +68,9 @@ struct LfnImpl : public LiteFlowNetBase {
   T* subcat[7]; int subC[7];
   T *mfeat, *warpbuf, *corr, *corrU, *b128a, *b128b, *b64a, *b64b, *b32a, *b32b, *d0, *d1, *regcat;
   float *flow_up, *flow_m, *flow_s, *flow_r[7], *meanbuf;
+  unsigned* chain_bars = nullptr;   // arrival counters of the layer chains: one block per chain site of the forward pass
+  int chain_site = 0;
+  unsigned* next_chain() { return (IsBf16<T>::v && chain_bars && chain_site < 64) ? chain_bars + (chain_site++) * CHAIN_BAR_WORDS : nullptr; }
   float* out_planar = nullptr;   // [B][2][H0][W0]
 
   ~LfnImpl() override {}
@@ -233,6 +236,7 @@ struct LfnImpl : public LiteFlowNetBase {
     for (int L = 2; L <= 6; ++L) ALLOC(flow_r[L], float, px(L) * 2);
     ALLOC(meanbuf, float, flow_mean_buffer_floats(B));
     ALLOC(out_planar, float, (size_t)B * 2 * H0 * W0);
+    ALLOC(chain_bars, unsigned, 64 * CHAIN_BAR_WORDS);
     return DFVO_OK;
   }
 
@@ -264,6 +268,7 @@ struct LfnImpl : public LiteFlowNetBase {
       DFVO_REQUIRE(fOne.w_direct, DFVO_ESTATE, "moduleOne weights");
       TRY((conv_direct<float, T>(d, cfview(img[1], 1, 3, 4), view(f1buf, 1, 32, 32), none, s)));
     }
+    ChainScope chain(s, next_chain());          // consecutive stride-1 layers of the pyramid become one launch
     TRY(run_conv<T>(fTwo0, cview(f1buf, 1, 32, 32), view(t2a, 2, 32, 32), ACT_LEAKY, none, 0, s));
     TRY(run_conv<T>(fTwo2, cview(t2a, 2, 32, 32), view(t2b, 2, 32, 32), ACT_LEAKY, none, 0, s));
     TRY(run_conv<T>(fTwo4, cview(t2b, 2, 32, 32), view(feat2, 2, 32, 32), ACT_LEAKY, none, 0, s));
@@ -273,7 +278,7 @@ struct LfnImpl : public LiteFlowNetBase {
     TRY(run_conv<T>(fFou2, cview(t4a, 4, 96, 96), view(subcat[4], 4, 96, subC[4]), ACT_LEAKY, none, 0, s));
     TRY(run_conv<T>(fFiv0, cview(subcat[4], 4, 96, subC[4]), view(subcat[5], 5, 128, subC[5]), ACT_LEAKY, none, 0, s));
     TRY(run_conv<T>(fSix0, cview(subcat[5], 5, 128, subC[5]), view(subcat[6], 6, 192, subC[6]), ACT_LEAKY, none, 0, s));
-    return DFVO_OK;
+    return chain.end();
   }
 
   int level(int L, const float* flow_prev, cudaStream_t s) {
@@ -310,18 +315,26 @@ struct LfnImpl : public LiteFlowNetBase {
     } else {
       cin = cview(corr, L, 64, 64);
     }
-    TRY(run_conv<T>(v.mMain0, cin, view(b128a, L, 128, 128), ACT_LEAKY, none, 0, s));
-    TRY(run_conv<T>(v.mMain2, cview(b128a, L, 128, 128), view(b64a, L, 64, 64), ACT_LEAKY, none, 0, s));
-    TRY(run_conv<T>(v.mMain4, cview(b64a, L, 64, 64), view(b32a, L, 32, 32), ACT_LEAKY, none, 0, s));
+    {
+      ChainScope chain(s, next_chain());
+      TRY(run_conv<T>(v.mMain0, cin, view(b128a, L, 128, 128), ACT_LEAKY, none, 0, s));
+      TRY(run_conv<T>(v.mMain2, cview(b128a, L, 128, 128), view(b64a, L, 64, 64), ACT_LEAKY, none, 0, s));
+      TRY(run_conv<T>(v.mMain4, cview(b64a, L, 64, 64), view(b32a, L, 32, 32), ACT_LEAKY, none, 0, s));
+      TRY(chain.end());
+    }
     TRY(run_conv_f32out<T>(v.mMain6, cview(b32a, L, 32, 32), fview(flow_m, L, 2, 2), ACT_NONE,
                            flow_prev ? cfview(flow_up, L, 2, 2) : fnone, s));
     // ------------------------------ Subpixel (lite_flow_net.py:182-190) -----------------------
     if (L == 2) TRY(run_conv<T>(v.sFeat, cview(feat2, 2, 32, 32), view(subcat[2], 2, 64, subC[2]), ACT_LEAKY, none, 0, s));
     TRY(warp_bilinear<T>(cview(subcat[L], L, C, subC[L]), cfview(flow_m, L, 2, 2), dbl, 1, view(subcat[L] + C, L, C, subC[L]), s));
     TRY((convert_copy<float, T>(cfview(flow_m, L, 2, 2), view(subcat[L] + 2 * C, L, 16, subC[L]), s)));
-    TRY(run_conv<T>(v.sMain0, cview(subcat[L], L, subC[L], subC[L]), view(b128a, L, 128, 128), ACT_LEAKY, none, 0, s));
-    TRY(run_conv<T>(v.sMain2, cview(b128a, L, 128, 128), view(b64a, L, 64, 64), ACT_LEAKY, none, 0, s));
-    TRY(run_conv<T>(v.sMain4, cview(b64a, L, 64, 64), view(b32a, L, 32, 32), ACT_LEAKY, none, 0, s));
+    {
+      ChainScope chain(s, next_chain());
+      TRY(run_conv<T>(v.sMain0, cview(subcat[L], L, subC[L], subC[L]), view(b128a, L, 128, 128), ACT_LEAKY, none, 0, s));
+      TRY(run_conv<T>(v.sMain2, cview(b128a, L, 128, 128), view(b64a, L, 64, 64), ACT_LEAKY, none, 0, s));
+      TRY(run_conv<T>(v.sMain4, cview(b64a, L, 64, 64), view(b32a, L, 32, 32), ACT_LEAKY, none, 0, s));
+      TRY(chain.end());
+    }
     TRY(run_conv_f32out<T>(v.sMain6, cview(b32a, L, 32, 32), fview(flow_s, L, 2, 2), ACT_NONE, cfview(flow_m, L, 2, 2), s));
     // ------------------------------ Regularization (lite_flow_net.py:243-264) ------------------
     const int RF = (L < 5) ? 128 : kFeatC[L];
@@ -329,11 +342,11 @@ struct LfnImpl : public LiteFlowNetBase {
     TRY(flow_mean(cfview(flow_s, L, 2, 2), meanbuf, s));
     TRY(reg_prep<T>(cfview(img[L], L, 3, 4), cfview(img[L], L, 3, 4), 1, cfview(flow_s, L, 2, 2), meanbuf, dbl,
                     view(regcat, L, 16, RC), s));
+    if (L >= 5) TRY((convert_copy<T, T>(cview(subcat[L], L, RF, subC[L]), view(regcat + 16, L, RF, RC), s)));
+    ChainScope chain(s, next_chain());            // rFeat, the six main layers and the distance conv(s): one launch
     if (L < 5) {
       Ten<const T> rf = (L == 2) ? cview(feat2, 2, 32, 32) : cview(subcat[L], L, kFeatC[L], subC[L]);
       TRY(run_conv<T>(v.rFeat, rf, view(regcat + 16, L, 128, RC), ACT_LEAKY, none, 0, s));
-    } else {
-      TRY((convert_copy<T, T>(cview(subcat[L], L, RF, subC[L]), view(regcat + 16, L, RF, RC), s)));
     }
     TRY(run_conv<T>(v.rMain[0], cview(regcat, L, RC, RC), view(b128a, L, 128, 128), ACT_LEAKY, none, 0, s));
     TRY(run_conv<T>(v.rMain[1], cview(b128a, L, 128, 128), view(b128b, L, 128, 128), ACT_LEAKY, none, 0, s));
@@ -351,6 +364,7 @@ struct LfnImpl : public LiteFlowNetBase {
       TRY(run_conv<T>(v.rDist1, cview(d0, L, cdp, cdp), view(d1, L, cd, cdp), ACT_NONE, none, 0, s));
       dist = d1;
     }
+    TRY(chain.end());
     TRY(reg_tail<T>(cview(dist, L, cd, cdp), cfview(flow_s, L, 2, 2), kl, v.wx, v.wy, v.bx, v.by, fview(flow_r[L], L, 2, 2), s));
     return DFVO_OK;
   }
@@ -358,6 +372,7 @@ struct LfnImpl : public LiteFlowNetBase {
   // everything between the ingest and the emit: touches only buffers this object owns, so it is one fixed launch
   // sequence (replayed as a CUDA graph by the C-ABI layer)
   int body(cudaStream_t s) override {
+    chain_site = 0;
     TRY(features(s));
     const float* prev = nullptr;
     for (int L = 6; L >= 2; --L) {

@@ -37,6 +37,7 @@ struct MonoImpl : public Monodepth2Base {
   T* padbuf;                  // reflection-padded conv input scratch
   T *dA, *dB;                 // decoder activations
   float* disp;
+  unsigned* chain_bars = nullptr;     // arrival counters of the encoder's layer chain
 
   Ten<T> tv(T* p, int H, int W, int C, int pitch) { return make_ten<T>(p, 1, H, W, C, pitch); }
   Ten<const T> ctv(const T* p, int H, int W, int C, int pitch) { return cten(make_ten<T>(const_cast<T*>(p), 1, H, W, C, pitch)); }
@@ -125,6 +126,7 @@ struct MonoImpl : public Monodepth2Base {
     ALLOCM(padbuf, T, pmax);
     ALLOCM(dA, T, (size_t)h * w * 16 + (size_t)(h / 2) * (w / 2) * 32); ALLOCM(dB, T, (size_t)h * w * 16 + (size_t)(h / 2) * (w / 2) * 32);
     ALLOCM(disp, float, (size_t)h * w);
+    ALLOCM(chain_bars, unsigned, 4 * CHAIN_BAR_WORDS);
     return DFVO_OK;
   }
 
@@ -152,12 +154,17 @@ struct MonoImpl : public Monodepth2Base {
     TRYM(maxpool3x3s2<T>(ctv(f[0], fh[0], fw[0], 64, 64), tv(pool, fh[1], fw[1], 64, 64), s));
     const T* cur = pool;
     int ch = fh[1], cw = fw[1], cc = 64;
-    for (int li = 0; li < 4; ++li) {
-      const int oc = fc[li + 1];
-      TRYM(basic_block(blk[li][0], cur, ch, cw, cc, tB, oc, s));
-      ch /= blk[li][0].stride; cw /= blk[li][0].stride; cc = oc;
-      TRYM(basic_block(blk[li][1], tB, ch, cw, cc, f[li + 1], oc, s));
-      cur = f[li + 1];
+    {
+      // the encoder is convolutions only: consecutive stride-1 layers (c1 -> c2 of a block, and on into the next block) form chains
+      ChainScope chain(s, IsBf16m<T>::v ? chain_bars : nullptr);
+      for (int li = 0; li < 4; ++li) {
+        const int oc = fc[li + 1];
+        TRYM(basic_block(blk[li][0], cur, ch, cw, cc, tB, oc, s));
+        ch /= blk[li][0].stride; cw /= blk[li][0].stride; cc = oc;
+        TRYM(basic_block(blk[li][1], tB, ch, cw, cc, f[li + 1], oc, s));
+        cur = f[li + 1];
+      }
+      TRYM(chain.end());
     }
     // ---------------- decoder (depth_decoder.py:50-65) ----------------
     const int dec[5] = {16, 32, 64, 128, 256};

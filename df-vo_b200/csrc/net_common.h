@@ -63,4 +63,12 @@ int run_conv_f32out(const ConvLayer& L, Ten<const T> in, Ten<float> out, int act
 
 const HostTensor* find_weight(const WeightStore& ws, const std::string& key);
 
+// RAII scope of a layer chain (ops.h::conv_chain_begin): the run_conv calls inside are issued as one launch at end() / scope exit.
+struct ChainScope {
+  bool open;
+  ChainScope(cudaStream_t s, unsigned* bar) : open(bar != nullptr) { if (open) conv_chain_begin(s, bar); }
+  int end() { if (!open) return DFVO_OK; open = false; return conv_chain_end(); }
+  ~ChainScope() { if (open) conv_chain_end(); }
+};
+
 }  // namespace dfvo

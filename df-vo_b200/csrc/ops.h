@@ -110,6 +110,14 @@ struct ConvTc {
 void conv_tc_profile_enable(int on);
 void conv_tc_profile_read(double* ms, long long* launches, double* flops);
 int conv_tc(const ConvTc& c, cudaStream_t s);
+// Layer chains (conv_chain.cu): between begin and end, consecutive eligible conv_tc() calls on stream s are collected and issued
+// as ONE persistent cooperative launch with grid-wide barriers between the layers.  ONLY conv_tc() calls may be made inside the
+// scope (collected layers run at conv_chain_end).  `bar`: CHAIN_BAR_WORDS zero-initialised device words owned by the caller, one
+// block per chain site (launches that can be in flight together must not share it).  No-op in the CPU test build.
+#define CHAIN_BAR_WORDS 16
+void conv_chain_begin(cudaStream_t s, unsigned* bar);
+int conv_chain_end();
+bool conv_chain_take(const ConvTc& c, cudaStream_t s, int* rc);
 // tile shape chooser shared with tests
 void conv_tc_tile_shape(int H, int W, int* tw, int* th);
 

@@ -210,6 +210,51 @@ __global__ void k_replay(const int32_t* __restrict__ ncand, const int32_t* __res
   st[r] = s;
 }
 
+// Warp version of k_replay (one warp per repeat): the acceptance rule is sequential only through the running best, so each lane
+// loads one iteration's candidate counts (max and its first index) -- 32 iterations per round trip to memory instead of one --
+// and the warp then applies, in iteration order, only the iterations that beat the running best (a handful).  Same state
+// transitions as k_replay: within an iteration the first candidate with the largest count wins, and niters after several
+// improvements equals RANSACUpdateNumIters of the last one (it only ever shrinks with the inlier ratio).
+__global__ void __launch_bounds__(32)
+k_replay_warp(const int32_t* __restrict__ ncand, const int32_t* __restrict__ counts, int N, int i1, double prob, EssState* st, int max_iters) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  EssState s = st[r];
+  if (s.done) return;
+  int it = s.it;
+  while (it < s.niters && it < i1) {
+    const int mine = it + lane;
+    int m = -1, mk = -1;
+    if (mine < i1) {
+      const size_t h = (size_t)r * max_iters + mine;
+      const int nc = ncand[h];
+      for (int k = 0; k < nc; ++k) { const int g = counts[h * 10 + k]; if (g > m) { m = g; mk = k; } }
+    }
+    int from = 0;                                             // lanes below `from` are settled
+    while (true) {
+      const int lim = s.best_good > 4 ? s.best_good : 4;
+      const int upto = (s.niters < i1 ? s.niters : i1) - it;   // iterations of this batch that OpenCV would still run
+      const unsigned cand = __ballot_sync(0xffffffffu, lane >= from && lane < upto && m > lim);
+      if (!cand) break;
+      const int j = __ffs(cand) - 1;
+      const int good = __shfl_sync(0xffffffffu, m, j), k = __shfl_sync(0xffffffffu, mk, j);
+      // within the winning iteration candidates are visited in order: the first one that beats the running best may be an earlier,
+      // smaller one -- but every later strictly larger one replaces it, so the iteration ends on its maximum (first occurrence)
+      s.best_good = good; s.best_iter = it + j; s.best_cand = k;
+      s.niters = ransac_update_num_iters(prob, (double)(N - good) / (double)N, 5, s.niters);
+      from = j + 1;
+    }
+    const int upto = (s.niters < i1 ? s.niters : i1) - it;
+    it += upto < 32 ? (upto > 0 ? upto : 0) : 32;
+    if (upto <= 0) break;
+  }
+  if (lane == 0) {
+    s.it = it;
+    s.evaluated = i1;
+    if (it >= s.niters) s.done = 1;
+    st[r] = s;
+  }
+}
+
 // mask of the winner in ORIGINAL point order (E_tracker.py:278-285 un-permutes), GRIC-E (gric.py), counts.
 // out per repeat: E[9], info[4] = {inlier count, iterations, best_iter, best_cand}, gric
 __global__ void __launch_bounds__(256)
@@ -302,7 +347,7 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
       DFVO_LAUNCH(k_hypotheses, dim3(cdiv(i1 - i0, 32), R), dim3(32), 0, s, x1n, x2n, subsets, N, i0, i1, st, Ecand, ncand, max_iters);
     DFVO_LAUNCH(k_score_round, dim3(cdiv((i1 - i0) * 10 * 32, 256), R), dim3(256), 0, s, Ecand, ncand, x1n, x2n, N, i0, i1, thr2, st,
                 counts, max_iters);
-    DFVO_LAUNCH(k_replay, dim3(1), dim3(32), 0, s, ncand, counts, N, i1, prob, st, max_iters, R);
+    DFVO_LAUNCH(k_replay_warp, dim3(R), dim3(32), 0, s, ncand, counts, N, i1, prob, st, max_iters);
   }
   DFVO_LAUNCH(k_finalize, dim3(R), dim3(256), 0, s, Ecand, st, x1n, x2n, perm, p1, p2, N, thr2, fx, fy, cx, cy, max_iters, E_out,
               mask_out, info, gric);
