@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "net_common.cu", "flow_ops.cu", "conv_direct.cu", "conv_tc.cu", "conv_halo.cu", "conv_chain.cu", "liteflownet.cu", "select.cu", "ransac.cu", "pnp.cu", "homog.cu", "depth_ops.cu", "monodepth2.cu", "geometry.cu"]
+SOURCES = ["capi.cu", "net_common.cu", "flow_ops.cu", "conv_direct.cu", "conv_tc.cu", "conv_halo.cu", "conv_chain.cu", "liteflownet.cu", "select.cu", "ransac.cu", "pnp.cu", "homog.cu", "depth_ops.cu", "monodepth2.cu", "geometry.cu", "corr_mma.cu"]
 NO_FMA = {"ransac.cu", "pnp.cu", "homog.cu"}
 OUT = os.path.join(HERE, "libdfvo_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -114,7 +114,11 @@ static int stage_correlation(const float* first, const float* second, float* out
   if ((rc = convert_copy<float, T>(cten(Ac), TA, s))) return rc;
   if ((rc = convert_copy<float, T>(cten(Bc), TB, s))) return rc;
   Ten<T> TO = make_ten<T>(to, B, Ho, Wo, 64, 64);
-  if ((rc = correlation49<T>(cten(TA), cten(TB), 0, stride, leaky, TO, s))) return rc;
+  {
+    Ten<const float> noflow; memset(&noflow, 0, sizeof(noflow));
+    Ten<T> noscratch; memset(&noscratch, 0, sizeof(noscratch));
+    if ((rc = correlation49_warped<T>(cten(TA), cten(TB), 0, noflow, 0.f, stride, leaky, noscratch, TO, s))) return rc;
+  }
   Ten<T> TO49 = TO; TO49.C = 49;
   if ((rc = nhwc_to_nchw<T>(cten(TO49), out, s))) return rc;
   DFVO_CUDA(cudaStreamSynchronize(s));
@@ -285,7 +289,9 @@ int dfvo_correlation_nhwc_bf16(const void* first, const void* second, void* out,
   Ten<bf16> A = make_ten<bf16>((bf16*)const_cast<void*>(first), B, H, W, C, Cpitch);
   Ten<bf16> Bn = make_ten<bf16>((bf16*)const_cast<void*>(second), B, H, W, C, Cpitch);
   Ten<bf16> O = make_ten<bf16>((bf16*)out, B, Ho, Wo, 64, 64);
-  return correlation49<bf16>(cten(A), cten(Bn), second_nxor, stride, leaky, O, (cudaStream_t)stream);
+  Ten<const float> noflow; memset(&noflow, 0, sizeof(noflow));
+  Ten<bf16> noscratch; memset(&noscratch, 0, sizeof(noscratch));
+  return correlation49_warped<bf16>(cten(A), cten(Bn), second_nxor, noflow, 0.f, stride, leaky, noscratch, O, (cudaStream_t)stream);
   API_END
 }
 

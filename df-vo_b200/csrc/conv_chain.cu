@@ -342,6 +342,11 @@ static bool chain_rect(const ConvTc& c, int* kh, int* kw, int* dy0, int* dx0) {
 
 bool conv_chain_eligible(const ConvTc& c) {
   if (c.stride == 2 || c.esize == 4 || c.nsrc < 1 || c.nsrc > 3) return false;
+  // DFVO_CHAIN_MAX_PIXELS: only layers up to this many output pixels join chains (a chain is a cooperative launch -- all its CTAs must be
+  // resident at once -- which costs concurrency with the other streams of the frame pipeline; the big levels gain little from chaining)
+  static long long max_px = -1;
+  if (max_px < 0) max_px = chain_env("DFVO_CHAIN_MAX_PIXELS", 1 << 30);
+  if ((long long)c.N * c.H * c.W > max_px) return false;
   int kh, kw, dy0, dx0;
   if (!chain_rect(c, &kh, &kw, &dy0, &dx0)) return false;
   for (int i = 0; i < c.nsrc; ++i)

@@ -301,10 +301,9 @@ struct LfnImpl : public LiteFlowNetBase {
     if (flow_prev) {
       Ten<const float> fp = cfview(flow_prev, L + 1, 2, 2);
       TRY(deconv4x4s2_dw<float>(fp, v.upflow, fview(flow_up, L, 2, 2), s));
-      TRY(warp_bilinear<T>(f1m, cfview(flow_up, L, 2, 2), dbl, 1, view(warpbuf, L, C, C), s));
-      TRY(correlation49<T>(f1m, cview(warpbuf, L, C, C), 0, cs, 1, corr_o, s));
+      TRY(correlation49_warped<T>(f1m, f1m, 1, cfview(flow_up, L, 2, 2), dbl, cs, 1, view(warpbuf, L, C, C), corr_o, s));
     } else {
-      TRY(correlation49<T>(f1m, f1m, 1, cs, 1, corr_o, s));
+      TRY(correlation49_warped<T>(f1m, f1m, 1, fnone, 0.f, cs, 1, view(warpbuf, L, C, C), corr_o, s));
     }
     Ten<const T> cin;
     if (L < 4) {

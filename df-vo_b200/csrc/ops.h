@@ -30,6 +30,12 @@ int warp_bilinear(Ten<const T> in, Ten<const float> flow, float scale, int in_nx
 // 49-channel correlation + fused LeakyReLU(0.1) (correlation.py:38-106, lite_flow_net.py:145-149)
 template <typename T>
 int correlation49(Ten<const T> f1, Ten<const T> f2, int f2_nxor, int stride, int leaky, Ten<T> out, cudaStream_t s);
+// Backward warp + correlation + LeakyReLU of a Matching unit in one call (corr_mma.cu): second operand = feat2[n ^ feat2_nxor]
+// warped by flow * scale (flow.p == nullptr: no warp).  bf16 on the device: one tensor-core kernel (mma.sync banded GEMM, warp
+// fused into the operand staging); otherwise warp_bilinear into warp_scratch + correlation49.
+template <typename T>
+int correlation49_warped(Ten<const T> first, Ten<const T> feat2, int feat2_nxor, Ten<const float> flow, float scale, int stride, int leaky,
+                         Ten<T> warp_scratch, Ten<T> out, cudaStream_t s);
 // per-(n,c) spatial mean of a 2-channel float field (lite_flow_net.py:257) -> mean[n*2+c].  `mean` must have
 // room for flow_mean_buffer_floats(N) floats (the means followed by the per-block partial sums).
 int flow_mean(Ten<const float> flow, float* mean, cudaStream_t s);
