@@ -29,6 +29,7 @@ SIGNATURES = {
     "dfvo_version": (c_char_p, []),
     "dfvo_is_device_build": (c_int, []),
     "dfvo_launch_count": (ctypes.c_longlong, []),
+    "dfvo_set_conv_chain": (c_int, [c_int]),
     "dfvo_profile_enable": (None, [c_int]),
     "dfvo_profile_read": (None, [ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_double)]),
     "dfvo_create": (c_int, [ctypes.POINTER(c_void_p), c_int]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "dfvo_rigid_flow": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfvo_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "dfvo_fb_consistency": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dfvo_fb_consistency_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dfvo_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
     "dfvo_local_bestn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -184,6 +184,7 @@ int dfvo_is_device_build(void) {
 }
 
 long long dfvo_launch_count(void) { return dfvo::g_launch_count.load(); }
+int dfvo_set_conv_chain(int on) { return dfvo::conv_chain_set_enabled(on); }
 void dfvo_profile_enable(int on) { dfvo::conv_tc_profile_enable(on); }
 void dfvo_profile_read(double* tc_ms, long long* tc_launches, double* tc_flops) { dfvo::conv_tc_profile_read(tc_ms, tc_launches, tc_flops); }
 
@@ -307,6 +308,13 @@ int dfvo_fb_consistency(const float* flow_fwd, const float* flow_bwd, float* dif
   API_BEGIN
   DFVO_REQUIRE(flow_fwd && flow_bwd && diff && H > 1 && W > 1, DFVO_EINVAL, "dfvo_fb_consistency args");
   return fb_consistency(flow_fwd, flow_bwd, H, W, diff, (cudaStream_t)stream);
+  API_END
+}
+
+int dfvo_fb_consistency_batch(const float* flow_fwd, const float* flow_bwd, float* diff, int n_pairs, int H, int W, void* stream) {
+  API_BEGIN
+  DFVO_REQUIRE(flow_fwd && flow_bwd && diff && n_pairs > 0 && n_pairs <= 65535 && H > 1 && W > 1, DFVO_EINVAL, "dfvo_fb_consistency_batch args");
+  return fb_consistency(flow_fwd, flow_bwd, H, W, diff, (cudaStream_t)stream, n_pairs, (long long)2 * H * W);
   API_END
 }
 

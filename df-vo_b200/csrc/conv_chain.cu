@@ -493,11 +493,12 @@ int conv_chain_launch(const std::vector<ConvTc>& layers, unsigned* bar, cudaStre
 struct ChainRec { bool open = false; cudaStream_t s = nullptr; unsigned* bar = nullptr; std::vector<ConvTc> layers; };
 static thread_local ChainRec g_rec;
 
+static int g_chain_on = -1;
 static int chain_enabled() {
-  static int on = -1;
-  if (on < 0) on = chain_env("DFVO_CONV_CHAIN", 1);
-  return on;
+  if (g_chain_on < 0) g_chain_on = chain_env("DFVO_CONV_CHAIN", 0);
+  return g_chain_on;
 }
+int conv_chain_set_enabled(int on) { const int prev = chain_enabled(); g_chain_on = on ? 1 : 0; return prev; }
 
 int conv_tc_single(const ConvTc& c, cudaStream_t s);
 
@@ -541,5 +542,6 @@ namespace dfvo {
 void conv_chain_begin(cudaStream_t, unsigned*) {}
 int conv_chain_end() { return DFVO_OK; }
 bool conv_chain_take(const ConvTc&, cudaStream_t, int* rc) { *rc = DFVO_OK; return false; }
+int conv_chain_set_enabled(int) { return 0; }
 }  // namespace dfvo
 #endif

@@ -882,11 +882,12 @@ int flow_upsample_final(Ten<const float> flow, float mul, int H, int W, float* o
 // Keeps the reference's normalise -> un-normalise arithmetic so coordinates round the same way.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_fb_consistency(const float* __restrict__ fwd, const float* __restrict__ bwd, int H, int W,
-                                 float* __restrict__ diff) {
+                                 float* __restrict__ diff, long long pair_stride) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y;
   if (x >= W) return;
   size_t hw = (size_t)H * W, i = (size_t)y * W + x;
+  fwd += blockIdx.z * pair_stride; bwd += blockIdx.z * pair_stride; diff += blockIdx.z * hw;
   float fx = fwd[i], fy = fwd[hw + i];
   float gx = (((float)x + fx) / (float)(W - 1) - 0.5f) * 2.f;
   float gy = (((float)y + fy) / (float)(H - 1) - 0.5f) * 2.f;
@@ -902,9 +903,10 @@ __global__ void k_fb_consistency(const float* __restrict__ fwd, const float* __r
   diff[i] = sqrtf(dx * dx + dy * dy);
 }
 
-int fb_consistency(const float* fwd, const float* bwd, int H, int W, float* diff, cudaStream_t s) {
-  dim3 block(128), grid(cdiv(W, 128), H);
-  DFVO_LAUNCH(k_fb_consistency, grid, block, 0, s, fwd, bwd, H, W, diff);
+// n pairs in one launch: pair p reads fwd + p * pair_stride, bwd + p * pair_stride ([2,H,W] planes each), writes diff + p * H * W
+int fb_consistency(const float* fwd, const float* bwd, int H, int W, float* diff, cudaStream_t s, int n, long long pair_stride) {
+  dim3 block(128), grid(cdiv(W, 128), H, n);
+  DFVO_LAUNCH(k_fb_consistency, grid, block, 0, s, fwd, bwd, H, W, diff, pair_stride);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }

@@ -386,10 +386,11 @@ struct LfnImpl : public LiteFlowNetBase {
   // the only launches that write caller memory: consistency map + copies of the two flows
   int emit(float* flow_fwd, float* flow_bwd, float* flow_diff, cudaStream_t s) override {
     const size_t plane2 = (size_t)2 * H0 * W0;
+    // all pairs in one launch: pair p's forward / backward flows sit at out_planar + (2p, 2p + 1) * plane2
+    if (flow_diff) TRY(fb_consistency(out_planar, out_planar + plane2, H0, W0, flow_diff, s, P, (long long)(2 * plane2)));
     for (int p = 0; p < P; ++p) {
       const float* f = out_planar + (size_t)(2 * p) * plane2;
       const float* b = out_planar + (size_t)(2 * p + 1) * plane2;
-      if (flow_diff) TRY(fb_consistency(f, b, H0, W0, flow_diff + (size_t)p * H0 * W0, s));
       if (flow_fwd) DFVO_CUDA(cudaMemcpyAsync(flow_fwd + p * plane2, f, plane2 * 4, cudaMemcpyDeviceToDevice, s));
       if (flow_bwd) DFVO_CUDA(cudaMemcpyAsync(flow_bwd + p * plane2, b, plane2 * 4, cudaMemcpyDeviceToDevice, s));
     }

@@ -54,7 +54,7 @@ int reg_tail(Ten<const T> dist, Ten<const float> flow, int k, const float* wx, c
 // (lite_flow_net.py:322-324, deep_flow.py:107-129)
 int flow_upsample_final(Ten<const float> flow, float mul, int H, int W, float* out_planar, cudaStream_t s);
 // forward-backward consistency (layers.py:213-229, deep_flow.py:171-196); planar [2][H][W] inputs
-int fb_consistency(const float* flow_fwd, const float* flow_bwd, int H, int W, float* diff, cudaStream_t s);
+int fb_consistency(const float* flow_fwd, const float* flow_bwd, int H, int W, float* diff, cudaStream_t s, int n = 1, long long pair_stride = 0);
 // converts / layout helpers (used by stage-level parity entry points)
 template <typename TI, typename TO>
 int convert_copy(Ten<const TI> in, Ten<TO> out, cudaStream_t s);          // NHWC -> NHWC (C=min)
@@ -124,6 +124,7 @@ int conv_tc(const ConvTc& c, cudaStream_t s);
 void conv_chain_begin(cudaStream_t s, unsigned* bar);
 int conv_chain_end();
 bool conv_chain_take(const ConvTc& c, cudaStream_t s, int* rc);
+int conv_chain_set_enabled(int on);      // returns the previous setting; applies to chain scopes opened afterwards
 // tile shape chooser shared with tests
 void conv_tc_tile_shape(int H, int W, int* tw, int* th);
 

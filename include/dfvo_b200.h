@@ -57,6 +57,10 @@ int dfvo_is_device_build(void);
 long long dfvo_launch_count(void);
 void dfvo_profile_enable(int on);
 void dfvo_profile_read(double* tc_ms, long long* tc_launches, double* tc_flops);
+/* Layer chains (csrc/conv_chain.cu): consecutive stride-1 convolutions of a network unit as ONE cooperative launch.  Off by default
+ * (measured: fewer launches and a shorter single-stream conv time, but less overlap between the frame pipeline's streams, DESIGN.md
+ * 4.4); env DFVO_CONV_CHAIN=1 or this call turn it on for networks created afterwards.  Returns the previous setting. */
+int dfvo_set_conv_chain(int on);
 
 int dfvo_create(dfvo_ctx** out, int device);
 int dfvo_destroy(dfvo_ctx* ctx);
@@ -121,6 +125,9 @@ int dfvo_backward_warp(const float* input, const float* flow, float* out, int B,
  * flow_fwd / flow_bwd [2,H,W] -> diff [H,W] */
 int dfvo_fb_consistency(const float* flow_fwd, const float* flow_bwd, float* diff, int H, int W,
                         void* stream);
+/* the same over a batch (deep_flow.py:171-196 takes [N,2,H,W]): flow_fwd / flow_bwd [n_pairs,2,H,W] -> diff [n_pairs,H,W], one launch */
+int dfvo_fb_consistency_batch(const float* flow_fwd, const float* flow_bwd, float* diff, int n_pairs, int H, int W,
+                              void* stream);
 /* torch.nn.Conv2d (+ activation): x [B,Cin,H,W], w_host [Cout,Cin,kh,kw], bias_host [Cout] or NULL
  * -> y [B,Cout,Ho,Wo].  precision DFVO_PREC_BF16 / DFVO_PREC_TF32 run the tcgen05 kernels (kind::f16 on bf16 operands /
  * kind::tf32 on fp32 operands; stride 1, or stride 2 on even sizes with 'same' padding). */

@@ -105,3 +105,26 @@ def test_pair_batch_runner_matches_single_pairs(dev_lib):
     for p in range(3):
         assert np.array_equal(one.forward(imgs[2 * p:2 * p + 2])[0], all3[p]), p
     assert all3.shape == (3, 2) and (all3[:, 0] > 0).all()
+
+
+def test_layer_chains_bit_equal_to_per_layer_launches(dev_lib):
+    """csrc/conv_chain.cu (opt-in, dfvo_set_conv_chain / DFVO_CONV_CHAIN=1): the chained launch walks the same K order per output
+    element as the per-layer kernels, so both flows and the consistency map must be bit-identical, at the BASELINE size (all five
+    levels, chains of 3..9 layers) and at a small ragged size."""
+    w = synth.liteflownet_weights()
+    prev = dev_lib.dfvo_set_conv_chain(0)
+    try:
+        for H, W, seed in [(376, 1241, 21), (70, 150, 23)]:
+            ref, cur = synth.value_noise_image(H, W, seed), synth.value_noise_image(H, W, seed + 1)
+            dev_lib.dfvo_set_conv_chain(0)
+            n0 = dev_lib.dfvo_launch_count()
+            a = run_device(dev_lib, H, W, ref, cur, native.PREC_BF16, w)
+            n1 = dev_lib.dfvo_launch_count()
+            dev_lib.dfvo_set_conv_chain(1)
+            b = run_device(dev_lib, H, W, ref, cur, native.PREC_BF16, w)
+            n2 = dev_lib.dfvo_launch_count()
+            assert (n2 - n1) < (n1 - n0) - 30, (n1 - n0, n2 - n1)          # the chains really replaced launches
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+    finally:
+        dev_lib.dfvo_set_conv_chain(prev)

@@ -118,6 +118,16 @@ def test_fb_consistency(dev_lib):
     # mask agreement at the reference threshold (kp_selection.thre = 0.1) is reported, not asserted bit-exact
     flips = ((got < 0.1) != (ref < 0.1)).mean()
     assert flips < 1e-4
+    # batched entry: three pairs in one launch == the single-pair call on each
+    f3 = np.concatenate([fwd, fwd[:, :, ::-1].copy(), fwd * 0.5]).astype(np.float32)
+    b3 = np.concatenate([bwd, bwd[:, :, ::-1].copy(), bwd * 0.5]).astype(np.float32)
+    df3, db3 = cu(f3), cu(b3)
+    out3 = torch.zeros((3, H, W), dtype=torch.float32, device="cuda")
+    dev_lib.check(dev_lib.dfvo_fb_consistency_batch(dptr(df3), dptr(db3), dptr(out3), 3, H, W, None))
+    for p in range(3):
+        one = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+        dev_lib.check(dev_lib.dfvo_fb_consistency(dptr(df3[p]), dptr(db3[p]), dptr(one), H, W, None))
+        assert torch.equal(one, out3[p])
 
 
 CONV_CASES = [

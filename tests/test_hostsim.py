@@ -42,6 +42,10 @@ def test_warp_and_fb(hostsim_lib):
     d = np.zeros(fwd.shape[1:], np.float32)
     hostsim_lib.check(hostsim_lib.dfvo_fb_consistency(hptr(fwd), hptr(bwd), hptr(d), fwd.shape[1], fwd.shape[2], None))
     assert np.abs(d - g["fb_diff"][0, :, :, 0]).max() < 2e-5      # vs DeepFlow.forward_backward_consistency
+    f2, b2 = np.ascontiguousarray(np.stack([fwd, bwd])), np.ascontiguousarray(np.stack([bwd, fwd]))
+    d2 = np.zeros((2,) + fwd.shape[1:], np.float32)
+    hostsim_lib.check(hostsim_lib.dfvo_fb_consistency_batch(hptr(f2), hptr(b2), hptr(d2), 2, fwd.shape[1], fwd.shape[2], None))
+    assert np.array_equal(d2[0], d)
 
 
 @pytest.mark.parametrize("case", [(1, 3, 12, 20, 8, 7, 7, 1, 3, 3, 0, 1, 0), (1, 16, 9, 14, 24, 3, 3, 2, 1, 1, 0, 2, 0),
