@@ -41,6 +41,124 @@ __device__ __forceinline__ void cm_mma(float* c, uint32_t a0, uint32_t a1, uint3
 // byte offset of 16-byte chunk `ch` of pixel `px` in a [pixels][pitch] tile (pitch a multiple of 128 B)
 __device__ __forceinline__ uint32_t cm_off(int px, int ch, int pitch) { return (uint32_t)px * (uint32_t)pitch + (uint32_t)(((ch & ~7) | ((ch ^ px) & 7)) << 4); }
 
+// Single-slice variant (C <= 64): displacement rows outermost, 12 accumulators live -> 48 registers, three blocks per SM.
+__global__ void __launch_bounds__(CM_THREADS)
+k_corr_mma1(Ten<const bf16> f1, Ten<const bf16> f2, int f2_nxor, const float* __restrict__ flow, long long fN, long long fH, long long fW,
+           float scale, int stride, int leaky, Ten<bf16> out, int pitch) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_f1 = smem;                                              // [128 px][pitch]
+  uint8_t* s_p = s_f1 + (size_t)CM_TW * CM_TH * pitch;               // [14 * 24 px][pitch]
+  uint8_t* s_out = s_p + (size_t)CM_PH * CM_PW * pitch;              // [128 px][128 B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * CM_TW, y0 = blockIdx.y * CM_TH, n = blockIdx.z;
+  const int C = f1.C, nch = C >> 3;                                  // 16-byte chunks per pixel
+  // ---- stage the first map's tile (pixels sampled with the stride)
+  for (int i = tid; i < CM_TW * CM_TH * nch; i += CM_THREADS) {
+    const int m = i / nch, ch = i - m * nch;
+    const int ox = x0 + (m & 15), oy = y0 + (m >> 4);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ox < out.W && oy < out.H) v = *reinterpret_cast<const uint4*>(f1.at(n, oy * stride, ox * stride) + ch * 8);
+    *reinterpret_cast<uint4*>(s_f1 + cm_off(m, ch, pitch)) = v;
+  }
+  // ---- stage the second map's patch: plain copy, or the Backward warp evaluated here
+  const int n2 = n ^ f2_nxor;
+  for (int i = tid; i < CM_PH * CM_PW * nch; i += CM_THREADS) {
+    const int q = i / nch, ch = i - q * nch;
+    const int pj = q / CM_PW, pi = q - pj * CM_PW;
+    const int sx = (x0 + pi - 3) * stride, sy = (y0 + pj - 3) * stride;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pi < CM_TW + 6 && sx >= 0 && sx < f2.W && sy >= 0 && sy < f2.H) {
+      if (flow == nullptr) {
+        v = *reinterpret_cast<const uint4*>(f2.at(n2, sy, sx) + ch * 8);
+      } else {
+        // Backward (lite_flow_net.py:10-28): bilinear sample at (x, y) + flow * scale, zeros outside; same arithmetic as
+        // flow_ops.cu::k_warp_bilinear_vec (fp32 blend, round to bf16)
+        const float* fl = flow + n * fN + (long long)sy * fH + (long long)sx * fW;
+        const float px = (float)sx + fl[0] * scale, py = (float)sy + fl[1] * scale;
+        const float fx0 = floorf(px), fy0 = floorf(py);
+        const int ix = (int)fx0, iy = (int)fy0;
+        const float wx1 = px - fx0, wy1 = py - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        const bool fin = (px == px) && (py == py) && fabsf(px) < 1e9f && fabsf(py) < 1e9f;      // non-finite coordinates sample nothing
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xx = ix + (k & 1), yy = iy + (k >> 1);
+          const float wgt = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
+          if (!fin || xx < 0 || xx > f2.W - 1 || yy < 0 || yy > f2.H - 1 || wgt == 0.f) continue;
+          const uint4 t = *reinterpret_cast<const uint4*>(f2.at(n2, yy, xx) + ch * 8);
+          const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __uint_as_float(w4[j] << 16) * wgt;
+            acc[2 * j + 1] += __uint_as_float(w4[j] & 0xffff0000u) * wgt;
+          }
+        }
+        uint32_t o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+          o4[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        v = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+    *reinterpret_cast<uint4*>(s_p + cm_off(q, ch, pitch)) = v;
+  }
+  // zero the pad channels 49..63 of the output staging once
+  for (int i = tid; i < CM_TW * CM_TH * 2; i += CM_THREADS) {
+    // channels 48..63 of pixel i/2 = chunks 6, 7; channel 48 is rewritten below
+    *reinterpret_cast<uint4*>(s_out + (size_t)(i >> 1) * 128 + 96 + (i & 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  // ---- banded GEMMs: warp w = output row w of the tile
+  const uint32_t f1_base = cm_smem(s_f1), p_base = cm_smem(s_p);
+  const float inv = 1.f / (float)C;
+  const int arow = warp * CM_TW + (lane & 7) + ((lane >> 3) & 1) * 8;          // A: pixel of this lane's ldmatrix row
+  const int akc = lane >> 4;                                                  //    k-chunk within the k16 step
+  const int brow4 = (lane & 7) + ((lane >> 4) & 1) * 8, bkc = (lane >> 3) & 1; // B x4: two n8 tiles;  B x2 uses lanes 0..15
+  const int g = lane >> 2, tq = lane & 3;
+  __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(s_out);
+#pragma unroll 1
+  for (int dy = 0; dy < 7; ++dy) {
+    float acc[3][4];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    const int prow = (warp + dy) * CM_PW;                                       // patch row of this output row and displacement
+    for (int ks = 0; ks < (C >> 4); ++ks) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3, b4, b5;
+      cm_ldsm4(f1_base + cm_off(arow, 2 * ks + akc, pitch), a0, a1, a2, a3);
+      cm_ldsm4(p_base + cm_off(prow + brow4, 2 * ks + bkc, pitch), b0, b1, b2, b3);       // columns 0..15
+      cm_ldsm2(p_base + cm_off(prow + 16 + (lane & 7), 2 * ks + bkc, pitch), b4, b5);      // columns 16..23
+      cm_mma(acc[0], a0, a1, a2, a3, b0, b1);
+      cm_mma(acc[1], a0, a1, a2, a3, b2, b3);
+      cm_mma(acc[2], a0, a1, a2, a3, b4, b5);
+    }
+    // band extraction: accumulator e of tile t sits at (row, col) = (g + 8 * (e >> 1), 8 * t + 2 * tq + (e & 1)); dx = col - row
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = g + 8 * (e >> 1), col = 8 * t + 2 * tq + (e & 1);
+        const int dx = col - row;
+        if (dx >= 0 && dx < 7) {
+          float v = acc[t][e] * inv;
+          if (leaky) v = v > 0.f ? v : 0.1f * v;
+          so[(warp * CM_TW + row) * 64 + dy * 7 + dx] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- write the tile: 128 pixels x 128 bytes
+  for (int i = tid; i < CM_TW * CM_TH * 8; i += CM_THREADS) {
+    const int m = i >> 3, ch = i & 7;
+    const int ox = x0 + (m & 15), oy = y0 + (m >> 4);
+    if (ox < out.W && oy < out.H) *reinterpret_cast<uint4*>(out.at(n, oy, ox) + ch * 8) = *reinterpret_cast<const uint4*>(s_out + (size_t)m * 128 + ch * 16);
+  }
+}
+
 __global__ void __launch_bounds__(CM_THREADS, 2)
 k_corr_mma(Ten<const bf16> f1, Ten<const bf16> f2, int f2_nxor, const float* __restrict__ flow, long long fN, long long fH, long long fW,
            float scale, int stride, int leaky, Ten<bf16> out) {
@@ -212,10 +330,17 @@ int correlation49_warped<bf16>(Ten<const bf16> first, Ten<const bf16> feat2, int
   }
   const size_t smem = (size_t)(CM_TW * CM_TH + CM_PH * CM_PW) * 128 + (size_t)CM_TW * CM_TH * 128;
   static bool attr_set = false;
-  if (!attr_set) { DFVO_CUDA(cudaFuncSetAttribute(k_corr_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  if (!attr_set) {
+    DFVO_CUDA(cudaFuncSetAttribute(k_corr_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DFVO_CUDA(cudaFuncSetAttribute(k_corr_mma1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
   dim3 grid(cdiv(out.W, CM_TW), cdiv(out.H, CM_TH), out.N);
   ++g_launch_count;
-  k_corr_mma<<<grid, CM_THREADS, smem, s>>>(first, feat2, feat2_nxor, has_flow ? flow.p : nullptr, flow.sN, flow.sH, flow.sW, scale, stride, leaky, out);
+  if (first.C <= 64)
+    k_corr_mma1<<<grid, CM_THREADS, smem, s>>>(first, feat2, feat2_nxor, has_flow ? flow.p : nullptr, flow.sN, flow.sH, flow.sW, scale, stride, leaky, out, 128);
+  else
+    k_corr_mma<<<grid, CM_THREADS, smem, s>>>(first, feat2, feat2_nxor, has_flow ? flow.p : nullptr, flow.sN, flow.sH, flow.sW, scale, stride, leaky, out);
   DFVO_CHECK_LAUNCH();
   return DFVO_OK;
 }
