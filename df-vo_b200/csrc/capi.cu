@@ -555,4 +555,11 @@ int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* 
   API_END
 }
 
+int dfvo_epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop, double* rt,
+                      int32_t* ok, void* stream) {
+  API_BEGIN
+  return epnp_minimal(obj, img, M, fx, fy, cx, cy, coop, rt, ok, (cudaStream_t)stream);
+  API_END
+}
+
 }  // extern "C"

@@ -10,6 +10,7 @@
 // "nearest-upsample + concat skip + reflect-pad" kernel, so the convs are plain valid convs and run on
 // the tcgen05 kernel (T = bf16) or the CUDA-core kernel (T = float, parity mode; stride-2 / 3-channel /
 // 1-channel layers in both modes).
+#include <stdlib.h>
 #include "monodepth2.h"
 
 #include <math.h>
@@ -27,6 +28,9 @@ struct MonoImpl : public Monodepth2Base {
   int h = 0, w = 0;
   float min_depth = 0.1f, max_depth = 100.f, baseline = 5.4f;
   ConvLayer conv1;
+  ConvLayer conv1_tc;          // bf16: the 7x7 stride-2 stem on the tensor cores (see stem_tc_layer)
+  bool stem_tc = false;
+  T* imgpad = nullptr;        // [h][w+8][8] column-padded normalised image (zero borders / pad channels)
   struct Block { ConvLayer c1, c2, down; bool has_down = false; int stride = 1; } blk[4][2];
   ConvLayer up[10], disp0;
   // buffers
@@ -63,6 +67,42 @@ struct MonoImpl : public Monodepth2Base {
     return build_conv_layer(arena, *wgt, nullptr, {{cin, cp}}, stride, pad, pad, 0, want_tc, !want_tc || !IsBf16m<T>::v, scale.data(), shift.data(), L,
                             IsBf16m<T>::v ? 2 : 4);
   }
+  // The stem (resnet_encoder.py:87-98: conv1 7x7 s2 p3 + bn1 + relu) as a stride-1 tensor-core convolution:
+  //   * columns: output pixel x needs input columns 2x-3 .. 2x+3 = padded columns 2x .. 2x+6: a 64-element window (8 pixels x 8
+  //     channels, the 8th pixel and channels 3..7 carry zero weights) starting at padded column 2x -- an overlapping-box view
+  //     with a pixel stride of 2 padded pixels (32 B), exactly LiteFlowNet's window stem with a doubled stride;
+  //   * rows: output row y needs input rows 2y-3 .. 2y+3.  Split the rows by parity (two views E, O of the same buffer with a row
+  //     stride of two image rows): rows 2y+{-2,0,2} = E[y-1], E[y], E[y+1] (ky = 1, 3, 5) and rows 2y+{-3,-1,1,3} = O[y-2 .. y+1]
+  //     (ky = 0, 2, 4, 6) -- a 4 x 1 window (dy = -2 .. 1) over the two sources, E's dy = -2 tap carrying zero weights.
+  // 8 K-steps x 4 taps of N = 64 MMAs per 128 outputs instead of 147 x 64 scalar FMAs per output; zero padding by TMA out-of-bounds
+  // fill (rows) and the zero borders of the padded image (columns).
+  int stem_tc_layer(const WeightStore& ws) {
+    const HostTensor* wgt = find_weight(ws, "encoder.conv1.weight");
+    const HostTensor* g = find_weight(ws, "encoder.bn1.weight");
+    const HostTensor* b = find_weight(ws, "encoder.bn1.bias");
+    const HostTensor* m = find_weight(ws, "encoder.bn1.running_mean");
+    const HostTensor* v = find_weight(ws, "encoder.bn1.running_var");
+    DFVO_REQUIRE(wgt && g && b && m && v && wgt->shape.size() == 4 && wgt->shape[0] == 64 && wgt->shape[1] == 3 && wgt->shape[2] == 7 && wgt->shape[3] == 7,
+                 DFVO_ESTATE, "encoder.conv1 / bn1 weights");
+    std::vector<float> scale(64), shift(64);
+    for (int c = 0; c < 64; ++c) {
+      scale[c] = g->data[c] / sqrtf(v->data[c] + 1e-5f);
+      shift[c] = b->data[c] - m->data[c] * scale[c];
+    }
+    HostTensor wr;
+    wr.shape = {64, 128, 4, 1};
+    wr.data.assign((size_t)64 * 128 * 4, 0.f);
+    for (int co = 0; co < 64; ++co)
+      for (int c = 0; c < 3; ++c)
+        for (int ky = 0; ky < 7; ++ky)
+          for (int dx = 0; dx < 7; ++dx) {
+            const int src = (ky & 1) ? 0 : 1;                         // odd ky -> even input rows (E), even ky -> odd rows (O)
+            const int kyy = (ky & 1) ? (ky + 1) / 2 : ky / 2;         // E: ky = 2 kyy - 1;  O: ky = 2 kyy
+            wr.data[((size_t)co * 128 + src * 64 + dx * 8 + c) * 4 + kyy] = wgt->data[(((size_t)co * 3 + c) * 7 + ky) * 7 + dx];
+          }
+    return build_conv_layer(arena, wr, nullptr, {{64, 64}, {64, 64}}, 1, 2, 0, 0, true, false, scale.data(), shift.data(), &conv1_tc, 2);
+  }
+
   int plain_conv(const WeightStore& ws, const std::string& name, int cin, bool tc_ok, ConvLayer* L) {
     const HostTensor* wgt = find_weight(ws, name + ".weight");
     const HostTensor* b = find_weight(ws, name + ".bias");
@@ -76,6 +116,11 @@ struct MonoImpl : public Monodepth2Base {
     h = feed_h; w = feed_w; min_depth = mind; max_depth = maxd; baseline = base;
     DFVO_REQUIRE(h % 32 == 0 && w % 32 == 0 && h >= 32 && w >= 32, DFVO_ESHAPE, "monodepth2 feed size must be a multiple of 32");
     TRYM(bn_conv(ws, "encoder.conv1", "encoder.bn1", 3, 2, 3, false, &conv1));
+    {
+      const char* e = getenv("DFVO_MONO_STEM_TC");
+      stem_tc = IsBf16m<T>::v && !(e && atoi(e) == 0);
+      if (stem_tc) TRYM(stem_tc_layer(ws));
+    }
     const int chans[4] = {64, 128, 256, 512};
     int cin = 64;
     for (int li = 0; li < 4; ++li) {
@@ -109,6 +154,7 @@ struct MonoImpl : public Monodepth2Base {
     for (int i = 1; i < 5; ++i) { fh[i] = h >> (i + 1); fw[i] = w >> (i + 1); fc[i] = enc[i]; }
 #define ALLOCM(ptr, type, count) do { ptr = arena.alloc_t<type>(count); if (!ptr) return DFVO_ENOMEM; } while (0)
     ALLOCM(x0, T, (size_t)h * w * 4);
+    ALLOCM(imgpad, T, stem_tc ? (size_t)h * (w + 8) * 8 + 64 : 64);
     for (int i = 0; i < 5; ++i) ALLOCM(f[i], T, (size_t)fh[i] * fw[i] * fc[i]);
     const size_t big = (size_t)fh[1] * fw[1] * 64;      // largest BasicBlock tensor (layer1)
     ALLOCM(pool, T, big); ALLOCM(tA, T, big); ALLOCM(tB, T, big); ALLOCM(tD, T, big);
@@ -146,8 +192,18 @@ struct MonoImpl : public Monodepth2Base {
 
   int run(const float* img, float* depth_out, cudaStream_t s) override {
     Ten<const T> none; memset(&none, 0, sizeof(none));
-    TRYM(normalize_nchw_to_nhwc<T>(img, 1, 3, h, w, 0.45f, 0.225f, tv(x0, h, w, 4, 4), s));
-    {
+    if (stem_tc) {
+      const long long row = (long long)(w + 8) * 8;
+      Ten<T> pv; pv.p = imgpad + 3 * 8; pv.N = 1; pv.H = h; pv.W = w; pv.C = 3; pv.sW = 8; pv.sH = row; pv.sN = (long long)h * row;
+      TRYM(normalize_nchw_to_nhwc<T>(img, 1, 3, h, w, 0.45f, 0.225f, pv, s));          // borders / pad channels stay zero
+      Ten<const T> eo[2];
+      for (int par = 0; par < 2; ++par) {
+        Ten<const T>& v = eo[par];
+        v.p = imgpad + par * row; v.N = 1; v.H = h / 2; v.W = w / 2; v.C = 64; v.sW = 16; v.sH = 2 * row; v.sN = (long long)h * row;
+      }
+      TRYM(run_conv_multi<T>(conv1_tc, eo, 2, tv(f[0], fh[0], fw[0], 64, 64), ACT_RELU, 2.0 * fh[0] * fw[0] * 64.0 * 147.0, s));
+    } else {
+      TRYM(normalize_nchw_to_nhwc<T>(img, 1, 3, h, w, 0.45f, 0.225f, tv(x0, h, w, 4, 4), s));
       ConvDirect d = {3, 64, 7, 7, 2, 3, 3, 0, ACT_RELU, conv1.w_direct, conv1.w_pitch, conv1.bias};
       TRYM((conv_direct<T, T>(d, ctv(x0, h, w, 3, 4), tv(f[0], fh[0], fw[0], 64, 64), none, s)));
     }

@@ -202,6 +202,29 @@ static int launch_tc(const ConvLayer& L, Ten<const T> in, Ten<TO> out, int act, 
   return conv_tc(c, s);
 }
 
+template <typename T>
+int run_conv_multi(const ConvLayer& L, const Ten<const T>* ins, int nin, Ten<T> out, int act, double flops, cudaStream_t s) {
+  DFVO_REQUIRE(L.tc && nin >= 1 && nin <= 3 && L.stride == 1 && (int)sizeof(T) == L.tc_esize, DFVO_ESTATE, "run_conv_multi: tensor-core stride-1 layers only");
+  ConvTc c;
+  memset(&c, 0, sizeof(c));
+  int ktot = 0;
+  for (int i = 0; i < nin; ++i) {
+    DFVO_REQUIRE(ins[i].N == ins[0].N && ins[i].H == ins[0].H && ins[i].W == ins[0].W, DFVO_ESHAPE, "run_conv_multi: source %d shape", i);
+    c.src[i].p = ins[i].p; c.src[i].C = ins[i].C; c.src[i].sN = ins[i].sN; c.src[i].sH = ins[i].sH; c.src[i].sW = ins[i].sW;
+    ktot += ins[i].C;
+  }
+  DFVO_REQUIRE(ktot == L.Ktot, DFVO_ESHAPE, "run_conv_multi: sources carry %d channels, layer expects %d", ktot, L.Ktot);
+  c.N = ins[0].N; c.H = out.H; c.W = out.W; c.inH = ins[0].H; c.inW = ins[0].W; c.stride = 1; c.nsrc = nin;
+  fill_taps(L, &c);
+  c.esize = L.tc_esize; c.round_out_tf32 = sizeof(T) == 4;
+  c.w = L.w_tc; c.Cout_pad = L.Cout_pad; c.Cout = L.Cout; c.bias = L.bias; c.act = act; c.out_f32 = 0;
+  c.out = out.p; c.oN = out.sN; c.oH = out.sH; c.oW = out.sW;
+  c.flops = flops > 0 ? flops : 2.0 * (double)c.N * out.H * out.W * (double)L.Cout * L.Cin_ref * L.kh * L.kw;
+  return conv_tc(c, s);
+}
+template int run_conv_multi<bf16>(const ConvLayer&, const Ten<const bf16>*, int, Ten<bf16>, int, double, cudaStream_t);
+template int run_conv_multi<float>(const ConvLayer&, const Ten<const float>*, int, Ten<float>, int, double, cudaStream_t);
+
 template <>
 int run_conv<float>(const ConvLayer& L, Ten<const float> in, Ten<float> out, int act, Ten<const float> residual,
                     int zero_pad_to, cudaStream_t s) {

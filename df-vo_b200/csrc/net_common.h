@@ -56,6 +56,11 @@ int build_conv_layer(Arena& arena, const HostTensor& w, const HostTensor* bias, 
 template <typename T>
 int run_conv(const ConvLayer& L, Ten<const T> in, Ten<T> out, int act, Ten<const T> residual, int zero_pad_to,
              cudaStream_t s);
+// the same over nin <= 3 virtual-concat sources (views of equal N, H, W; channels in the layer's segment order); the input views may
+// be smaller / larger than "same" padding implies (asymmetric windows): anything outside them reads as zero.  flops: algorithmic
+// FLOPs of the launch for the roofline report (0 = derive from the layer).  Tensor-core layers only.
+template <typename T>
+int run_conv_multi(const ConvLayer& L, const Ten<const T>* ins, int nin, Ten<T> out, int act, double flops, cudaStream_t s);
 // flow head: T input, float output (+ float residual)
 template <typename T>
 int run_conv_f32out(const ConvLayer& L, Ten<const T> in, Ten<float> out, int act, Ten<const float> residual,

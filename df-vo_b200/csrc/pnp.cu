@@ -14,6 +14,7 @@
 // formulation OpenCV ships (control points from the PCA of the object points, 12x12 M^T M null space, the three
 // beta approximations N = 1..3 + five Gauss-Newton steps each, absolute orientation by Horn/Arun, best reprojection
 // error wins).  All arithmetic FP64; one thread per minimal sample (the 12x12 Jacobi eigen-solve dominates).
+#include <stdlib.h>
 #include "ransac.h"
 #include "smallmat.cuh"
 
@@ -181,13 +182,11 @@ DFVO_HD void gauss_newton(const double L[6][10], const double rho[6], double b[4
   }
 }
 
-// EPnP on n <= 5 points.  pw: object points, uv: pixels.  Returns false for a degenerate configuration.
-DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu, double fv, double uc, double vc, double R[3][3],
-                   double t[3]) {
-  Ctx c;
+// ---- the stages of EPnP, shared by the one-thread driver (solve) and the lane-cooperative one (solve_coop) ----------------------
+// control points (centroid + principal directions scaled by sqrt(eigenvalue / n)) and barycentric coordinates
+DFVO_HD bool prepare(Ctx& c, int n, const double pw[][3], const double uv[][2], double fu, double fv, double uc, double vc) {
   c.n = n; c.fu = fu; c.fv = fv; c.uc = uc; c.vc = vc;
   for (int p = 0; p < n; ++p) { for (int k = 0; k < 3; ++k) c.pw[p][k] = pw[p][k]; c.uv[p][0] = uv[p][0]; c.uv[p][1] = uv[p][1]; }
-  // ---- control points: centroid + principal directions scaled by sqrt(eigenvalue / n)
   for (int k = 0; k < 3; ++k) { double s = 0; for (int p = 0; p < n; ++p) s += pw[p][k]; c.cws[0][k] = s / n; }
   {
     double C[3][3], W[3], Ut[3][3], Vt[3][3];
@@ -199,81 +198,99 @@ DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu,
       for (int j = 0; j < 3; ++j) c.cws[i][j] = c.cws[0][j] + k * Ut[i - 1][j];
     }
   }
-  // ---- barycentric coordinates
-  {
-    double cc[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 1; j < 4; ++j) cc[i][j - 1] = c.cws[j][i] - c.cws[0][i];
-    const double det = sm::det3(cc);
-    if (!(fabs(det) > 1e-300)) return false;
-    double ci[3][3];
-    ci[0][0] = (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) / det; ci[0][1] = (cc[0][2] * cc[2][1] - cc[0][1] * cc[2][2]) / det; ci[0][2] = (cc[0][1] * cc[1][2] - cc[0][2] * cc[1][1]) / det;
-    ci[1][0] = (cc[1][2] * cc[2][0] - cc[1][0] * cc[2][2]) / det; ci[1][1] = (cc[0][0] * cc[2][2] - cc[0][2] * cc[2][0]) / det; ci[1][2] = (cc[0][2] * cc[1][0] - cc[0][0] * cc[1][2]) / det;
-    ci[2][0] = (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]) / det; ci[2][1] = (cc[0][1] * cc[2][0] - cc[0][0] * cc[2][1]) / det; ci[2][2] = (cc[0][0] * cc[1][1] - cc[0][1] * cc[1][0]) / det;
-    for (int p = 0; p < n; ++p) {
-      double d[3] = {pw[p][0] - c.cws[0][0], pw[p][1] - c.cws[0][1], pw[p][2] - c.cws[0][2]};
-      for (int j = 0; j < 3; ++j) c.al[p][1 + j] = ci[j][0] * d[0] + ci[j][1] * d[1] + ci[j][2] * d[2];
-      c.al[p][0] = 1.0 - c.al[p][1] - c.al[p][2] - c.al[p][3];
-    }
+  double cc[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 1; j < 4; ++j) cc[i][j - 1] = c.cws[j][i] - c.cws[0][i];
+  const double det = sm::det3(cc);
+  if (!(fabs(det) > 1e-300)) return false;
+  double ci[3][3];
+  ci[0][0] = (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) / det; ci[0][1] = (cc[0][2] * cc[2][1] - cc[0][1] * cc[2][2]) / det; ci[0][2] = (cc[0][1] * cc[1][2] - cc[0][2] * cc[1][1]) / det;
+  ci[1][0] = (cc[1][2] * cc[2][0] - cc[1][0] * cc[2][2]) / det; ci[1][1] = (cc[0][0] * cc[2][2] - cc[0][2] * cc[2][0]) / det; ci[1][2] = (cc[0][2] * cc[1][0] - cc[0][0] * cc[1][2]) / det;
+  ci[2][0] = (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]) / det; ci[2][1] = (cc[0][1] * cc[2][0] - cc[0][0] * cc[2][1]) / det; ci[2][2] = (cc[0][0] * cc[1][1] - cc[0][1] * cc[1][0]) / det;
+  for (int p = 0; p < n; ++p) {
+    double d[3] = {pw[p][0] - c.cws[0][0], pw[p][1] - c.cws[0][1], pw[p][2] - c.cws[0][2]};
+    for (int j = 0; j < 3; ++j) c.al[p][1 + j] = ci[j][0] * d[0] + ci[j][1] * d[1] + ci[j][2] * d[2];
+    c.al[p][0] = 1.0 - c.al[p][1] - c.al[p][2] - c.al[p][3];
   }
+  return true;
+}
+
+// row i of M^T M (12 x 12), accumulated over the points in the same order as the full matrix
+DFVO_HD void mtm_row(const Ctx& c, int i, double row[12]) {
+  for (int j = 0; j < 12; ++j) row[j] = 0;
+  for (int p = 0; p < c.n; ++p) {
+    double m1[12], m2[12];
+    for (int j = 0; j < 4; ++j) {
+      m1[3 * j] = c.al[p][j] * c.fu; m1[3 * j + 1] = 0.0;                m1[3 * j + 2] = c.al[p][j] * (c.uc - c.uv[p][0]);
+      m2[3 * j] = 0.0;               m2[3 * j + 1] = c.al[p][j] * c.fv;  m2[3 * j + 2] = c.al[p][j] * (c.vc - c.uv[p][1]);
+    }
+    for (int j = 0; j < 12; ++j) row[j] += m1[i] * m1[j] + m2[i] * m2[j];
+  }
+}
+
+// L (6 x 10) and rho from the null-space vectors c.v
+DFVO_HD void build_L(const Ctx& c, double L[6][10], double rho[6]) {
+  const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+  double dv[4][6][3];
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 3; ++j) dv[k][i][j] = c.v[k][3 * pa[i] + j] - c.v[k][3 * pb[i] + j];
+  auto dot = [&](int a, int b, int i) { return dv[a][i][0] * dv[b][i][0] + dv[a][i][1] * dv[b][i][1] + dv[a][i][2] * dv[b][i][2]; };
+  for (int i = 0; i < 6; ++i) {
+    L[i][0] = dot(0, 0, i); L[i][1] = 2 * dot(0, 1, i); L[i][2] = dot(1, 1, i); L[i][3] = 2 * dot(0, 2, i); L[i][4] = 2 * dot(1, 2, i);
+    L[i][5] = dot(2, 2, i); L[i][6] = 2 * dot(0, 3, i); L[i][7] = 2 * dot(1, 3, i); L[i][8] = 2 * dot(2, 3, i); L[i][9] = dot(3, 3, i);
+    double s = 0;
+    for (int j = 0; j < 3; ++j) { const double d = c.cws[pa[i]][j] - c.cws[pb[i]][j]; s += d * d; }
+    rho[i] = s;
+  }
+}
+
+// the three beta approximations (N = 1, 2, 3); false when the start is not finite
+DFVO_HD bool initial_betas(int approx, const double L[6][10], const double rho[6], double b[4]) {
+  b[0] = b[1] = b[2] = b[3] = 0;
+  if (approx == 1) {                       // betas10 columns {B11, B12, B13, B14}
+    double A[6][4], x[4];
+    for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][3]; A[i][3] = L[i][6]; }
+    lstsq<6, 4>(A, rho, x);
+    if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = -x[1] / b[0]; b[2] = -x[2] / b[0]; b[3] = -x[3] / b[0]; }
+    else { b[0] = sqrt(x[0]); b[1] = x[1] / b[0]; b[2] = x[2] / b[0]; b[3] = x[3] / b[0]; }
+  } else if (approx == 2) {                // {B11, B12, B22}
+    double A[6][3], x[3];
+    for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][2]; }
+    lstsq<6, 3>(A, rho, x);
+    if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+    else { b[0] = sqrt(x[0]); b[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+    if (x[1] < 0) b[0] = -b[0];
+  } else {                                 // {B11, B12, B22, B13, B23}
+    double A[6][5], x[5];
+    for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][2]; A[i][3] = L[i][3]; A[i][4] = L[i][4]; }
+    lstsq<6, 5>(A, rho, x);
+    if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+    else { b[0] = sqrt(x[0]); b[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+    if (x[1] < 0) b[0] = -b[0];
+    b[2] = x[3] / b[0];
+  }
+  return (b[0] == b[0]) && (fabs(b[0]) < 1e300);
+}
+
+// EPnP on n <= 5 points.  pw: object points, uv: pixels.  Returns false for a degenerate configuration.
+DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu, double fv, double uc, double vc, double R[3][3],
+                   double t[3]) {
+  Ctx c;
+  if (!prepare(c, n, pw, uv, fu, fv, uc, vc)) return false;
   // ---- M^T M (12 x 12) and its four smallest eigenvectors
   {
     double MtM[12][12], W[12], Ut[12][12], Vt[12][12];
-    for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) MtM[i][j] = 0;
-    for (int p = 0; p < n; ++p) {
-      double m1[12], m2[12];
-      for (int j = 0; j < 4; ++j) {
-        m1[3 * j] = c.al[p][j] * fu; m1[3 * j + 1] = 0.0;              m1[3 * j + 2] = c.al[p][j] * (uc - uv[p][0]);
-        m2[3 * j] = 0.0;             m2[3 * j + 1] = c.al[p][j] * fv;  m2[3 * j + 2] = c.al[p][j] * (vc - uv[p][1]);
-      }
-      for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) MtM[i][j] += m1[i] * m1[j] + m2[i] * m2[j];
-    }
+    for (int i = 0; i < 12; ++i) mtm_row(c, i, MtM[i]);
     svd12(MtM, W, Ut, Vt);
     for (int k = 0; k < 4; ++k) for (int i = 0; i < 12; ++i) c.v[k][i] = Ut[11 - k][i];      // smallest singular values last
   }
-  // ---- L (6 x 10) and rho
   double L[6][10], rho[6];
-  {
-    const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
-    double dv[4][6][3];
-    for (int k = 0; k < 4; ++k)
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 3; ++j) dv[k][i][j] = c.v[k][3 * pa[i] + j] - c.v[k][3 * pb[i] + j];
-    auto dot = [&](int a, int b, int i) { return dv[a][i][0] * dv[b][i][0] + dv[a][i][1] * dv[b][i][1] + dv[a][i][2] * dv[b][i][2]; };
-    for (int i = 0; i < 6; ++i) {
-      L[i][0] = dot(0, 0, i); L[i][1] = 2 * dot(0, 1, i); L[i][2] = dot(1, 1, i); L[i][3] = 2 * dot(0, 2, i); L[i][4] = 2 * dot(1, 2, i);
-      L[i][5] = dot(2, 2, i); L[i][6] = 2 * dot(0, 3, i); L[i][7] = 2 * dot(1, 3, i); L[i][8] = 2 * dot(2, 3, i); L[i][9] = dot(3, 3, i);
-      double s = 0;
-      for (int j = 0; j < 3; ++j) { const double d = c.cws[pa[i]][j] - c.cws[pb[i]][j]; s += d * d; }
-      rho[i] = s;
-    }
-  }
+  build_L(c, L, rho);
   // ---- three beta approximations, Gauss-Newton, keep the smallest reprojection error
   double best = 1e300;
   for (int approx = 1; approx <= 3; ++approx) {
-    double b[4] = {0, 0, 0, 0};
-    if (approx == 1) {                       // betas10 columns {B11, B12, B13, B14}
-      double A[6][4], x[4];
-      for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][3]; A[i][3] = L[i][6]; }
-      lstsq<6, 4>(A, rho, x);
-      if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = -x[1] / b[0]; b[2] = -x[2] / b[0]; b[3] = -x[3] / b[0]; }
-      else { b[0] = sqrt(x[0]); b[1] = x[1] / b[0]; b[2] = x[2] / b[0]; b[3] = x[3] / b[0]; }
-    } else if (approx == 2) {                // {B11, B12, B22}
-      double A[6][3], x[3];
-      for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][2]; }
-      lstsq<6, 3>(A, rho, x);
-      if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-      else { b[0] = sqrt(x[0]); b[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-      if (x[1] < 0) b[0] = -b[0];
-    } else {                                 // {B11, B12, B22, B13, B23}
-      double A[6][5], x[5];
-      for (int i = 0; i < 6; ++i) { A[i][0] = L[i][0]; A[i][1] = L[i][1]; A[i][2] = L[i][2]; A[i][3] = L[i][3]; A[i][4] = L[i][4]; }
-      lstsq<6, 5>(A, rho, x);
-      if (x[0] < 0) { b[0] = sqrt(-x[0]); b[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-      else { b[0] = sqrt(x[0]); b[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-      if (x[1] < 0) b[0] = -b[0];
-      b[2] = x[3] / b[0];
-    }
-    if (!(b[0] == b[0]) || !(fabs(b[0]) < 1e300)) continue;
+    double b[4];
+    if (!initial_betas(approx, L, rho, b)) continue;
     gauss_newton(L, rho, b);
     double Rc[3][3], tc[3];
     const double e = r_and_t(c, b, Rc, tc);
@@ -283,6 +300,123 @@ DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu,
     }
   }
   return best < 1e300;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-cooperative EPnP: 16 lanes per minimal sample (two samples per warp).
+//   * the 12 x 12 one-sided Jacobi SVD -- 55 % of the one-thread solve -- keeps ONE COLUMN of Ut / Vt per lane (lanes 12..15 carry
+//     zeros): the row-pair dot product and the two row norms are butterfly sums over the 16-lane group (every lane ends with the
+//     same bits, so the skip / rotate decision is group-uniform), the rotation is two FMAs per lane.  The PAIR ORDER is the
+//     sequential cyclic order of cv::SVD (it fixes the signs and the basis inside the rank-deficient null space, see ocv_svd); only
+//     the order of the 12 additions inside a dot product differs from the one-thread path (round-off, as between any two builds);
+//   * control points / barycentric coordinates / L / rho are recomputed redundantly by every lane (no communication);
+//   * the three beta approximations + Gauss-Newton + absolute orientation run on lanes 0, 1, 2 of the group in parallel;
+//     the winner (first strictly smaller reprojection error, as in the sequential loop) is broadcast.
+// Control flow around the shuffles is warp-uniform (sweep loop exits on a warp-wide vote; a converged group's extra sweeps skip
+// every pair), so the CPU emulation build runs it unchanged with one warp per block.
+struct CoopSm { double u[12][16], v[12][16], w[12][16]; };
+#define EP_FULL 0xffffffffu
+// Shuffles name only the 16 lanes of the group (gm): the two groups of a warp take different branches (one rotates a pair the other
+// skips), and a *_sync primitive must be reached by every lane of its mask at the same instruction.
+DFVO_D double grp_sum(double x, unsigned gm) {
+  x += __shfl_xor_sync(gm, x, 8); x += __shfl_xor_sync(gm, x, 4);
+  x += __shfl_xor_sync(gm, x, 2); x += __shfl_xor_sync(gm, x, 1);
+  return x;
+}
+
+// arow: row gl of the symmetric A (= this lane's column of At); vout[k]: this lane's element of null vector k (Ut[11 - k][gl])
+DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, unsigned gm, double vout[4]) {
+  const double eps = 2.220446049250313e-16 * 10;
+  for (int i = 0; i < 12; ++i) {
+    const double t = gl < 12 ? arow[i] : 0.0;
+    sm.u[i][gl] = t;
+    sm.v[i][gl] = (i == gl) ? 1.0 : 0.0;
+    sm.w[i][gl] = grp_sum(t * t, gm);
+  }
+  for (int iter = 0; iter < 30; ++iter) {
+    bool changed = false;
+    for (int i = 0; i < 11; ++i)
+      for (int j = i + 1; j < 12; ++j) {
+        const double ui = sm.u[i][gl], uj = sm.u[j][gl];
+        double a = sm.w[i][gl], b = sm.w[j][gl];
+        double p = grp_sum(ui * uj, gm);
+        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        p *= 2;
+        const double beta = a - b, gamma = hypot(p, beta);
+        double c, s;
+        if (beta < 0) {
+          const double delta = (gamma - beta) * 0.5;
+          s = sqrt(delta / gamma);
+          c = p / (gamma * s * 2);
+        } else {
+          c = sqrt((gamma + beta) / (gamma * 2));
+          s = p / (gamma * c * 2);
+        }
+        const double t0 = c * ui + s * uj, t1 = -s * ui + c * uj;
+        sm.u[i][gl] = t0; sm.u[j][gl] = t1;
+        double a2 = t0 * t0, b2 = t1 * t1;                       // two independent butterflies in flight
+        a2 += __shfl_xor_sync(gm, a2, 8); b2 += __shfl_xor_sync(gm, b2, 8);
+        a2 += __shfl_xor_sync(gm, a2, 4); b2 += __shfl_xor_sync(gm, b2, 4);
+        a2 += __shfl_xor_sync(gm, a2, 2); b2 += __shfl_xor_sync(gm, b2, 2);
+        a2 += __shfl_xor_sync(gm, a2, 1); b2 += __shfl_xor_sync(gm, b2, 1);
+        sm.w[i][gl] = a2; sm.w[j][gl] = b2;
+        changed = true;
+        const double vi = sm.v[i][gl], vj = sm.v[j][gl];
+        sm.v[i][gl] = c * vi + s * vj; sm.v[j][gl] = -s * vi + c * vj;
+      }
+    if (__ballot_sync(EP_FULL, changed) == 0u) break;            // the whole warp: both groups leave the sweep loop together
+  }
+  double W[12];
+  int perm[12];
+  for (int i = 0; i < 12; ++i) { const double t = sm.u[i][gl]; W[i] = sqrt(grp_sum(t * t, gm)); perm[i] = i; }
+  for (int i = 0; i < 11; ++i) {                                 // the selection sort of ocv_svd, on a row permutation
+    int j = i;
+    for (int k = i + 1; k < 12; ++k) if (W[j] < W[k]) j = k;
+    if (i != j) { const double t = W[i]; W[i] = W[j]; W[j] = t; const int q = perm[i]; perm[i] = perm[j]; perm[j] = q; }
+  }
+  for (int k = 0; k < 4; ++k) {
+    const double sc = W[11 - k] > 2.2250738585072014e-308 ? 1.0 / W[11 - k] : 0.0;
+    vout[k] = sm.u[perm[11 - k]][gl] * sc;
+  }
+}
+
+// every lane of the 16-lane group passes the same sample; R, t, return value are group-uniform
+DFVO_D bool solve_coop(const double pw[][3], const double uv[][2], double fu, double fv, double uc, double vc, CoopSm& sm, int lane,
+                       double R[3][3], double t[3]) {
+  const int gl = lane & 15, gbase = lane & 16;
+  const unsigned gm = 0xffffu << gbase;
+  Ctx c;
+  bool good = prepare(c, 5, pw, uv, fu, fv, uc, vc);
+  if (!good)                                                    // degenerate sample: keep walking (group-uniform shuffles), report failure
+    for (int p = 0; p < 5; ++p) for (int j = 0; j < 4; ++j) c.al[p][j] = 0.25;
+  double row[12], vout[4];
+  mtm_row(c, gl < 12 ? gl : 0, row);
+  svd12_coop(row, sm, gl, gm, vout);
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 12; ++i) c.v[k][i] = __shfl_sync(gm, vout[k], gbase | i);
+  double L[6][10], rho[6];
+  build_L(c, L, rho);
+  double e = 1e300, Rc[3][3], tc[3];
+  for (int i = 0; i < 3; ++i) { tc[i] = 0; for (int j = 0; j < 3; ++j) Rc[i][j] = 0; }
+  if (gl < 3) {
+    double b[4];
+    if (initial_betas(gl + 1, L, rho, b)) {
+      gauss_newton(L, rho, b);
+      const double ee = r_and_t(c, b, Rc, tc);
+      if (ee == ee) e = ee;
+    }
+  }
+  double best = 1e300;
+  int win = 0;
+  for (int a = 0; a < 3; ++a) {
+    const double ea = __shfl_sync(gm, e, gbase | a);
+    if (ea < best) { best = ea; win = a; }
+  }
+  for (int i = 0; i < 3; ++i) {
+    t[i] = __shfl_sync(gm, tc[i], gbase | win);
+    for (int j = 0; j < 3; ++j) R[i][j] = __shfl_sync(gm, Rc[i][j], gbase | win);
+  }
+  return good && best < 1e300;
 }
 
 }  // namespace epnp
@@ -310,7 +444,7 @@ __global__ void k_pnp_hypotheses(const double* __restrict__ objp, const double* 
   if (i >= iters) return;
   double pw[5][3], uv[5][2];
   for (int k = 0; k < 5; ++k) {
-    const size_t o = (size_t)r * N + subsets[i * 5 + k];
+    const size_t o = (size_t)r * N + (subsets ? subsets[i * 5 + k] : i * 5 + k);
     for (int j = 0; j < 3; ++j) pw[k][j] = objp[o * 3 + j];
     uv[k][0] = imgp[o * 2]; uv[k][1] = imgp[o * 2 + 1];
   }
@@ -327,6 +461,70 @@ __global__ void k_pnp_hypotheses(const double* __restrict__ objp, const double* 
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) hyp[h * 12 + 3 * a + b] = Rm[a][b];
     for (int a = 0; a < 3; ++a) hyp[h * 12 + 9 + a] = t[a];
   }
+}
+
+// two minimal samples per warp (16 lanes each), epnp::solve_coop
+#ifdef DFVO_HOSTSIM
+#define PNP_COOP_WARPS 1            // the CPU emulation treats a shuffle as a block-wide rendezvous: one warp per block
+#else
+#define PNP_COOP_WARPS 2
+#endif
+__global__ void __launch_bounds__(32 * PNP_COOP_WARPS)
+k_pnp_hypotheses_coop(const double* __restrict__ objp, const double* __restrict__ imgp, const int32_t* __restrict__ subsets, int N,
+                      int iters, double fx, double fy, double cx, double cy, double* __restrict__ hyp, int32_t* __restrict__ ok) {
+  __shared__ epnp::CoopSm sm[2 * PNP_COOP_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 4, r = blockIdx.y;
+  const int i0 = (blockIdx.x * PNP_COOP_WARPS + warp) * 2 + grp;
+  const bool live = i0 < iters;
+  const int i = live ? i0 : iters - 1;                      // idle groups recompute the last sample (uniform control flow), no store
+  double pw[5][3], uv[5][2];
+  const double ifx = 1.0 / fx, ify = 1.0 / fy;
+  for (int k = 0; k < 5; ++k) {
+    const size_t o = (size_t)r * N + (subsets ? subsets[i * 5 + k] : i * 5 + k);
+    for (int j = 0; j < 3; ++j) pw[k][j] = objp[o * 3 + j];
+    uv[k][0] = (double)(float)((imgp[o * 2] - cx) * ifx); uv[k][1] = (double)(float)((imgp[o * 2 + 1] - cy) * ify);   // see k_pnp_hypotheses
+  }
+  double Rm[3][3], t[3];
+  const bool good = epnp::solve_coop(pw, uv, 1.0, 1.0, 0.0, 0.0, sm[warp * 2 + grp], lane, Rm, t);
+  if (live && (lane & 15) == 0) {
+    const size_t h = (size_t)r * iters + i;
+    ok[h] = good ? 1 : 0;
+    if (good) {
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) hyp[h * 12 + 3 * a + b] = Rm[a][b];
+      for (int a = 0; a < 3; ++a) hyp[h * 12 + 9 + a] = t[a];
+    }
+  }
+}
+
+// DFVO_PNP_COOP=0/1 (default: cooperative on the device, one thread per sample in the CPU emulation build where every shuffle
+// is a fiber switch); read per call so tests can compare the two paths
+static bool pnp_coop_enabled() {
+  const char* e = getenv("DFVO_PNP_COOP");
+#ifdef DFVO_HOSTSIM
+  return e && atoi(e) == 1;
+#else
+  return !(e && atoi(e) == 0);
+#endif
+}
+
+static int pnp_hypotheses(const double* objp, const double* imgp, const int32_t* subsets, int N, int R, int iters, double fx, double fy,
+                          double cx, double cy, double* hyp, int32_t* ok, int coop, cudaStream_t s) {
+  if (coop < 0) coop = pnp_coop_enabled() ? 1 : 0;
+  if (coop) {
+    DFVO_LAUNCH(k_pnp_hypotheses_coop, dim3(cdiv(iters, 2 * PNP_COOP_WARPS), R), dim3(32 * PNP_COOP_WARPS), 0, s, objp, imgp, subsets, N, iters,
+                fx, fy, cx, cy, hyp, ok);
+  } else {
+    DFVO_LAUNCH(k_pnp_hypotheses, dim3(cdiv(iters, 32), R), dim3(32), 0, s, objp, imgp, subsets, N, iters, fx, fy, cx, cy, hyp, ok);
+  }
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// stage entry (dfvo_epnp_minimal): M independent 5-point samples, obj [M*5][3], img [M*5][2] (device, FP64) -> rt [M][12], ok [M]
+int epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop, double* rt,
+                 int32_t* ok, cudaStream_t s) {
+  DFVO_REQUIRE(obj && img && rt && ok && M >= 1, DFVO_EINVAL, "epnp_minimal args");
+  return pnp_hypotheses(obj, img, nullptr, 5 * M, 1, M, fx, fy, cx, cy, rt, ok, coop, s);
 }
 
 DFVO_D bool pnp_inlier(const double* __restrict__ h, const double* __restrict__ X, const double* __restrict__ u, double fx, double fy,
@@ -590,7 +788,7 @@ int pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm,
   PnpState* st = (PnpState*)take((size_t)R * sizeof(PnpState));
   const float thr2 = (float)(threshold * threshold);
   DFVO_LAUNCH(k_pnp_prepare, dim3(cdiv(N, 128), R), dim3(128), 0, s, obj, img, perm, N, objp, imgp, st, iters);
-  DFVO_LAUNCH(k_pnp_hypotheses, dim3(cdiv(iters, 32), R), dim3(32), 0, s, objp, imgp, subsets, N, iters, fx, fy, cx, cy, hyp, ok);
+  { int rc = pnp_hypotheses(objp, imgp, subsets, N, R, iters, fx, fy, cx, cy, hyp, ok, -1, s); if (rc) return rc; }
   DFVO_LAUNCH(k_pnp_score, dim3(cdiv(iters * 32, 256), R), dim3(256), 0, s, hyp, ok, objp, imgp, N, iters, fx, fy, cx, cy, thr2, counts);
   DFVO_LAUNCH(k_pnp_replay, dim3(1), dim3(32), 0, s, ok, counts, N, iters, prob, st, R);
   DFVO_LAUNCH(k_pnp_refine, dim3(R), dim3(256), 0, s, hyp, st, objp, imgp, N, iters, fx, fy, cx, cy, thr2, rt_out, info, inl);

@@ -27,6 +27,11 @@ int pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm,
                double fy, double cx, double cy, double threshold, double prob, void* workspace, size_t ws_bytes, double* rt_out,
                int32_t* info, cudaStream_t s);
 
+// stage entry: EPnP (cv2.solvePnP(flags=SOLVEPNP_EPNP) as solvePnPRansac's minimal solver uses it) on M independent 5-point
+// samples; coop: 1 = lane-cooperative kernel, 0 = one thread per sample, -1 = the default of the build
+int epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop, double* rt,
+                 int32_t* ok, cudaStream_t s);
+
 // cv2.findHomography(p1, p2, RANSAC, threshold, maxIters, confidence) + GRIC-H (homog.cu)
 size_t homography_workspace_bytes(int N, int max_iters);
 int homography_ransac(const double* p1, const double* p2, int N, int max_iters, double threshold, double prob, void* workspace, size_t ws_bytes,

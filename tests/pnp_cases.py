@@ -127,3 +127,39 @@ def check_homography_vs_cv2(engine):
         assert abs(g - want) < 1e-9 * abs(want), (name, g, want)
         worst = max(worst, abs(g - want) / abs(want))
     return worst
+
+
+def check_epnp_minimal(engine, samples=6):
+    """csrc/pnp.cu's minimal solver through the stage entry dfvo_epnp_minimal: the lane-cooperative kernel (16 lanes per sample, one
+    column of the 12x12 Jacobi SVD per lane) against the one-thread-per-sample kernel, and both against cv2.solvePnP(SOLVEPNP_EPNP)
+    on the same 5 points.  Tolerances: cooperative vs sequential differ only in the summation order of the 12-term dot products, but
+    EPnP's null-space basis is normalised round-off (pnp_cases docstring), so poses agree to ~1e-6, not to the last bit; vs OpenCV
+    the same bound applies (rotation angle < 1e-5 rad, relative translation < 1e-5) on well-conditioned samples."""
+    import ctypes
+    import cv2
+    K, Kmat, kp1, d, XYZ, kp2 = scene(11, 0.0, 0.0, n=400)
+    cx, cy, fx, fy = K
+    rs = np.random.RandomState(3)
+    idx = np.stack([rs.choice(400, 5, replace=False) for _ in range(samples)])
+    obj = np.ascontiguousarray(XYZ[idx].astype(np.float32).astype(np.float64).reshape(-1, 3))
+    img = np.ascontiguousarray(kp2[idx].astype(np.float32).astype(np.float64).reshape(-1, 2))
+    rt = engine.rt
+    d_obj, d_img = rt.from_host(obj), rt.from_host(img)
+    out = {}
+    for coop in (0, 1):
+        d_rt, d_ok = rt.zeros((samples, 12), np.float64), rt.zeros((samples,), np.int32)
+        engine.lib.check(engine.lib.dfvo_epnp_minimal(d_obj.ptr, d_img.ptr, samples, fx, fy, cx, cy, coop, d_rt.ptr, d_ok.ptr, rt.stream_ptr()))
+        rt.sync()
+        out[coop] = (d_rt.numpy().copy(), d_ok.numpy().copy())
+    assert out[0][1].all() and out[1][1].all()
+    worst = [0.0, 0.0]
+    for s in range(samples):
+        Ra, ta = out[0][0][s, :9].reshape(3, 3), out[0][0][s, 9:]
+        Rb, tb = out[1][0][s, :9].reshape(3, 3), out[1][0][s, 9:]
+        ang, dt = pose_delta(Ra, ta, Rb, tb)
+        assert ang < 1e-5 and dt < 1e-5, ("coop vs sequential", s, ang, dt)
+        flag, rv, tv = cv2.solvePnP(obj[5 * s:5 * s + 5], img[5 * s:5 * s + 5], Kmat, None, flags=cv2.SOLVEPNP_EPNP)
+        ang2, dt2 = pose_delta(Rb, tb, cv2.Rodrigues(rv)[0], tv.ravel())
+        worst = [max(worst[0], ang2), max(worst[1], dt2)]
+    assert worst[0] < 1e-4 and worst[1] < 1e-4, ("vs cv2 EPNP", worst)
+    return worst

@@ -192,6 +192,11 @@ def test_pnp_ransac_vs_cv2(dev_lib):
     assert exact >= 0.8 * total
 
 
+def test_epnp_cooperative_vs_sequential_vs_cv2(dev_lib):
+    import pnp_cases
+    pnp_cases.check_epnp_minimal(_gpu_engine(), samples=64)
+
+
 def test_pnp_tracker_vs_reference_golden(dev_lib):
     import pnp_cases
     ang, dt = pnp_cases.check_vs_reference_golden(_gpu_engine(), np.load(os.path.join(G, "trackers_2000.npz")))

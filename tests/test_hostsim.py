@@ -161,6 +161,21 @@ def test_monodepth2_vs_reference_golden(hostsim_lib):
     assert (np.abs(out - g["depth"]) / g["depth"]).max() < 2e-5
 
 
+def test_monodepth2_bf16_stem_on_tensor_core_path(hostsim_lib):
+    """bf16 mode: the 7x7 stride-2 stem as a 4x1 window conv over the two row-parity views of the column-padded image
+    (monodepth2.cu::stem_tc_layer; weight packing, views and taps are host logic, the MMAs are emulated) vs the reference golden."""
+    g = np.load(os.path.join(G, "deep_models_70x150.npz"))
+    fh, fw = [int(x) for x in g["feed_hw"]]
+    enc, dec = synth.monodepth2_weights(4869, fh, fw)
+    ctx = native.Context(hostsim_lib)
+    ctx.load_weights(native.NET_MONODEPTH2, enc); ctx.load_weights(native.NET_MONODEPTH2, dec)
+    ctx.monodepth2_build(fh, fw, native.PREC_BF16)
+    out = np.zeros((fh, fw), np.float32)
+    ctx.monodepth2_forward(hptr(np.ascontiguousarray(g["depth_feed"][None])), hptr(out))
+    rel = np.abs(out - g["depth"]) / g["depth"]
+    assert rel.max() < 3e-2 and rel.mean() < 3e-3, (rel.max(), rel.mean())
+
+
 def test_selection_vs_reference_golden(hostsim_lib):
     g = np.load(os.path.join(G, "selection_376x1241.npz"))
     H, W = 376, 1241

@@ -23,6 +23,11 @@ def test_pnp_ransac_vs_cv2(hostsim_lib):
     print("repeats reproduced exactly: %d / %d" % (exact, total))
 
 
+def test_epnp_cooperative_vs_sequential_vs_cv2(hostsim_lib):
+    worst = pnp_cases.check_epnp_minimal(_engine(hostsim_lib), samples=4)
+    print("EPnP minimal solver vs cv2: %.2e rad, %.2e" % tuple(worst))
+
+
 def test_pnp_tracker_vs_reference_golden(hostsim_lib):
     worst = pnp_cases.check_vs_reference_golden(_engine(hostsim_lib), np.load(os.path.join(G, "trackers_2000.npz")))
     print("worst rotation / relative translation difference: %.2e rad, %.2e" % worst)
