@@ -84,7 +84,7 @@ class FramePipeline:
         self._bufs = {}
         self.overlap = bool(overlap)
         self.inflight = int(inflight) if self.overlap else 1
-        assert self.inflight in (1, 2)
+        assert self.inflight in (1, 2, 3)
         self.nslots = self.inflight + 2 if self.overlap else 2
         self.pending = []            # overlap mode: frames whose networks are enqueued but which are not tracked yet
         self.trk_ref = None          # overlap mode: the tracker's reference frame (self.ref is the networks')

@@ -303,72 +303,69 @@ DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Lane-cooperative EPnP: 16 lanes per minimal sample (two samples per warp).
-//   * the 12 x 12 one-sided Jacobi SVD -- 55 % of the one-thread solve -- keeps ONE COLUMN of Ut / Vt per lane (lanes 12..15 carry
-//     zeros): the row-pair dot product and the two row norms are butterfly sums over the 16-lane group (every lane ends with the
-//     same bits, so the skip / rotate decision is group-uniform), the rotation is two FMAs per lane.  The PAIR ORDER is the
-//     sequential cyclic order of cv::SVD (it fixes the signs and the basis inside the rank-deficient null space, see ocv_svd); only
-//     the order of the 12 additions inside a dot product differs from the one-thread path (round-off, as between any two builds);
+// Lane-cooperative EPnP: one warp per minimal sample.
+//   * the 12 x 12 one-sided Jacobi SVD -- 55 % of the one-thread solve -- keeps ONE COLUMN of Ut / Vt per lane (lanes 12..31 carry
+//     zeros): the row-pair dot product and the two row norms are butterfly sums (every lane ends with the same bits, so the
+//     skip / rotate decision is warp-uniform), the rotation is two FMAs per lane.  The PAIR ORDER is the sequential cyclic order of
+//     cv::SVD (it fixes the signs and the basis inside the rank-deficient null space, see ocv_svd); what differs from the
+//     one-thread path is round-off only: the order of the 12 additions inside a dot product, and the rotation (c, s) evaluated with
+//     two reciprocal square roots instead of hypot + 2 divisions + 2 square roots (the dependent FP64 chain that dominates a pair:
+//     measured on B200, a first version that kept the division / sqrt chain and packed two samples per warp was 2.2x SLOWER than
+//     the one-thread kernel -- the two halves diverge on every skipped pair);
 //   * control points / barycentric coordinates / L / rho are recomputed redundantly by every lane (no communication);
-//   * the three beta approximations + Gauss-Newton + absolute orientation run on lanes 0, 1, 2 of the group in parallel;
-//     the winner (first strictly smaller reprojection error, as in the sequential loop) is broadcast.
-// Control flow around the shuffles is warp-uniform (sweep loop exits on a warp-wide vote; a converged group's extra sweeps skip
-// every pair), so the CPU emulation build runs it unchanged with one warp per block.
+//   * the three beta approximations + Gauss-Newton + absolute orientation run on lanes 0, 1, 2 in parallel; the winner (first
+//     strictly smaller reprojection error, as in the sequential loop) is broadcast.
+// Control flow around the shuffles is warp-uniform, so the CPU emulation build runs it unchanged with one warp per block.
 struct CoopSm { double u[12][16], v[12][16], w[12][16]; };
 #define EP_FULL 0xffffffffu
-// Shuffles name only the 16 lanes of the group (gm): the two groups of a warp take different branches (one rotates a pair the other
-// skips), and a *_sync primitive must be reached by every lane of its mask at the same instruction.
-DFVO_D double grp_sum(double x, unsigned gm) {
-  x += __shfl_xor_sync(gm, x, 8); x += __shfl_xor_sync(gm, x, 4);
-  x += __shfl_xor_sync(gm, x, 2); x += __shfl_xor_sync(gm, x, 1);
+DFVO_D double grp_sum(double x) {                // lanes 0..15 (lanes 16..31 mirror them)
+  x += __shfl_xor_sync(EP_FULL, x, 8); x += __shfl_xor_sync(EP_FULL, x, 4);
+  x += __shfl_xor_sync(EP_FULL, x, 2); x += __shfl_xor_sync(EP_FULL, x, 1);
   return x;
 }
 
 // arow: row gl of the symmetric A (= this lane's column of At); vout[k]: this lane's element of null vector k (Ut[11 - k][gl])
-DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, unsigned gm, double vout[4]) {
-  const double eps = 2.220446049250313e-16 * 10;
+DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, double vout[4]) {
+  const double eps = 2.220446049250313e-16 * 10, eps2 = eps * eps;
   for (int i = 0; i < 12; ++i) {
     const double t = gl < 12 ? arow[i] : 0.0;
     sm.u[i][gl] = t;
     sm.v[i][gl] = (i == gl) ? 1.0 : 0.0;
-    sm.w[i][gl] = grp_sum(t * t, gm);
+    sm.w[i][gl] = grp_sum(t * t);
   }
   for (int iter = 0; iter < 30; ++iter) {
     bool changed = false;
     for (int i = 0; i < 11; ++i)
       for (int j = i + 1; j < 12; ++j) {
         const double ui = sm.u[i][gl], uj = sm.u[j][gl];
-        double a = sm.w[i][gl], b = sm.w[j][gl];
-        double p = grp_sum(ui * uj, gm);
-        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        const double a = sm.w[i][gl], b = sm.w[j][gl];
+        double p = grp_sum(ui * uj);
+        if (p * p <= eps2 * (a * b)) continue;                    // |p| <= eps sqrt(a b)
         p *= 2;
-        const double beta = a - b, gamma = hypot(p, beta);
-        double c, s;
-        if (beta < 0) {
-          const double delta = (gamma - beta) * 0.5;
-          s = sqrt(delta / gamma);
-          c = p / (gamma * s * 2);
-        } else {
-          c = sqrt((gamma + beta) / (gamma * 2));
-          s = p / (gamma * c * 2);
-        }
+        // gamma = hypot(p, beta);  beta < 0: s = sqrt((gamma - beta) / (2 gamma)), c = p / (2 gamma s)
+        //                          else:     c = sqrt((gamma + beta) / (2 gamma)), s = p / (2 gamma c)
+        const double beta = a - b, g2 = p * p + beta * beta;
+        const double rg = rsqrt(g2), gamma = g2 * rg;             // 1 / gamma, gamma
+        const double q = 0.5 * (gamma + fabs(beta)) * rg;          // the larger of c^2, s^2  (in [0.5, 1])
+        const double rq = rsqrt(q), big = q * rq, small_ = 0.5 * p * rg * rq;
+        const double c = beta < 0 ? small_ : big, s = beta < 0 ? big : small_;
         const double t0 = c * ui + s * uj, t1 = -s * ui + c * uj;
         sm.u[i][gl] = t0; sm.u[j][gl] = t1;
         double a2 = t0 * t0, b2 = t1 * t1;                       // two independent butterflies in flight
-        a2 += __shfl_xor_sync(gm, a2, 8); b2 += __shfl_xor_sync(gm, b2, 8);
-        a2 += __shfl_xor_sync(gm, a2, 4); b2 += __shfl_xor_sync(gm, b2, 4);
-        a2 += __shfl_xor_sync(gm, a2, 2); b2 += __shfl_xor_sync(gm, b2, 2);
-        a2 += __shfl_xor_sync(gm, a2, 1); b2 += __shfl_xor_sync(gm, b2, 1);
+        a2 += __shfl_xor_sync(EP_FULL, a2, 8); b2 += __shfl_xor_sync(EP_FULL, b2, 8);
+        a2 += __shfl_xor_sync(EP_FULL, a2, 4); b2 += __shfl_xor_sync(EP_FULL, b2, 4);
+        a2 += __shfl_xor_sync(EP_FULL, a2, 2); b2 += __shfl_xor_sync(EP_FULL, b2, 2);
+        a2 += __shfl_xor_sync(EP_FULL, a2, 1); b2 += __shfl_xor_sync(EP_FULL, b2, 1);
         sm.w[i][gl] = a2; sm.w[j][gl] = b2;
         changed = true;
         const double vi = sm.v[i][gl], vj = sm.v[j][gl];
         sm.v[i][gl] = c * vi + s * vj; sm.v[j][gl] = -s * vi + c * vj;
       }
-    if (__ballot_sync(EP_FULL, changed) == 0u) break;            // the whole warp: both groups leave the sweep loop together
+    if (!changed) break;                                          // warp-uniform
   }
   double W[12];
   int perm[12];
-  for (int i = 0; i < 12; ++i) { const double t = sm.u[i][gl]; W[i] = sqrt(grp_sum(t * t, gm)); perm[i] = i; }
+  for (int i = 0; i < 12; ++i) { const double t = sm.u[i][gl]; W[i] = sqrt(grp_sum(t * t)); perm[i] = i; }
   for (int i = 0; i < 11; ++i) {                                 // the selection sort of ocv_svd, on a row permutation
     int j = i;
     for (int k = i + 1; k < 12; ++k) if (W[j] < W[k]) j = k;
@@ -380,27 +377,26 @@ DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, unsigned gm, d
   }
 }
 
-// every lane of the 16-lane group passes the same sample; R, t, return value are group-uniform
+// every lane of the warp passes the same sample; R, t, return value are warp-uniform
 DFVO_D bool solve_coop(const double pw[][3], const double uv[][2], double fu, double fv, double uc, double vc, CoopSm& sm, int lane,
                        double R[3][3], double t[3]) {
-  const int gl = lane & 15, gbase = lane & 16;
-  const unsigned gm = 0xffffu << gbase;
+  const int gl = lane & 15;
   Ctx c;
   bool good = prepare(c, 5, pw, uv, fu, fv, uc, vc);
-  if (!good)                                                    // degenerate sample: keep walking (group-uniform shuffles), report failure
+  if (!good)                                                    // degenerate sample: keep walking (uniform shuffles), report failure
     for (int p = 0; p < 5; ++p) for (int j = 0; j < 4; ++j) c.al[p][j] = 0.25;
   double row[12], vout[4];
   mtm_row(c, gl < 12 ? gl : 0, row);
-  svd12_coop(row, sm, gl, gm, vout);
+  svd12_coop(row, sm, gl, vout);
   for (int k = 0; k < 4; ++k)
-    for (int i = 0; i < 12; ++i) c.v[k][i] = __shfl_sync(gm, vout[k], gbase | i);
+    for (int i = 0; i < 12; ++i) c.v[k][i] = __shfl_sync(EP_FULL, vout[k], i);
   double L[6][10], rho[6];
   build_L(c, L, rho);
   double e = 1e300, Rc[3][3], tc[3];
   for (int i = 0; i < 3; ++i) { tc[i] = 0; for (int j = 0; j < 3; ++j) Rc[i][j] = 0; }
-  if (gl < 3) {
+  if (lane < 3) {
     double b[4];
-    if (initial_betas(gl + 1, L, rho, b)) {
+    if (initial_betas(lane + 1, L, rho, b)) {
       gauss_newton(L, rho, b);
       const double ee = r_and_t(c, b, Rc, tc);
       if (ee == ee) e = ee;
@@ -409,12 +405,12 @@ DFVO_D bool solve_coop(const double pw[][3], const double uv[][2], double fu, do
   double best = 1e300;
   int win = 0;
   for (int a = 0; a < 3; ++a) {
-    const double ea = __shfl_sync(gm, e, gbase | a);
+    const double ea = __shfl_sync(EP_FULL, e, a);
     if (ea < best) { best = ea; win = a; }
   }
   for (int i = 0; i < 3; ++i) {
-    t[i] = __shfl_sync(gm, tc[i], gbase | win);
-    for (int j = 0; j < 3; ++j) R[i][j] = __shfl_sync(gm, Rc[i][j], gbase | win);
+    t[i] = __shfl_sync(EP_FULL, tc[i], win);
+    for (int j = 0; j < 3; ++j) R[i][j] = __shfl_sync(EP_FULL, Rc[i][j], win);
   }
   return good && best < 1e300;
 }
@@ -463,20 +459,19 @@ __global__ void k_pnp_hypotheses(const double* __restrict__ objp, const double* 
   }
 }
 
-// two minimal samples per warp (16 lanes each), epnp::solve_coop
+// one minimal sample per warp, epnp::solve_coop
 #ifdef DFVO_HOSTSIM
 #define PNP_COOP_WARPS 1            // the CPU emulation treats a shuffle as a block-wide rendezvous: one warp per block
 #else
-#define PNP_COOP_WARPS 2
+#define PNP_COOP_WARPS 4
 #endif
 __global__ void __launch_bounds__(32 * PNP_COOP_WARPS)
 k_pnp_hypotheses_coop(const double* __restrict__ objp, const double* __restrict__ imgp, const int32_t* __restrict__ subsets, int N,
                       int iters, double fx, double fy, double cx, double cy, double* __restrict__ hyp, int32_t* __restrict__ ok) {
-  __shared__ epnp::CoopSm sm[2 * PNP_COOP_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 4, r = blockIdx.y;
-  const int i0 = (blockIdx.x * PNP_COOP_WARPS + warp) * 2 + grp;
-  const bool live = i0 < iters;
-  const int i = live ? i0 : iters - 1;                      // idle groups recompute the last sample (uniform control flow), no store
+  __shared__ epnp::CoopSm sm[PNP_COOP_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = blockIdx.y;
+  const int i = blockIdx.x * PNP_COOP_WARPS + warp;
+  if (i >= iters) return;                                    // whole warps leave: the shuffles below stay warp-complete
   double pw[5][3], uv[5][2];
   const double ifx = 1.0 / fx, ify = 1.0 / fy;
   for (int k = 0; k < 5; ++k) {
@@ -485,8 +480,8 @@ k_pnp_hypotheses_coop(const double* __restrict__ objp, const double* __restrict_
     uv[k][0] = (double)(float)((imgp[o * 2] - cx) * ifx); uv[k][1] = (double)(float)((imgp[o * 2 + 1] - cy) * ify);   // see k_pnp_hypotheses
   }
   double Rm[3][3], t[3];
-  const bool good = epnp::solve_coop(pw, uv, 1.0, 1.0, 0.0, 0.0, sm[warp * 2 + grp], lane, Rm, t);
-  if (live && (lane & 15) == 0) {
+  const bool good = epnp::solve_coop(pw, uv, 1.0, 1.0, 0.0, 0.0, sm[warp], lane, Rm, t);
+  if (lane == 0) {
     const size_t h = (size_t)r * iters + i;
     ok[h] = good ? 1 : 0;
     if (good) {
@@ -511,7 +506,7 @@ static int pnp_hypotheses(const double* objp, const double* imgp, const int32_t*
                           double cx, double cy, double* hyp, int32_t* ok, int coop, cudaStream_t s) {
   if (coop < 0) coop = pnp_coop_enabled() ? 1 : 0;
   if (coop) {
-    DFVO_LAUNCH(k_pnp_hypotheses_coop, dim3(cdiv(iters, 2 * PNP_COOP_WARPS), R), dim3(32 * PNP_COOP_WARPS), 0, s, objp, imgp, subsets, N, iters,
+    DFVO_LAUNCH(k_pnp_hypotheses_coop, dim3(cdiv(iters, PNP_COOP_WARPS), R), dim3(32 * PNP_COOP_WARPS), 0, s, objp, imgp, subsets, N, iters,
                 fx, fy, cx, cy, hyp, ok);
   } else {
     DFVO_LAUNCH(k_pnp_hypotheses, dim3(cdiv(iters, 32), R), dim3(32), 0, s, objp, imgp, subsets, N, iters, fx, fy, cx, cy, hyp, ok);

@@ -130,7 +130,7 @@ def check_homography_vs_cv2(engine):
 
 
 def check_epnp_minimal(engine, samples=6):
-    """csrc/pnp.cu's minimal solver through the stage entry dfvo_epnp_minimal: the lane-cooperative kernel (16 lanes per sample, one
+    """csrc/pnp.cu's minimal solver through the stage entry dfvo_epnp_minimal: the lane-cooperative kernel (one warp per sample, one
     column of the 12x12 Jacobi SVD per lane) against the one-thread-per-sample kernel, and both against cv2.solvePnP(SOLVEPNP_EPNP)
     on the same 5 points.  Tolerances: cooperative vs sequential differ only in the summation order of the 12-term dot products, but
     EPnP's null-space basis is normalised round-off (pnp_cases docstring), so poses agree to ~1e-6, not to the last bit; vs OpenCV
