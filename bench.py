@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--config", default="vo", choices=["vo", "corr64", "ransac10k", "pairs64", "parity"])
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip precision modes / library baseline / extra configs / e2e_libs")
+    ap.add_argument("--diag-no-track", action="store_true",
+                    help="DIAGNOSTIC, not a bench value: replace the tracker by an identity pose to see the networks-only ceiling of the pipeline")
     return ap.parse_args()
 
 
@@ -662,7 +664,8 @@ def run_b200(args):
 
     def build_pipe(precision, overlap_, inflight_):
         np.random.seed(4869 + rank)
-        p = pipeline.FramePipeline(K, H, W, precision=precision, runtime=rt, overlap=overlap_, inflight=inflight_, inject=inject)
+        p = pipeline.FramePipeline(K, H, W, precision=precision, runtime=rt, overlap=overlap_, inflight=inflight_, inject=inject,
+                                   tracker_thread=overlap_ and os.environ.get("DFVO_TRACKER_THREAD", "1") != "0")
         p.load_weights(flow_w, enc, dec)
         return p
 
@@ -706,6 +709,9 @@ def run_b200(args):
 
     # ---------------------------------------------------------------- headline: bf16, two engines in flight
     pipe = build_pipe(native.PREC_BF16, overlap, inflight)
+    if args.diag_no_track:
+        pipe.track = lambda cur, ref: np.eye(4)
+        sys.stderr.write("bench.py: --diag-no-track: tracker replaced by an identity pose; the printed value is NOT the metric\n")
     # every network engine needs three forwards before it replays its CUDA graph (eager, capture, replay)
     warmup = max(3 * inflight + 1, args.warmup)
     warm(pipe, warmup)
@@ -835,6 +841,9 @@ def run_b200(args):
         gpu_library_baseline=gpu_lib,
         extra_configs=extra_cfg,
     )
+    if args.diag_no_track:
+        line = dict(diagnostic="--diag-no-track: networks-only ceiling of the pipeline, tracker replaced by an identity pose; NOT the metric",
+                    frames_per_s=line["value"], e2e_frames_per_s=line["e2e"]["value"], ms_per_step=line["ms_per_step"])
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

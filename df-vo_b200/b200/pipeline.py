@@ -49,7 +49,7 @@ class _ForkJoin:
 
 class FramePipeline:
     def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
-                 overlap=False, engine=None, inflight=1, inject=None):
+                 overlap=False, engine=None, inflight=1, inject=None, tracker_thread=False):
         """K = [cx, cy, fx, fy].
 
         inject: optional ``callable(pipeline, frame_state)`` run by ``infer`` right after the two networks of a frame were
@@ -64,7 +64,12 @@ class FramePipeline:
         depend on each other through the reference image / depth, which are triple-buffered here.
         inflight=2 (overlap mode only): a second, independent network engine, so the networks of two consecutive frames run
         concurrently (their small-grid phases fill each other's idle SMs) and tracking lags by two frames: ``step``
-        returns the pose of frame t-2, ``flush()`` the remaining ones (a list).  Same poses again."""
+        returns the pose of frame t-2, ``flush()`` the remaining ones (a list).  Same poses again.
+        tracker_thread=True (overlap mode only): the tracker runs on its own host thread (one frame at a time, in frame order, so
+        the RNG stream and the poses are unchanged).  ``step(img)`` enqueues the networks of ``img``, hands the frame to the tracker
+        thread and then waits for the pose of frame t-inflight, which that thread has been working on meanwhile: the host work
+        of enqueueing a frame (~0.4 ms) and the tracker's device waits (1.6-3.4 ms per frame) overlap instead of adding up.
+        Measured on B200: the networks alone sustain 1.9 ms per frame with two engines; the single-thread pipeline 2.6."""
         self.cfg = cfg or cfg_mod.default_cfg(height, width)
         self.K = [float(v) for v in K]
         self.H, self.W = height, width
@@ -86,6 +91,8 @@ class FramePipeline:
         self.inflight = int(inflight) if self.overlap else 1
         assert self.inflight in (1, 2, 3)
         self.nslots = self.inflight + 2 if self.overlap else 2
+        self.tracker_thread = bool(tracker_thread) and self.overlap
+        self._thr = None
         self.pending = []            # overlap mode: frames whose networks are enqueued but which are not tracked yet
         self.trk_ref = None          # overlap mode: the tracker's reference frame (self.ref is the networks')
         self.engs = [self.eng] + [tracking.Engine(height, width, self.rt) for _ in range(self.inflight - 1)]
@@ -328,9 +335,69 @@ class FramePipeline:
                 self.rt.wait_event(self._depth_done)
             cur.ready = self.rt.record_event()
         self.ref = cur
+        if self.tracker_thread:
+            return self._hand_over(cur)
         pose = self._track_oldest() if len(self.pending) >= self.inflight else None
         self.pending.append(cur)
         return pose
+
+    # ---- tracker thread -------------------------------------------------------------------------------------------------
+    def _start_tracker_thread(self):
+        import queue
+        import threading
+        self._q = queue.Queue()
+        self._cv = threading.Condition()
+        self._tracked = -1           # id of the last frame whose pose is in self.poses
+        self._thr_exc = None
+
+        def loop():
+            if getattr(self.rt, "is_device", True) and hasattr(self.rt, "torch"):
+                self.rt.torch.cuda.set_device(self.rt.device)
+            while True:
+                st = self._q.get()
+                if st is None:
+                    return
+                try:
+                    with self.rt.on_stream(self.s_trk):
+                        self.rt.wait_event(st.ready)
+                        self._advance(st, self.trk_ref)
+                    self.trk_ref = st
+                except BaseException as e:          # surfaced by the next step() / flush() on the caller's thread
+                    self._thr_exc = e
+                with self._cv:
+                    self._tracked = st.id
+                    self._cv.notify_all()
+                if self._thr_exc is not None:
+                    return
+        self._thr = threading.Thread(target=loop, name="dfvo-tracker", daemon=True)
+        self._thr.start()
+
+    def _wait_tracked(self, fid):
+        with self._cv:
+            while self._tracked < fid and self._thr_exc is None:
+                self._cv.wait(0.5)
+        if self._thr_exc is not None:
+            e, self._thr_exc = self._thr_exc, None
+            raise e
+
+    def _hand_over(self, cur):
+        """tracker_thread mode: queue `cur` for tracking, return the pose of frame cur.id - inflight (the buffers are
+        inflight + 2 deep, so the networks may run exactly that far ahead of the tracker)."""
+        if self._thr is None:
+            self._start_tracker_thread()
+        self._q.put(cur)
+        back = cur.id - self.inflight
+        if back < 0:
+            return None
+        self._wait_tracked(back)
+        return self.poses[back]
+
+    def close(self):
+        """Stops the tracker thread (tracker_thread mode); the pipeline can be used again afterwards."""
+        if self._thr is not None:
+            self._q.put(None)
+            self._thr.join(timeout=30)
+            self._thr = None
 
     def _track_oldest(self):
         nxt = self.pending.pop(0)
@@ -344,6 +411,11 @@ class FramePipeline:
         """Overlap mode: track the frames whose networks are still in flight; returns the last pose for inflight=1 (None if
         there is none), the list of remaining poses for inflight=2."""
         poses = []
+        if self.tracker_thread:
+            last = self.stage - 1
+            if self._thr is not None and last >= 0:
+                self._wait_tracked(last)
+                poses = [self.poses[f] for f in range(max(last - self.inflight + 1, 0), last + 1)]
         while self.overlap and self.pending:
             poses.append(self._track_oldest())
         if self.inflight > 1:

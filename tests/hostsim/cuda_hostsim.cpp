@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- see cuda_hostsim.h.
 #include "cuda_hostsim.h"
 #include <stdio.h>
+#include <mutex>
 
 uint3_ threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -48,6 +49,10 @@ unsigned long long shfl_u64(unsigned long long v, int src_lane) {
 }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  // one emulated kernel at a time: the fiber scheduler's state is global, and the frame pipeline's tracker thread launches
+  // kernels while the main thread enqueues the next frame
+  static std::mutex launch_mutex;
+  std::lock_guard<std::mutex> guard(launch_mutex);
   static std::vector<unsigned char> dyn;
   if (dyn.size() < smem + 16) dyn.resize(smem + 16);
   hostsim_dyn_smem = dyn.data();

@@ -10,11 +10,11 @@ from b200 import native, pipeline, runtime as rt_mod
 pytestmark = pytest.mark.gpu
 
 
-def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1):
+def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1, tracker_thread=False):
     rt = rt_mod.CudaRuntime(0)
     rt_mod.set_runtime(rt)
     np.random.seed(4869)
-    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight)
+    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight, tracker_thread=tracker_thread)
     p.load_weights(flow_w, enc, dec)
     base_infer = p.infer
     net_flows = {}
@@ -44,6 +44,7 @@ def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1):
         if q is not None:
             poses.append(q.copy())
     rt.torch.cuda.synchronize()
+    p.close()
     return poses, net_flows, [p.poses[i] for i in sorted(p.poses)]
 
 
@@ -58,7 +59,8 @@ def test_overlap_pipeline_equals_in_order(dev_lib):
     pa, fa, all_a = run(False, frames, analytic, K, h, w, enc, dec, flow_w)
     pb, fb, all_b = run(True, frames, analytic, K, h, w, enc, dec, flow_w)
     pc, fc, all_c = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2)       # two network engines in flight
-    assert len(pa) == n and len(pb) == n and len(pc) == n
+    pd, fd, all_d = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2, tracker_thread=True)   # + tracker on its own host thread
+    assert len(pa) == n and len(pb) == n and len(pc) == n and len(pd) == n
     for i in range(1, n):
         assert (fa[i][0] == fb[i][0]).all() and (fa[i][1] == fb[i][1]).all(), "network flow of frame %d differs" % i
         assert (fa["depth"][i] == fb["depth"][i]).all(), "network depth of frame %d differs" % i
@@ -67,4 +69,6 @@ def test_overlap_pipeline_equals_in_order(dev_lib):
     for i in range(n):
         assert np.array_equal(all_a[i], all_b[i]), "pose of frame %d differs between in-order and overlapped pipeline" % i
         assert np.array_equal(all_a[i], all_c[i]), "pose of frame %d differs with two frames in flight" % i
+        assert np.array_equal(all_a[i], all_d[i]), "pose of frame %d differs with the tracker thread" % i
+        assert np.array_equal(pc[i], pd[i]), "step() / flush() hand out different poses with the tracker thread (frame %d)" % i
     assert not np.allclose(all_a[-1], np.eye(4))

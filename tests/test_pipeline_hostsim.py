@@ -12,8 +12,8 @@ from oracle import seqdata
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("overlap,iterative", [(False, False), (True, True)])
-def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative):
+@pytest.mark.parametrize("overlap,iterative,threaded", [(False, False, False), (True, True, False), (True, False, True)])
+def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative, threaded):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     from runtime import HostsimRuntime
     from b200 import pipeline, runtime as rt_mod
@@ -50,9 +50,8 @@ def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative):
     if iterative:
         cfg.kp_selection.rigid_flow_kp.enable = True
         cfg.scale_recovery.method = "iterative"
-    inflight = 2 if iterative else 1     # the (True, True) case also runs two frames in flight (tracker two frames behind)
-    p = Injected(K, h, w, cfg=cfg, overlap=overlap, inflight=inflight)
-    modes = []
+    inflight = 2 if (iterative or threaded) else 1     # two frames in flight (tracker two frames behind); threaded: tracker on its own host thread
+    p = Injected(K, h, w, cfg=cfg, overlap=overlap, inflight=inflight, tracker_thread=threaded)
     if overlap:                          # two-stream mode: step(t) returns the pose of frame t-inflight, flush() the rest
         for _ in range(inflight):
             assert p.step(None) is None
@@ -67,11 +66,11 @@ def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative):
                 f = p.flush()
                 tail = f if isinstance(f, list) else [f]
             pose = tail.pop(0)
-        modes.append(p.last.get("mode"))
         dR = pose[:3, :3].T @ g["poses"][t][:3, :3]
         ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
         dt = np.linalg.norm(pose[:3, 3] - g["poses"][t][:3, 3])
         assert ang < 1e-6 and dt < 1e-6 * max(1.0, np.linalg.norm(g["poses"][t][:3, 3])), (t, ang, dt)
+    p.close()
     modes = list(p.modes.values())
     assert "PnP" in modes and "const" in modes and "E" in modes      # all three branches of dfvo.py:121-262 exercised
 
