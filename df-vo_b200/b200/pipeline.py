@@ -11,6 +11,7 @@ kilobytes (keypoints, masks, scores) instead of the reference's ~9.8 MB of dense
 This is the object ``bench.py`` times; ``df-vo_b200/libs`` exposes the same kernels behind the reference's
 class API for the unmodified driver.
 """
+import os
 import time
 
 import numpy as np
@@ -91,6 +92,7 @@ class FramePipeline:
         self.inflight = int(inflight) if self.overlap else 1
         assert self.inflight in (1, 2, 3)
         self.nslots = self.inflight + 2 if self.overlap else 2
+        self.fused_tail = os.environ.get("DFVO_FUSED_TAIL", "1") != "0"     # device-side tail of the E branch (track_fused)
         self.tracker_thread = bool(tracker_thread) and self.overlap
         self._thr = None
         self.pending = []            # overlap mode: frames whose networks are enqueued but which are not tracked yet
@@ -207,6 +209,9 @@ class FramePipeline:
         self.last = dict(good=good, n=n, mode="const")
         if not good:
             return self.motion.copy()                                     # constant motion (dfvo.py:157-161)
+        iterative = c.scale_recovery.method == "iterative"
+        if not iterative and 10 < n <= eng.TAIL_MAX_N and self.fused_tail:
+            return self.track_fused(cur, ref, kp1_buf, kp2_buf, n)
         kp_ref = kp1_buf.numpy()[:n]
         kp_cur = kp2_buf.numpy()[:n]
         # ---- E-tracker (dfvo.py:165-193).  The homography vote runs on a host worker thread; the pose-dependent device
@@ -238,6 +243,47 @@ class FramePipeline:
             self.last["mode"] = "PnP"
         return hybrid
 
+    def track_fused(self, cur, ref, kp1_buf, kp2_buf, n):
+        """The E branch of `track` with the device-side tail (tracking.Engine.essential_tail): after the keypoint count is known the
+        host draws the five shuffles, enqueues the homography model, the essential-matrix repeats and the fused tail, and reads ONE
+        packed result -- instead of eleven small reads with host arithmetic in between (keypoints, RANSAC info, GRIC, mask, pose,
+        cheirality, triangulated depths, CNN depths, H-GRIC, scale).  Same decisions, same generator stream; the host copies of the
+        keypoints are fetched only when the PnP fallback needs them."""
+        c, eng, K = self.cfg, self.eng, self.K
+        rs = c.scale_recovery.ransac
+        perms = []
+        for _ in range(c.e_tracker.ransac.repeat):
+            order = np.arange(0, n, 1)
+            self.rng.shuffle(order)
+            perms.append(order)
+        h = eng.homography_launch(kp2_buf, kp1_buf, n)
+        w = eng.essential_launch(kp2_buf, kp1_buf, n, perms, K, threshold=c.e_tracker.ransac.reproj_thre)
+        o = eng.essential_tail(w, h, kp2_buf, kp1_buf, n, K, cur.depth, self.rng, rs.min_samples, rs.max_trials, rs.stop_prob, rs.thre)
+        self.last.update(valid=o["valid"], inliers=None, inlier_handle=(w, o["best"]), mode="E", scale=None)
+        hybrid = np.eye(4)
+        hybrid[:3, :3] = o["R"]
+        t = o["t"]
+        scale = None
+        if np.linalg.norm(t) != 0:
+            scale = o["scale"]
+            if scale != -1:
+                hybrid[:3, 3] = t[:, 0] * scale
+        self.last["scale"] = scale
+        if np.linalg.norm(t) == 0 or scale == -1:                    # PnP fallback (dfvo.py:225-250)
+            kp_ref, kp_cur = kp1_buf.numpy()[:n], kp2_buf.numpy()[:n]
+            hybrid = self.pnp(kp_ref, kp_cur, kp1_buf, n, ref)
+            self.last["mode"] = "PnP"
+        return hybrid
+
+    def last_inliers(self):
+        """Inlier mask of the last E-tracked frame (bool [n]); read from the device on demand in the fused path."""
+        if self.last.get("inliers") is not None:
+            return self.last["inliers"]
+        hw = self.last.get("inlier_handle")
+        if hw is None or hw[1] < 0:
+            return None
+        return hw[0]["mask"].numpy()[hw[1]].astype(bool)
+
     def scale_prepare(self, kp_ref, kp_cur, kp_cur_buf, T_21, depth_buf, n):
         """E_tracker.py:476-507,571-616: device triangulation + device gather of the CNN depth at the keypoints ->
         (depth ratios, number of valid ones).  Consumes no host RNG."""
@@ -250,11 +296,11 @@ class FramePipeline:
         return hostmath.last_writer_depth_ratio_sparse(kp_cur, z, dk.numpy(), self.H, self.W)
 
     def scale_finish(self, prep):
-        """E_tracker.py:617-643: the RNG-consuming 1-parameter RANSAC on the host (~0.5 ms)."""
+        """E_tracker.py:617-643: the 1-parameter RANSAC, on the device with the host generator's MT19937 state (Engine.ransac_scale)."""
         c = self.cfg.scale_recovery.ransac
         ratio, nvalid = prep
         if nvalid > 10:
-            return hostmath.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
+            return self.eng.ransac_scale(ratio, c.min_samples, c.max_trials, c.stop_prob, c.thre, self.rng)
         return -1
 
     def scale_iterative(self, cur, ref, kp_ref, kp_cur, E_pose):

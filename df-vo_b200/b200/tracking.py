@@ -238,6 +238,49 @@ class Engine:
                                                       w["info"].ptr, w["gric"].ptr, self.rt.stream_ptr()))
         return w
 
+    TAIL_MAX_N = 4096
+
+    def essential_tail(self, w, h, kp_cur_buf, kp_ref_buf, n, K, depth_buf, rng, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1):
+        """Everything between the essential-matrix repeats and "pose and scale known" in one enqueue and ONE device->host read
+        (dfvo_essential_tail): best repeat, recoverPose, the GRIC vote against the homography handle `h`, the cheirality gate, the depth
+        ratios and the scale regressor (with `rng`'s MT19937 state; the advanced state is installed back).  Returns a dict with
+        R, t (identity / zero when the pose is rejected, as compute_pose_2d2d + resolve_validity give them), valid, cheirality, best,
+        E_gric, H_gric, ransac_info, scale (-1 when not recovered), scale_status, and `w` for a lazy inlier mask."""
+        cx, cy, fx, fy = K
+        R = w["info"].shape[0]
+        cap = w["cap"]
+        c = getattr(self, "_tail", None)
+        if c is None or c["cap"] < cap or c["R"] != R:
+            nb = int(self.lib.dfvo_essential_tail_workspace_bytes(cap))
+            c = self._tail = dict(cap=cap, R=R, ws=self.rt.empty((nb,), np.uint8), res=self.rt.empty((335 + 5 * R,), np.float64),
+                                  host=np.zeros(335 + 5 * R, np.float64))
+        st = rng.get_state()
+        if st[0] != "MT19937":
+            raise TypeError("essential_tail needs a legacy MT19937 generator (np.random / np.random.RandomState)")
+        u = c["host"][4:317].view(np.uint32)
+        u[:624] = st[1]
+        u[624] = st[2]
+        c["res"].upload(c["host"])
+        self.rt.wait_event(h["done"])                               # order this stream after the homography side stream
+        self.lib.check(self.lib.dfvo_essential_tail(w["E"].ptr, w["info"].ptr, w["gric"].ptr, R, kp_cur_buf.ptr, kp_ref_buf.ptr, n, fx, fy,
+                                                    cx, cy, h["gric"].ptr, depth_buf.ptr, self.H, self.W, int(min_samples), int(max_trials),
+                                                    float(stop_prob), float(thre), c["ws"].ptr, c["ws"].shape[0], c["res"].ptr,
+                                                    w["pmask"].ptr, w["pinfo"].ptr, self.rt.stream_ptr()))
+        o = c["res"].numpy()                                        # the one synchronising read
+        u = o[4:317].view(np.uint32)
+        rng.set_state(("MT19937", u[:624].copy(), int(u[624]), st[3], st[4]))
+        best, valid, cheir = int(o[317]), bool(o[318]), int(o[320])
+        out = dict(R=np.eye(3), t=np.zeros((3, 1)), valid=valid, cheirality=0, best=best, H_gric=float(o[319]),
+                   E_gric=o[335:335 + R].copy(), ransac_info=o[335 + R:335 + 5 * R].reshape(R, 4).astype(np.int32), scale=-1,
+                   scale_status=int(o[1]), n_ratios=int(o[321]), handle=w)
+        if valid and best >= 0 and cheir > n * 0.1:
+            out["R"], out["t"], out["cheirality"] = o[323:332].reshape(3, 3).copy(), o[332:335].reshape(3, 1).copy(), cheir
+        if o[1] == -1:
+            raise ValueError("RANSAC could not find a valid consensus set")
+        if o[1] == 1:
+            out["scale"] = float(o[0])
+        return out
+
     def recover_pose(self, w, best, kp_cur_buf, kp_ref_buf, n, K):
         """cv2.recoverPose(best_E, kp_cur, kp_ref, focal=fx, pp) (E_tracker.py:292-295)."""
         cx, cy, fx, fy = K
@@ -293,6 +336,36 @@ class Engine:
                                                 iters, fx, fy, cx, cy, float(reproj_thre), prob, w["ws"].ptr, w["ws"].shape[0],
                                                 w["rt"].ptr, w["info"].ptr, self.rt.stream_ptr()))
         return w["rt"].numpy(), w["info"].numpy()
+
+    def ransac_scale(self, ratio, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1, rng=np.random):
+        """The scale fit of find_scale_from_depth (E_tracker.py:618-641, sklearn RANSACRegressor through the origin) on the device
+        (csrc/ransac.cu::k_scale_ransac).  The regressor samples from NumPy's global generator; the kernel receives that generator's
+        MT19937 state, draws exactly what scikit-learn would draw, and the advanced state is installed back into ``rng`` -- the
+        shuffles of the next frame continue from the same position as in the reference.  Raises ValueError like sklearn when no
+        consensus set exists."""
+        ratio = np.ascontiguousarray(ratio, np.float64).reshape(-1)
+        n = ratio.shape[0]
+        st = rng.get_state()
+        if st[0] != "MT19937":
+            raise TypeError("ransac_scale needs a legacy MT19937 generator (np.random / np.random.RandomState)")
+        cap = self._capacity(n)
+        if not hasattr(self, "_sr") or self._sr["x"].size < cap:
+            self._sr = dict(x=self.rt.empty((cap,), np.float64), io=self.rt.empty((4 + 313,), np.float64), perm=self.rt.empty((cap,), np.int32))
+        w = self._sr
+        w["x"].view((n,)).upload(ratio)
+        io_h = np.zeros(4 + 313, np.float64)
+        u = io_h[4:].view(np.uint32)
+        u[:624] = st[1]
+        u[624] = st[2]
+        w["io"].upload(io_h)
+        self.lib.check(self.lib.dfvo_scale_ransac(w["x"].ptr, n, int(min_samples), int(max_trials), float(stop_prob), float(thre), w["io"].ptr,
+                                                  w["perm"].ptr, self.rt.stream_ptr()))
+        out = w["io"].numpy()
+        u = out[4:].view(np.uint32)
+        rng.set_state(("MT19937", u[:624].copy(), int(u[624]), st[3], st[4]))
+        if out[1] < 0:
+            raise ValueError("RANSAC could not find a valid consensus set")
+        return float(out[0])
 
     def triangulate_depth(self, kp1n_buf, kp2n_buf, n, T21):
         if not hasattr(self, "_tri") or self._tri["z"].shape[0] < n:
@@ -401,7 +474,7 @@ def compute_pose_3d2d(engine, kp1, kp2, d, K, repeat=5, iters=100, reproj_thre=1
 def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1,
                           rng=np.random):
     """``EssTracker.find_scale_from_depth`` (E_tracker.py:571-643): triangulation on the device, the
-    (tiny, RNG-consuming) scale RANSAC on the host."""
+    scale RANSAC (which consumes the host generator's stream) on the device too (Engine.ransac_scale)."""
     cx, cy, fx, fy = K
     n = kp1.shape[0]
     k1 = (kp1 - np.array([cx, cy])) / np.array([fx, fy])
@@ -409,7 +482,7 @@ def find_scale_from_depth(engine, kp1, kp2, T_21, depth2, K, min_samples=3, max_
     z = engine.triangulate_depth(engine.rt.from_host(k1), engine.rt.from_host(k2), n, T_21)
     ratio, nvalid = hostmath.last_writer_depth_ratio(kp2, z, depth2)
     if nvalid > 10:
-        return hostmath.ransac_scale(ratio, min_samples, max_trials, stop_prob, thre, rng)
+        return engine.ransac_scale(ratio, min_samples, max_trials, stop_prob, thre, rng)
     return -1
 
 

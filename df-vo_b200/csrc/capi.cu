@@ -555,6 +555,24 @@ int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* 
   API_END
 }
 
+int dfvo_scale_ransac(const double* ratio, int n, int min_samples, int max_trials, double stop_prob, double threshold, double* io,
+                      int32_t* perm_scratch, void* stream) {
+  API_BEGIN
+  return scale_ransac(ratio, n, min_samples, max_trials, stop_prob, threshold, io, perm_scratch, (cudaStream_t)stream);
+  API_END
+}
+
+size_t dfvo_essential_tail_workspace_bytes(int N) { return essential_tail_workspace_bytes(N); }
+int dfvo_essential_tail(const double* E, const int32_t* info, const double* gric, int R, const double* kp_cur, const double* kp_ref, int N,
+                        double fx, double fy, double cx, double cy, const double* h_gric, const float* depth, int H, int W,
+                        int min_samples, int max_trials, double stop_prob, double threshold, void* workspace, size_t workspace_bytes,
+                        double* res, uint8_t* pose_mask, int32_t* pose_info, void* stream) {
+  API_BEGIN
+  return essential_tail(E, info, gric, R, kp_cur, kp_ref, N, fx, fy, cx, cy, h_gric, depth, H, W, min_samples, max_trials, stop_prob, threshold,
+                        workspace, workspace_bytes, res, pose_mask, pose_info, (cudaStream_t)stream);
+  API_END
+}
+
 int dfvo_epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop, double* rt,
                       int32_t* ok, void* stream) {
   API_BEGIN

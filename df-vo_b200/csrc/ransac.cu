@@ -516,4 +516,332 @@ int recover_pose(const double* E, const double* p1, const double* p2, int N, dou
   return DFVO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Scale recovery: sklearn.linear_model.RANSACRegressor(LinearRegression(fit_intercept=False), min_samples, max_trials, stop_probability,
+// residual_threshold).fit(ratio[:, None], ones) -> estimator_.coef_[0, 0]   (E_tracker.py:618-641), on the device, INCLUDING the host's
+// random stream: the regressor draws its samples from NumPy's global MT19937 (sample_without_replacement -> RandomState.randint /
+// permutation), and the reference's later shuffles continue from wherever it stopped -- so the kernel takes the generator's state
+// (key[624], pos), walks it exactly as NumPy does (32-bit draws, masked rejection: random_interval / buffered_bounded_masked_uint32)
+// and hands the advanced state back.  One block: thread 0 owns the generator and the accept / max_trials logic (sklearn's
+// _ransac.py loop), the block evaluates the residuals |1 - s x| <= threshold of a trial in parallel.
+// Arithmetic follows the NumPy expressions operation by operation (no FMA contraction) except the two long dot products of the
+// final refit, which NumPy hands to BLAS (order of additions unspecified): the scale agrees to ~1e-15 relative.
+// io (doubles): [0] scale, [1] status (1 ok, -1 no consensus), [2] trials run, [3] inliers of the best model, then key/pos as
+// 625 uint32 starting at io + 4.
+// ------------------------------------------------------------------------------------------------
+struct Mt { uint32_t* key; int pos; };
+DFVO_D void mt_regen(uint32_t* mt) {
+  const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+  int kk = 0;
+  for (; kk < 624 - 397; ++kk) { const uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+  for (; kk < 623; ++kk) { const uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+  const uint32_t y = (mt[623] & UP) | (mt[0] & LO);
+  mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+}
+DFVO_D uint32_t mt_next(Mt& g) {
+  if (g.pos >= 624) { mt_regen(g.key); g.pos = 0; }
+  uint32_t y = g.key[g.pos++];
+  y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+  return y;
+}
+// numpy random_interval(max) / bounded masked uint32: uniform integer in [0, max]
+DFVO_D uint32_t mt_interval(Mt& g, uint32_t max) {
+  if (max == 0) return 0;
+  uint32_t mask = max;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  uint32_t v;
+  do { v = mt_next(g) & mask; } while (v > max);
+  return v;
+}
+
+#define SR_THREADS 256
+#define SR_MAX_SAMPLES 16
+__global__ void __launch_bounds__(SR_THREADS)
+k_scale_ransac(const double* __restrict__ x, int n, int min_samples, int max_trials_in, double stop_prob, double thr, double* __restrict__ io,
+               int32_t* __restrict__ perm_scratch, const double* __restrict__ n_dev, const double* __restrict__ gate) {
+  // fused E-tracker tail: the sample count and the go / no-go decision live on the device (no generator draw when the gate is closed
+  // or fewer than 11 depth ratios are valid, exactly where the reference does not call the regressor: E_tracker.py:617-643)
+  if (gate != nullptr) {
+    if (*gate == 0.0) { if (threadIdx.x == 0) { io[0] = -1.0; io[1] = -3.0; io[2] = 0.0; io[3] = 0.0; } return; }
+    n = (int)*n_dev;
+    if (n <= 10) { if (threadIdx.x == 0) { io[0] = -1.0; io[1] = -2.0; io[2] = 0.0; io[3] = 0.0; } return; }
+  }
+  __shared__ uint32_t key[624];
+  __shared__ int idx[SR_MAX_SAMPLES];
+  __shared__ int part_i[SR_THREADS / 32], part_nz[SR_THREADS / 32];
+  __shared__ double part_d[2][SR_THREADS / 32];
+  __shared__ double s_best_sh;
+  __shared__ int go;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t* st = reinterpret_cast<uint32_t*>(io + 4);
+  for (int i = t; i < 624; i += SR_THREADS) key[i] = st[i];
+  __syncthreads();
+  Mt g; g.key = key; g.pos = (int)st[624];
+  double max_trials = (double)max_trials_in;
+  int n_trials = 0, n_best = 1, have = 0;
+  double score_best = -1e300, s_best = 0.0;
+  const double ratio = n > 0 ? (double)min_samples / (double)n : 1.0;
+  while (true) {
+    if (t == 0) {
+      go = ((double)n_trials < max_trials) ? 1 : 0;
+      if (go) {
+        // sklearn.utils.random.sample_without_replacement(n, min_samples, method='auto') of scikit-learn 1.9 (hostmath.py docstring)
+        if (ratio > 0.01 && ratio < 0.99) {                       // rng.permutation(n)[:k]: arange + legacy shuffle
+          for (int i = 0; i < n; ++i) perm_scratch[i] = i;
+          for (int i = n - 1; i >= 1; --i) {
+            const int j = (int)mt_interval(g, (uint32_t)i);
+            const int tmp = perm_scratch[i]; perm_scratch[i] = perm_scratch[j]; perm_scratch[j] = tmp;
+          }
+          for (int i = 0; i < min_samples; ++i) idx[i] = perm_scratch[i];
+        } else if (ratio < 0.2) {                                 // tracking selection: rng.randint(n) until unseen
+          for (int i = 0; i < min_samples; ++i) {
+            int j;
+            bool dup;
+            do {
+              j = (int)mt_interval(g, (uint32_t)(n - 1));
+              dup = false;
+              for (int q = 0; q < i; ++q) dup = dup || idx[q] == j;
+            } while (dup);
+            idx[i] = j;
+          }
+        } else {                                                  // reservoir sampling
+          for (int i = 0; i < min_samples; ++i) idx[i] = i;
+          for (int i = min_samples; i < n; ++i) {
+            const int j = (int)mt_interval(g, (uint32_t)i);
+            if (j < min_samples) idx[j] = i;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (!go) break;
+    ++n_trials;
+    // LinearRegression(fit_intercept=False) on the sample: s = dot(x, y) / dot(x, x), y = 1
+    double num = 0.0, den = 0.0;
+    for (int i = 0; i < min_samples; ++i) { const double xi = x[idx[i]]; num = __dadd_rn(num, xi); den = __dadd_rn(den, __dmul_rn(xi, xi)); }
+    const double s = den != 0.0 ? num / den : 0.0;
+    int cnt = 0, nz = 0;
+    for (int i = t; i < n; i += SR_THREADS) {
+      const double r = __dsub_rn(1.0, __dmul_rn(s, x[i]));
+      if (fabs(r) <= thr) { ++cnt; nz |= (r != 0.0) ? 1 : 0; }
+    }
+    for (int off = 16; off > 0; off >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, off); nz |= __shfl_xor_sync(0xffffffffu, nz, off); }
+    if (lane == 0) { part_i[warp] = cnt; part_nz[warp] = nz; }
+    __syncthreads();
+    int n_inl = 0, any_nz = 0;
+    for (int w8 = 0; w8 < SR_THREADS / 32; ++w8) { n_inl += part_i[w8]; any_nz |= part_nz[w8]; }
+    __syncthreads();                                              // part_* are rewritten by the next trial
+    // _ransac.py: fewer inliers -> next; equal inliers and worse score -> next (score = r2 of the constant target: 1 if exact, else 0)
+    if (n_inl < n_best) continue;
+    const double score = any_nz ? 0.0 : 1.0;
+    if (n_inl == n_best && score < score_best) continue;
+    n_best = n_inl; score_best = score; s_best = s; have = 1;
+    {
+      const double eps = 2.220446049250313e-16;
+      const double w = (double)n_best / (double)n;
+      const double nom = fmax(eps, 1.0 - stop_prob), denom = fmax(eps, 1.0 - pow(w, (double)min_samples));
+      double dyn;
+      if (nom == 1.0) dyn = 0.0;
+      else if (denom == 1.0) dyn = 1e300;
+      else dyn = fabs(ceil(log(nom) / log(denom)));
+      if (dyn < max_trials) max_trials = dyn;
+    }
+  }
+  // final refit on the best consensus set
+  double sx = 0.0, sxx = 0.0;
+  int cnt = 0;
+  if (have)
+    for (int i = t; i < n; i += SR_THREADS) {
+      const double xi = x[i];
+      if (fabs(__dsub_rn(1.0, __dmul_rn(s_best, xi))) <= thr) { sx += xi; sxx += xi * xi; ++cnt; }
+    }
+  for (int off = 16; off > 0; off >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, off); sxx += __shfl_xor_sync(0xffffffffu, sxx, off); cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if (lane == 0) { part_d[0][warp] = sx; part_d[1][warp] = sxx; part_i[warp] = cnt; }
+  __syncthreads();
+  if (t == 0) {
+    double a = 0, b = 0; int c = 0;
+    for (int w8 = 0; w8 < SR_THREADS / 32; ++w8) { a += part_d[0][w8]; b += part_d[1][w8]; c += part_i[w8]; }
+    io[0] = (have && b != 0.0) ? a / b : 0.0;
+    io[1] = have ? 1.0 : -1.0;
+    io[2] = (double)n_trials;
+    io[3] = (double)c;
+    (void)s_best_sh;
+  }
+  __syncthreads();
+  for (int i = t; i < 624; i += SR_THREADS) st[i] = key[i];
+  if (t == 0) st[624] = (uint32_t)g.pos;
+}
+
+int scale_ransac(const double* ratio, int n, int min_samples, int max_trials, double stop_prob, double thr, double* io, int32_t* perm_scratch,
+                 cudaStream_t s) {
+  DFVO_REQUIRE(ratio && io && perm_scratch && n >= 1 && min_samples >= 1 && min_samples <= SR_MAX_SAMPLES && min_samples <= n && max_trials >= 0,
+               DFVO_EINVAL, "scale_ransac args (n=%d min_samples=%d)", n, min_samples);
+  DFVO_LAUNCH(k_scale_ransac, dim3(1), dim3(SR_THREADS), 0, s, ratio, n, min_samples, max_trials, stop_prob, thr, io, perm_scratch,
+              (const double*)nullptr, (const double*)nullptr);
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused tail of the E-tracker (E_tracker.py:270-300 + dfvo.py:165-193 + E_tracker.py:476-507,571-643): everything between "the five
+// RANSAC repeats are done" and "the host knows pose and scale" without a host round trip:
+//   k_track_pick   first repeat with the most inliers (E_tracker.py:278-281), its E, the per-repeat numbers as doubles
+//   recover_pose   cv2.recoverPose on that E (kernels above)
+//   k_track_gate   majority vote H_gric > E_gric (:286-290), cheirality > 0.1 n (:299-300), |t| != 0 (dfvo.py:182) -> gate; T_21 = inv([R|t])
+//   k_scale_chain  find_scale_from_depth up to the regressor: normalise, triangulate, CNN depth at int(kp_cur), last-writer-wins
+//                  per pixel, ratios in row-major pixel order (ops_3d.py:15-41, E_tracker.py:598-616)
+//   k_scale_ransac the regressor with the host generator's MT19937 state (above), gated
+// res (doubles): [0..3] scale io, [4..316] generator state, [317] best, [318] valid, [319] H_gric, [320] cheirality count, [321] valid
+// depth ratios, [322] gate, [323..334] Rt of recoverPose, [335..335+R) E_gric, then info [R][4].
+// ------------------------------------------------------------------------------------------------
+#define TR_BEST 317
+#define TR_VALID 318
+#define TR_HGRIC 319
+#define TR_CHEIR 320
+#define TR_NVALID 321
+#define TR_GATE 322
+#define TR_RT 323
+#define TR_EGRIC 335
+
+__global__ void k_track_pick(const int32_t* __restrict__ info, const double* __restrict__ gric, const double* __restrict__ E, int R,
+                             double* __restrict__ res, double* __restrict__ E_best) {
+  if (threadIdx.x != 0) return;
+  int best = -1, cnt = 0;
+  for (int r = 0; r < R; ++r)
+    if (info[4 * r] > cnt) { best = r; cnt = info[4 * r]; }
+  res[TR_BEST] = (double)best;
+  for (int r = 0; r < R; ++r) {
+    res[TR_EGRIC + r] = gric[r];
+    for (int q = 0; q < 4; ++q) res[TR_EGRIC + R + 4 * r + q] = (double)info[4 * r + q];
+  }
+  for (int q = 0; q < 9; ++q) E_best[q] = best >= 0 ? E[9 * best + q] : ((q % 4 == 0 && q < 8) ? 1.0 : 0.0);    // any finite E keeps the kernels benign
+}
+
+__global__ void k_track_gate(double* __restrict__ res, const int32_t* __restrict__ pinfo, const double* __restrict__ h_gric, int R, int n,
+                             double* __restrict__ T21) {
+  if (threadIdx.x != 0) return;
+  const double hg = h_gric[0];
+  int votes = 0;
+  for (int r = 0; r < R; ++r) votes += (hg > res[TR_EGRIC + r]) ? 1 : 0;
+  const bool valid = (double)votes > (double)R / 2.0;
+  const int best = (int)res[TR_BEST], cheir = best >= 0 ? pinfo[0] : 0;
+  const double* Rt = res + TR_RT;
+  const bool pose_ok = valid && best >= 0 && (double)cheir > (double)n * 0.1;
+  const double tn = Rt[9] * Rt[9] + Rt[10] * Rt[10] + Rt[11] * Rt[11];
+  const bool gate = pose_ok && tn != 0.0;
+  res[TR_VALID] = valid ? 1.0 : 0.0; res[TR_HGRIC] = hg; res[TR_CHEIR] = (double)cheir; res[TR_GATE] = gate ? 1.0 : 0.0; res[TR_NVALID] = 0.0;
+  // T_21 = inv([R | t]) = [R^T | -R^T t], rows 0..2
+  for (int a = 0; a < 3; ++a) {
+    double tt = 0;
+    for (int b = 0; b < 3; ++b) { T21[4 * a + b] = Rt[3 * b + a]; tt += Rt[3 * b + a] * Rt[9 + b]; }
+    T21[4 * a + 3] = -tt;
+  }
+}
+
+#define SC_THREADS 1024
+#define SC_MAX 4096
+__global__ void __launch_bounds__(SC_THREADS)
+k_scale_chain(const double* __restrict__ kp_ref, const double* __restrict__ kp_cur, int n, double fx, double fy, double cx, double cy,
+              const double* __restrict__ T21, const float* __restrict__ depth, int H, int W, double* __restrict__ res,
+              double* __restrict__ zbuf, double* __restrict__ dbuf, double* __restrict__ ratio) {
+  __shared__ unsigned long long key[SC_MAX];
+  __shared__ int wsum[SC_THREADS / 32];
+  __shared__ int total_s;
+  if (res[TR_GATE] == 0.0) return;
+  const int t = threadIdx.x;
+  int P = 1; while (P < n) P <<= 1;
+  double Pm[3][4];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 4; ++b) Pm[a][b] = T21[4 * a + b];
+  for (int i = t; i < P; i += SC_THREADS) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      // normalised coordinates as the host computes them: (kp - [cx, cy]) / [fx, fy]
+      const double u0 = (kp_ref[2 * i] - cx) / fx, v0 = (kp_ref[2 * i + 1] - cy) / fy;
+      const double u1 = (kp_cur[2 * i] - cx) / fx, v1 = (kp_cur[2 * i + 1] - cy) / fy;
+      double X[4];
+      triangulate_dlt(Pm, u0, v0, u1, v1, X);
+      const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
+      zbuf[i] = Pm[2][0] * x + Pm[2][1] * y + Pm[2][2] * z + Pm[2][3];
+      const int px = (int)kp_cur[2 * i], py = (int)kp_cur[2 * i + 1];                    // truncation toward zero (ops_3d.py:35-37)
+      if (px >= 0 && px < W && py >= 0 && py < H) {
+        const unsigned lin = (unsigned)py * (unsigned)W + (unsigned)px;
+        dbuf[i] = (double)depth[lin];
+        k = ((unsigned long long)lin << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);   // equal pixels: the LAST keypoint sorts first
+      }
+    }
+    key[i] = k;
+  }
+  __syncthreads();
+  // bitonic sort, ascending
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < P; i += SC_THREADS) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const unsigned long long a = key[i], b = key[j];
+          if ((a > b) == up) { key[i] = b; key[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // heads of the runs with a usable ratio, compacted in order: thread t owns the slots [t * per, (t + 1) * per)
+  const int per = P / SC_THREADS > 0 ? P / SC_THREADS : 1;
+  const int j0 = t * per;
+  int cnt = 0;
+  double rloc[SC_MAX / SC_THREADS];
+  for (int q = 0; q < per; ++q) {
+    const int j = j0 + q;
+    if (j >= P) break;
+    const unsigned long long k = key[j];
+    if (k == ~0ull) continue;
+    if (j > 0 && (key[j - 1] >> 32) == (k >> 32)) continue;                  // an earlier keypoint of the same pixel: overwritten
+    const int i = (int)(0xffffffffu - (unsigned)(k & 0xffffffffu));
+    double zt = zbuf[i];
+    zt = zt < 0 ? 0.0 : zt;
+    const double dp = dbuf[i];
+    if (dp > 0 && zt > 0) rloc[cnt++] = zt / dp;
+  }
+  int incl = cnt;
+  for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if ((t & 31) >= off) incl += v; }
+  if ((t & 31) == 31) wsum[t >> 5] = incl;
+  __syncthreads();
+  if (t == 0) { int a = 0; for (int w8 = 0; w8 < SC_THREADS / 32; ++w8) { const int v = wsum[w8]; wsum[w8] = a; a += v; } total_s = a; }
+  __syncthreads();
+  const int base = wsum[t >> 5] + incl - cnt;
+  for (int q = 0; q < cnt; ++q) ratio[base + q] = rloc[q];
+  if (t == 0) res[TR_NVALID] = (double)total_s;
+}
+
+size_t essential_tail_workspace_bytes(int N) { return (size_t)N * 8 * 3 + (size_t)N * 4 + 9 * 8 + 12 * 8 + 1024; }
+
+int essential_tail(const double* E, const int32_t* info, const double* gric, int R, const double* kp_cur, const double* kp_ref, int N,
+                   double fx, double fy, double cx, double cy, const double* h_gric, const float* depth, int H, int W, int min_samples,
+                   int max_trials, double stop_prob, double thr, void* workspace, size_t ws_bytes, double* res, uint8_t* pose_mask,
+                   int32_t* pose_info, cudaStream_t s) {
+  DFVO_REQUIRE(E && info && gric && kp_cur && kp_ref && h_gric && depth && workspace && res && pose_mask && pose_info, DFVO_EINVAL, "essential_tail args");
+  DFVO_REQUIRE(R >= 1 && R <= 32 && N >= 1 && N <= SC_MAX && min_samples >= 1 && min_samples <= SR_MAX_SAMPLES, DFVO_EINVAL, "essential_tail: R=%d N=%d", R, N);
+  DFVO_REQUIRE(ws_bytes >= essential_tail_workspace_bytes(N), DFVO_EINVAL, "essential_tail workspace too small");
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  auto take = [&](size_t bytes) { uint8_t* p = w; w += (bytes + 127) & ~(size_t)127; return p; };
+  double* zbuf = (double*)take((size_t)N * 8);
+  double* dbuf = (double*)take((size_t)N * 8);
+  double* ratio = (double*)take((size_t)N * 8);
+  int32_t* perm = (int32_t*)take((size_t)N * 4);
+  double* E_best = (double*)take(9 * 8);
+  double* T21 = (double*)take(12 * 8);
+  DFVO_LAUNCH(k_track_pick, dim3(1), dim3(32), 0, s, info, gric, E, R, res, E_best);
+  DFVO_CUDA(cudaMemsetAsync(pose_info, 0, 5 * sizeof(int32_t), s));
+  DFVO_LAUNCH(k_recover_pose_vote, dim3(cdiv(4 * N, 256)), dim3(256), 0, s, (const double*)E_best, kp_cur, kp_ref, N, fx, cx, cy, 50.0, pose_mask, pose_info);
+  DFVO_LAUNCH(k_recover_pose_pick, dim3(cdiv(N, 256)), dim3(256), 0, s, (const double*)E_best, N, res + TR_RT, pose_mask, pose_info);
+  DFVO_LAUNCH(k_track_gate, dim3(1), dim3(32), 0, s, res, (const int32_t*)pose_info, h_gric, R, N, T21);
+  DFVO_LAUNCH(k_scale_chain, dim3(1), dim3(SC_THREADS), 0, s, kp_ref, kp_cur, N, fx, fy, cx, cy, (const double*)T21, depth, H, W, res, zbuf, dbuf, ratio);
+  DFVO_LAUNCH(k_scale_ransac, dim3(1), dim3(SR_THREADS), 0, s, (const double*)ratio, N, min_samples, max_trials, stop_prob, thr, res, perm,
+              (const double*)(res + TR_NVALID), (const double*)(res + TR_GATE));
+  DFVO_CHECK_LAUNCH();
+  return DFVO_OK;
+}
+
 }  // namespace dfvo

@@ -27,6 +27,20 @@ int pnp_ransac(const double* obj, const double* img, int N, const int32_t* perm,
                double fy, double cx, double cy, double threshold, double prob, void* workspace, size_t ws_bytes, double* rt_out,
                int32_t* info, cudaStream_t s);
 
+// sklearn RANSACRegressor scale fit on the device, walking NumPy's MT19937 stream (ransac.cu::k_scale_ransac).  io: device [4 + 313]
+// doubles = {scale, status, trials, inliers} + key[624], pos as uint32; perm_scratch: device [n] int32
+int scale_ransac(const double* ratio, int n, int min_samples, int max_trials, double stop_prob, double thr, double* io, int32_t* perm_scratch,
+                 cudaStream_t s);
+
+// fused tail of the E-tracker after essential_ransac (ransac.cu): best repeat -> recoverPose -> validity vote / cheirality gate ->
+// depth ratios -> scale regressor, no host round trip.  res: device [335 + 5 R] doubles (layout in ransac.cu), its [4..316] hold the
+// host generator's MT19937 state on entry.  h_gric: device [1] GRIC of the homography model (the caller orders the stream after it).
+size_t essential_tail_workspace_bytes(int N);
+int essential_tail(const double* E, const int32_t* info, const double* gric, int R, const double* kp_cur, const double* kp_ref, int N,
+                   double fx, double fy, double cx, double cy, const double* h_gric, const float* depth, int H, int W, int min_samples,
+                   int max_trials, double stop_prob, double thr, void* workspace, size_t ws_bytes, double* res, uint8_t* pose_mask,
+                   int32_t* pose_info, cudaStream_t s);
+
 // stage entry: EPnP (cv2.solvePnP(flags=SOLVEPNP_EPNP) as solvePnPRansac's minimal solver uses it) on M independent 5-point
 // samples; coop: 1 = lane-cooperative kernel, 0 = one thread per sample, -1 = the default of the build
 int epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop, double* rt,

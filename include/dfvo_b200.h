@@ -207,6 +207,29 @@ int dfvo_essential_ransac(const double* p1, const double* p2, int N, const int32
  * findEssentialMat / solvePnPRansac draw for `count` correspondences depend only on `count`.  HOST function:
  * out_host [n_subsets][model_points] int32. */
 int dfvo_cv_subset_stream_host(int count, int model_points, int n_subsets, int32_t* out_host);
+/* The scale fit of find_scale_from_depth (E_tracker.py:618-641): RANSACRegressor(LinearRegression(fit_intercept=False),
+ * min_samples, max_trials, stop_probability, residual_threshold).fit(ratio[:, None], ones).estimator_.coef_[0, 0], with the sampling
+ * drawn from NumPy's global MT19937 exactly as scikit-learn draws it.  ratio [n] float64 (device).  io (device, 4 + 313 doubles):
+ * in: doubles [4..] hold the generator state as 625 uint32 (key[624], pos -- np.random.get_state()[1:3]); out: io[0] = scale,
+ * io[1] = 1 (ok) / -1 (no consensus: the reference raises ValueError), io[2] = trials, io[3] = inliers, and the advanced
+ * generator state for np.random.set_state().  perm_scratch: device [n] int32. */
+int dfvo_scale_ransac(const double* ratio, int n, int min_samples, int max_trials, double stop_prob, double threshold,
+                      double* io, int32_t* perm_scratch, void* stream);
+/* Everything of the hybrid tracker between "the essential-matrix repeats are done" and "pose and scale are known" in one enqueue, no
+ * host round trip (dfvo.py:165-193): the first repeat with the most inliers (E_tracker.py:278-281), cv2.recoverPose on its E (:292-300),
+ * the validity vote H_gric > E_gric (:286-290), and -- when the pose stands and |t| != 0 -- find_scale_from_depth (:571-643): triangulation
+ * of the normalised keypoints with inv([R|t]), CNN depth at int(kp_cur), last-writer-wins per pixel, depth ratios in row-major pixel
+ * order, RANSACRegressor with NumPy's generator state (dfvo_scale_ransac).  E [R][9], info [R][4], gric [R]: outputs of
+ * dfvo_essential_ransac; h_gric [1]: GRIC of dfvo_homography_ransac (the caller makes the stream wait for it); depth [H][W] float32
+ * (pre-processed, dfvo_depth_post).  res (device, 335 + 5 R doubles): in: [4..316] = generator state (625 uint32); out: [0] scale,
+ * [1] status (1 fitted, -1 no consensus, -2 fewer than 11 ratios, -3 pose rejected: scale recovery not run, generator untouched),
+ * [2] trials, [3] inliers, [4..316] advanced generator state, [317] best repeat, [318] vote, [319] H_gric, [320] cheirality count,
+ * [321] valid ratios, [322] gate, [323..334] R|t of recoverPose, [335..) E_gric [R], info [R][4] as doubles.  N <= 4096. */
+size_t dfvo_essential_tail_workspace_bytes(int N);
+int dfvo_essential_tail(const double* E, const int32_t* info, const double* gric, int R, const double* kp_cur, const double* kp_ref, int N,
+                        double fx, double fy, double cx, double cy, const double* h_gric, const float* depth, int H, int W,
+                        int min_samples, int max_trials, double stop_prob, double threshold, void* workspace, size_t workspace_bytes,
+                        double* res, uint8_t* pose_mask, int32_t* pose_info, void* stream);
 /* cv::triangulatePoints([I|0], T_21[:3], x1, x2) followed by X2 = T_21[:3] X / X_w (ops_3d.py:44-67): x1, x2
  * [N][2] normalised (float64), T21 [12] row-major 3x4 -> depth2 [N] = z of the point in view 2. */
 int dfvo_triangulate_depth(const double* x1, const double* x2, int N, const double* T21, double* depth2, void* stream);

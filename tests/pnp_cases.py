@@ -163,3 +163,90 @@ def check_epnp_minimal(engine, samples=6):
         worst = [max(worst[0], ang2), max(worst[1], dt2)]
     assert worst[0] < 1e-4 and worst[1] < 1e-4, ("vs cv2 EPNP", worst)
     return worst
+
+
+def check_scale_ransac_vs_sklearn(engine, cases=40):
+    """Engine.ransac_scale (csrc/ransac.cu::k_scale_ransac: the RANSAC trial loop on the device, fed with NumPy's MT19937 state) against
+    sklearn.linear_model.RANSACRegressor as E_tracker.py:626-636 calls it, from the same generator state: same scale (1e-12 relative;
+    the final refit's long dot products are summed in a different order than BLAS does) and the SAME generator position afterwards
+    (checked by drawing from both) -- over sample counts that exercise scikit-learn's three sampling branches' two reachable ones
+    (permutation for n < 300, tracking selection above) and inlier ratios from 20 % to 100 %."""
+    from sklearn import linear_model
+    from b200 import hostmath
+    rs = np.random.RandomState(99)
+    worst = 0.0
+    for case in range(cases):
+        n = int(rs.choice([12, 40, 150, 299, 301, 700, 1500, 2000]))
+        w = rs.uniform(0.2, 1.0)
+        s_true = rs.uniform(0.5, 20.0)
+        x = (1.0 / s_true) * (1.0 + rs.standard_normal(n) * 0.01)
+        bad = rs.rand(n) > w
+        x[bad] = rs.uniform(0.01, 3.0, int(bad.sum()))
+        seed = 1000 + case
+        np.random.seed(seed)
+        np.random.rand(case % 7 * 89)                       # leave the generator at an arbitrary position (incl. near the 624 wrap)
+        st0 = np.random.get_state()
+        ransac = linear_model.RANSACRegressor(estimator=linear_model.LinearRegression(fit_intercept=False), min_samples=3, max_trials=100,
+                                              stop_probability=0.99, residual_threshold=0.1)
+        ransac.fit(x.reshape(-1, 1), np.ones((n, 1)))
+        want = float(ransac.estimator_.coef_[0, 0])
+        after_ref = np.random.randint(0, 2 ** 31 - 1, 4)
+        np.random.set_state(st0)
+        got = engine.ransac_scale(x, 3, 100, 0.99, 0.1, np.random)
+        after_dev = np.random.randint(0, 2 ** 31 - 1, 4)
+        np.random.set_state(st0)
+        host = hostmath.ransac_scale(x, 3, 100, 0.99, 0.1, np.random)
+        assert np.array_equal(after_ref, after_dev), ("generator position differs from sklearn's", case, n)
+        assert abs(got - want) <= 1e-12 * abs(want), (case, n, got, want)
+        assert abs(host - want) <= 1e-12 * abs(want)
+        worst = max(worst, abs(got - want) / abs(want))
+    return worst
+
+
+def check_fused_tail_vs_stepwise(engine):
+    """Engine.essential_tail (best repeat -> recoverPose -> GRIC vote -> cheirality gate -> depth ratios -> scale regressor on the
+    device, one read) against the step-by-step host orchestration (tracking.compute_pose_2d2d + find_scale_from_depth) from the same
+    generator state: same pose (bit-equal: same kernels on the same E), same vote, same scale to 1e-12 (T_21 is inverted
+    analytically on the device, by LAPACK on the host) and the same generator position afterwards -- moving and still camera,
+    0 / 30 / 60 % outliers."""
+    K = synthdata.kitti_intrinsics()
+    cases = {"out00": dict(seed=31, outlier_frac=0.0), "out30": dict(seed=32, outlier_frac=0.3), "out60": dict(seed=33, outlier_frac=0.6),
+             "still": dict(seed=34, outlier_frac=0.1, zero_motion=True)}
+    rt = engine.rt
+    seen_scale = seen_reject = 0
+    for name, kw in cases.items():
+        kp_ref, kp_cur, info = synthdata.correspondences(n=2000, **kw)
+        n = kp_ref.shape[0]
+        depth = info["depth"].astype(np.float32)
+        dp32 = (depth * ((depth < 50) & (depth > 0))).astype(np.float32)
+        # ---- step by step
+        np.random.seed(4869)
+        r = tracking.compute_pose_2d2d(engine, kp_ref, kp_cur, K)
+        scale_a = None
+        if np.linalg.norm(r["t"]) != 0:
+            pose = np.eye(4); pose[:3, :3] = r["R"]; pose[:3, 3:] = r["t"]
+            scale_a = tracking.find_scale_from_depth(engine, kp_ref, kp_cur, np.linalg.inv(pose), dp32.astype(np.float64), K)
+        after_a = np.random.randint(0, 2 ** 31 - 1, 4)
+        # ---- fused
+        np.random.seed(4869)
+        perms = []
+        for _ in range(5):
+            order = np.arange(0, n, 1)
+            np.random.shuffle(order)
+            perms.append(order)
+        b_ref, b_cur, b_depth = rt.from_host(kp_ref), rt.from_host(kp_cur), rt.from_host(dp32)
+        h = engine.homography_launch(b_cur, b_ref, n)
+        w = engine.essential_launch(b_cur, b_ref, n, perms, K, threshold=0.2)
+        o = engine.essential_tail(w, h, b_cur, b_ref, n, K, b_depth, np.random)
+        after_b = np.random.randint(0, 2 ** 31 - 1, 4)
+        assert o["valid"] == r["valid"] and np.array_equal(o["R"], r["R"]) and np.array_equal(o["t"], r["t"]), name
+        assert o["cheirality"] == r["cheirality"] and np.array_equal(o["ransac_info"], r["ransac_info"]) and np.array_equal(o["E_gric"], r["E_gric"])
+        assert np.array_equal(after_a, after_b), ("generator position", name)
+        if scale_a is None:
+            assert o["scale"] == -1 and o["scale_status"] == -3
+            seen_reject += 1
+        else:
+            assert abs(o["scale"] - scale_a) <= 1e-12 * abs(scale_a), (name, o["scale"], scale_a)
+            seen_scale += 1
+    assert seen_scale >= 2 and seen_reject >= 1
+    return seen_scale, seen_reject

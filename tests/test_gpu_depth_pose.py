@@ -197,6 +197,16 @@ def test_epnp_cooperative_vs_sequential_vs_cv2(dev_lib):
     pnp_cases.check_epnp_minimal(_gpu_engine(), samples=64)
 
 
+def test_scale_ransac_on_device_vs_sklearn(dev_lib):
+    import pnp_cases
+    pnp_cases.check_scale_ransac_vs_sklearn(_gpu_engine(), cases=60)
+
+
+def test_fused_tracker_tail_vs_stepwise(dev_lib):
+    import pnp_cases
+    pnp_cases.check_fused_tail_vs_stepwise(_gpu_engine())
+
+
 def test_pnp_tracker_vs_reference_golden(dev_lib):
     import pnp_cases
     ang, dt = pnp_cases.check_vs_reference_golden(_gpu_engine(), np.load(os.path.join(G, "trackers_2000.npz")))

@@ -28,6 +28,15 @@ def test_epnp_cooperative_vs_sequential_vs_cv2(hostsim_lib):
     print("EPnP minimal solver vs cv2: %.2e rad, %.2e" % tuple(worst))
 
 
+def test_scale_ransac_on_device_vs_sklearn(hostsim_lib):
+    worst = pnp_cases.check_scale_ransac_vs_sklearn(_engine(hostsim_lib), cases=24)
+    print("scale RANSAC vs sklearn: worst relative difference %.2e" % worst)
+
+
+def test_fused_tracker_tail_vs_stepwise(hostsim_lib):
+    pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib))
+
+
 def test_pnp_tracker_vs_reference_golden(hostsim_lib):
     worst = pnp_cases.check_vs_reference_golden(_engine(hostsim_lib), np.load(os.path.join(G, "trackers_2000.npz")))
     print("worst rotation / relative translation difference: %.2e rad, %.2e" % worst)
