@@ -665,7 +665,8 @@ def run_b200(args):
     def build_pipe(precision, overlap_, inflight_):
         np.random.seed(4869 + rank)
         p = pipeline.FramePipeline(K, H, W, precision=precision, runtime=rt, overlap=overlap_, inflight=inflight_, inject=inject,
-                                   tracker_thread=overlap_ and os.environ.get("DFVO_TRACKER_THREAD", "1") != "0")
+                                   tracker_thread=overlap_ and os.environ.get("DFVO_TRACKER_THREAD", "0") == "1",
+                                   pipelined=overlap_ and os.environ.get("DFVO_PIPELINED", "1") != "0")
         p.load_weights(flow_w, enc, dec)
         return p
 
@@ -676,7 +677,7 @@ def run_b200(args):
         l0 = lib.dfvo_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         submit, lat = {}, []
-        lag = pipe.inflight if pipe.overlap else 0
+        lag = pipe.lag
         barrier()
         if clocks:
             clocks.mark(True)

@@ -50,7 +50,7 @@ class _ForkJoin:
 
 class FramePipeline:
     def __init__(self, K, height=376, width=1241, cfg=None, precision=native.PREC_BF16, runtime=None, rng=np.random,
-                 overlap=False, engine=None, inflight=1, inject=None, tracker_thread=False):
+                 overlap=False, engine=None, inflight=1, inject=None, tracker_thread=False, pipelined=False):
         """K = [cx, cy, fx, fy].
 
         inject: optional ``callable(pipeline, frame_state)`` run by ``infer`` right after the two networks of a frame were
@@ -66,6 +66,11 @@ class FramePipeline:
         inflight=2 (overlap mode only): a second, independent network engine, so the networks of two consecutive frames run
         concurrently (their small-grid phases fill each other's idle SMs) and tracking lags by two frames: ``step``
         returns the pose of frame t-2, ``flush()`` the remaining ones (a list).  Same poses again.
+        pipelined=True (overlap mode only): the tracker of a frame is split into its enqueue half and its read half
+        (track_launch / track_finish): ``step(t)`` first reads the result of the tracker enqueued by the previous step, then enqueues
+        the networks of frame t, then enqueues the tracker of frame t-inflight and returns WITHOUT waiting for it -- the tracker's
+        kernels (~1 ms of dependent small launches) run while the caller fetches the next frame.  ``step`` then returns the pose of
+        frame t-inflight-1 (``self.lag`` steps behind) and ``flush()`` the remaining ones.  Same arithmetic, generator order and poses.
         tracker_thread=True (overlap mode only): the tracker runs on its own host thread (one frame at a time, in frame order, so
         the RNG stream and the poses are unchanged).  ``step(img)`` enqueues the networks of ``img``, hands the frame to the tracker
         thread and then waits for the pose of frame t-inflight, which that thread has been working on meanwhile: the host work
@@ -93,6 +98,9 @@ class FramePipeline:
         assert self.inflight in (1, 2, 3)
         self.nslots = self.inflight + 2 if self.overlap else 2
         self.fused_tail = os.environ.get("DFVO_FUSED_TAIL", "1") != "0"     # device-side tail of the E branch (track_fused)
+        self.pipelined = bool(pipelined) and self.overlap and not tracker_thread
+        self._tok = None             # pipelined mode: (frame state, token of track_launch, host ms so far) of the tracker in flight
+        self.lag = (self.inflight + (1 if self.pipelined else 0)) if self.overlap else 0     # step(t) returns the pose of frame t - lag
         self.tracker_thread = bool(tracker_thread) and self.overlap
         self._thr = None
         self.pending = []            # overlap mode: frames whose networks are enqueued but which are not tracked yet
@@ -197,6 +205,12 @@ class FramePipeline:
 
     def track(self, cur, ref=None):
         """dfvo.py:121-262 (hybrid).  Returns the relative pose cur -> ref as a 4x4."""
+        return self.track_finish(self.track_launch(cur, ref))
+
+    def track_launch(self, cur, ref=None):
+        """First half of `track`: everything up to the last enqueue.  Returns a token for `track_finish`.  On the fused E branch the
+        tracker's kernels are still running when this returns (the caller may do other host work -- e.g. enqueue the next frame's
+        networks -- before it finishes the frame); every other branch is finished here and the token just carries the pose."""
         c, eng, K = self.cfg, self.eng, self.K
         ref = ref or self.ref
         fwd = cur.fwd if cur.fwd is not None else eng.flow_fwd          # (subclasses may leave the flows in the engine's buffers)
@@ -208,10 +222,23 @@ class FramePipeline:
             good, n, kp1_buf, kp2_buf = eng.select_bestn(diff, fwd, c.kp_selection.bestN.num_bestN)
         self.last = dict(good=good, n=n, mode="const")
         if not good:
-            return self.motion.copy()                                     # constant motion (dfvo.py:157-161)
+            return dict(pose=self.motion.copy())                          # constant motion (dfvo.py:157-161)
         iterative = c.scale_recovery.method == "iterative"
         if not iterative and 10 < n <= eng.TAIL_MAX_N and self.fused_tail:
-            return self.track_fused(cur, ref, kp1_buf, kp2_buf, n)
+            return self.track_fused_launch(cur, ref, kp1_buf, kp2_buf, n)
+        return dict(pose=self.track_stepwise(cur, ref, kp1_buf, kp2_buf, n))
+
+    def track_finish(self, tok):
+        """Second half of `track`: the relative pose cur -> ref (4x4)."""
+        if "pose" in tok:
+            return tok["pose"]
+        return self.track_fused_finish(tok)
+
+    def track_stepwise(self, cur, ref, kp1_buf, kp2_buf, n):
+        """The E branch with the host in the loop after every stage (iterative scale recovery, tiny / huge keypoint sets,
+        DFVO_FUSED_TAIL=0)."""
+        c, eng, K = self.cfg, self.eng, self.K
+        iterative = c.scale_recovery.method == "iterative"
         kp_ref = kp1_buf.numpy()[:n]
         kp_cur = kp2_buf.numpy()[:n]
         # ---- E-tracker (dfvo.py:165-193).  The homography vote runs on a host worker thread; the pose-dependent device
@@ -243,7 +270,7 @@ class FramePipeline:
             self.last["mode"] = "PnP"
         return hybrid
 
-    def track_fused(self, cur, ref, kp1_buf, kp2_buf, n):
+    def track_fused_launch(self, cur, ref, kp1_buf, kp2_buf, n):
         """The E branch of `track` with the device-side tail (tracking.Engine.essential_tail): after the keypoint count is known the
         host draws the five shuffles, enqueues the homography model, the essential-matrix repeats and the fused tail, and reads ONE
         packed result -- instead of eleven small reads with host arithmetic in between (keypoints, RANSAC info, GRIC, mask, pose,
@@ -258,7 +285,14 @@ class FramePipeline:
             perms.append(order)
         h = eng.homography_launch(kp2_buf, kp1_buf, n)
         w = eng.essential_launch(kp2_buf, kp1_buf, n, perms, K, threshold=c.e_tracker.ransac.reproj_thre)
-        o = eng.essential_tail(w, h, kp2_buf, kp1_buf, n, K, cur.depth, self.rng, rs.min_samples, rs.max_trials, rs.stop_prob, rs.thre)
+        tail = eng.essential_tail_launch(w, h, kp2_buf, kp1_buf, n, K, cur.depth, self.rng, rs.min_samples, rs.max_trials, rs.stop_prob, rs.thre)
+        return dict(tail=tail, w=w, ref=ref, kp1_buf=kp1_buf, kp2_buf=kp2_buf, n=n, last=self.last)
+
+    def track_fused_finish(self, tok):
+        eng = self.eng
+        w, ref, kp1_buf, kp2_buf, n = tok["w"], tok["ref"], tok["kp1_buf"], tok["kp2_buf"], tok["n"]
+        self.last = tok["last"]
+        o = eng.essential_tail_finish(tok["tail"])
         self.last.update(valid=o["valid"], inliers=None, inlier_handle=(w, o["best"]), mode="E", scale=None)
         hybrid = np.eye(4)
         hybrid[:3, :3] = o["R"]
@@ -348,20 +382,31 @@ class FramePipeline:
     # ------------------------------------------------------------------ driver step
     def _advance(self, cur, ref):
         """Track `cur` against `ref` and chain the global pose (dfvo.py:358-403 loop body)."""
-        fid = cur.id
+        return self._advance_finish(self._advance_launch(cur, ref))
+
+    def _advance_launch(self, cur, ref):
         if ref is None:
+            return (cur, None, 0.0)
+        t0 = time.perf_counter()
+        tok = self.track_launch(cur, ref)
+        return (cur, tok, (time.perf_counter() - t0) * 1e3)
+
+    def _advance_finish(self, launched):
+        cur, tok, ms0 = launched
+        fid = cur.id
+        if tok is None:
             self.global_pose = np.eye(4)
             self.motion = np.eye(4)
         else:
             t0 = time.perf_counter()
-            rel = self.track(cur, ref)
-            self.track_ms[fid] = (time.perf_counter() - t0) * 1e3      # host time of the tracker path (includes its device waits)
+            rel = self.track_finish(tok)
+            self.track_ms[fid] = ms0 + (time.perf_counter() - t0) * 1e3      # host time of the tracker path (includes its device waits)
             self.motion = rel.copy()
             # update_global_pose (dfvo.py:109-119): t_w += R_w t ; R_w = R_w R
             self.global_pose[:3, 3:] = self.global_pose[:3, :3] @ rel[:3, 3:] + self.global_pose[:3, 3:]
             self.global_pose[:3, :3] = self.global_pose[:3, :3] @ rel[:3, :3]
         self.poses[fid] = self.global_pose.copy()
-        self.modes[fid] = self.last.get("mode") if ref is not None else None
+        self.modes[fid] = self.last.get("mode") if tok is not None else None
         return self.poses[fid]
 
     def step(self, img):
@@ -374,6 +419,9 @@ class FramePipeline:
             pose = self._advance(cur, self.ref)
             self.ref = cur
             return pose
+        pose = None
+        if self.pipelined and self._tok is not None:            # the tracker enqueued by the previous step
+            pose = self._finish_inflight()
         with self.rt.on_stream(self.s_nets[fid % len(self.engs)]):
             self._depth_done = None
             cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
@@ -383,9 +431,26 @@ class FramePipeline:
         self.ref = cur
         if self.tracker_thread:
             return self._hand_over(cur)
+        if self.pipelined:
+            self.pending.append(cur)
+            if len(self.pending) > self.inflight:
+                self._launch_oldest()
+            return pose
         pose = self._track_oldest() if len(self.pending) >= self.inflight else None
         self.pending.append(cur)
         return pose
+
+    def _launch_oldest(self):
+        nxt = self.pending.pop(0)
+        with self.rt.on_stream(self.s_trk):
+            self.rt.wait_event(nxt.ready)
+            self._tok = self._advance_launch(nxt, self.trk_ref)
+        self.trk_ref = nxt
+
+    def _finish_inflight(self):
+        launched, self._tok = self._tok, None
+        with self.rt.on_stream(self.s_trk):
+            return self._advance_finish(launched)
 
     # ---- tracker thread -------------------------------------------------------------------------------------------------
     def _start_tracker_thread(self):
@@ -457,6 +522,13 @@ class FramePipeline:
         """Overlap mode: track the frames whose networks are still in flight; returns the last pose for inflight=1 (None if
         there is none), the list of remaining poses for inflight=2."""
         poses = []
+        if self.pipelined:
+            if self._tok is not None:
+                poses.append(self._finish_inflight())
+            while self.pending:
+                self._launch_oldest()
+                poses.append(self._finish_inflight())
+            return poses
         if self.tracker_thread:
             last = self.stage - 1
             if self._thr is not None and last >= 0:

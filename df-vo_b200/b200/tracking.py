@@ -245,7 +245,12 @@ class Engine:
         (dfvo_essential_tail): best repeat, recoverPose, the GRIC vote against the homography handle `h`, the cheirality gate, the depth
         ratios and the scale regressor (with `rng`'s MT19937 state; the advanced state is installed back).  Returns a dict with
         R, t (identity / zero when the pose is rejected, as compute_pose_2d2d + resolve_validity give them), valid, cheirality, best,
-        E_gric, H_gric, ransac_info, scale (-1 when not recovered), scale_status, and `w` for a lazy inlier mask."""
+        E_gric, H_gric, ransac_info, scale (-1 when not recovered), scale_status, and `w` for a lazy inlier mask.
+        = essential_tail_launch + essential_tail_finish; between the two `rng` must not be used (its state travels with the launch)."""
+        return self.essential_tail_finish(self.essential_tail_launch(w, h, kp_cur_buf, kp_ref_buf, n, K, depth_buf, rng, min_samples,
+                                                                     max_trials, stop_prob, thre))
+
+    def essential_tail_launch(self, w, h, kp_cur_buf, kp_ref_buf, n, K, depth_buf, rng, min_samples=3, max_trials=100, stop_prob=0.99, thre=0.1):
         cx, cy, fx, fy = K
         R = w["info"].shape[0]
         cap = w["cap"]
@@ -266,6 +271,10 @@ class Engine:
                                                     cx, cy, h["gric"].ptr, depth_buf.ptr, self.H, self.W, int(min_samples), int(max_trials),
                                                     float(stop_prob), float(thre), c["ws"].ptr, c["ws"].shape[0], c["res"].ptr,
                                                     w["pmask"].ptr, w["pinfo"].ptr, self.rt.stream_ptr()))
+        return dict(c=c, w=w, n=n, R=R, rng=rng, st=st)
+
+    def essential_tail_finish(self, tok):
+        c, w, n, R, rng, st = tok["c"], tok["w"], tok["n"], tok["R"], tok["rng"], tok["st"]
         o = c["res"].numpy()                                        # the one synchronising read
         u = o[4:317].view(np.uint32)
         rng.set_state(("MT19937", u[:624].copy(), int(u[624]), st[3], st[4]))

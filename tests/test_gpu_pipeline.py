@@ -10,11 +10,11 @@ from b200 import native, pipeline, runtime as rt_mod
 pytestmark = pytest.mark.gpu
 
 
-def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1, tracker_thread=False):
+def run(overlap, frames, analytic, K, h, w, enc, dec, flow_w, inflight=1, tracker_thread=False, pipelined=False):
     rt = rt_mod.CudaRuntime(0)
     rt_mod.set_runtime(rt)
     np.random.seed(4869)
-    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight, tracker_thread=tracker_thread)
+    p = pipeline.FramePipeline(K, h, w, precision=native.PREC_BF16, runtime=rt, overlap=overlap, inflight=inflight, tracker_thread=tracker_thread, pipelined=pipelined)
     p.load_weights(flow_w, enc, dec)
     base_infer = p.infer
     net_flows = {}
@@ -60,7 +60,8 @@ def test_overlap_pipeline_equals_in_order(dev_lib):
     pb, fb, all_b = run(True, frames, analytic, K, h, w, enc, dec, flow_w)
     pc, fc, all_c = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2)       # two network engines in flight
     pd, fd, all_d = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2, tracker_thread=True)   # + tracker on its own host thread
-    assert len(pa) == n and len(pb) == n and len(pc) == n and len(pd) == n
+    pe, fe, all_e = run(True, frames, analytic, K, h, w, enc, dec, flow_w, inflight=2, pipelined=True)        # tracker split into enqueue / read halves
+    assert len(pa) == n and len(pb) == n and len(pc) == n and len(pd) == n and len(pe) == n
     for i in range(1, n):
         assert (fa[i][0] == fb[i][0]).all() and (fa[i][1] == fb[i][1]).all(), "network flow of frame %d differs" % i
         assert (fa["depth"][i] == fb["depth"][i]).all(), "network depth of frame %d differs" % i
@@ -71,4 +72,5 @@ def test_overlap_pipeline_equals_in_order(dev_lib):
         assert np.array_equal(all_a[i], all_c[i]), "pose of frame %d differs with two frames in flight" % i
         assert np.array_equal(all_a[i], all_d[i]), "pose of frame %d differs with the tracker thread" % i
         assert np.array_equal(pc[i], pd[i]), "step() / flush() hand out different poses with the tracker thread (frame %d)" % i
+        assert np.array_equal(all_a[i], all_e[i]) and np.array_equal(pc[i], pe[i]), "pose of frame %d differs in the pipelined-tracker mode" % i
     assert not np.allclose(all_a[-1], np.eye(4))

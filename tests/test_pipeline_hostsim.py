@@ -12,7 +12,7 @@ from oracle import seqdata
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("overlap,iterative,threaded", [(False, False, False), (True, True, False), (True, False, True)])
+@pytest.mark.parametrize("overlap,iterative,threaded", [(False, False, False), (True, True, False), (True, False, True), (True, False, "pipelined")])
 def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative, threaded):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     from runtime import HostsimRuntime
@@ -51,15 +51,16 @@ def test_pipeline_matches_reference_driver(hostsim_lib, overlap, iterative, thre
         cfg.kp_selection.rigid_flow_kp.enable = True
         cfg.scale_recovery.method = "iterative"
     inflight = 2 if (iterative or threaded) else 1     # two frames in flight (tracker two frames behind); threaded: tracker on its own host thread
-    p = Injected(K, h, w, cfg=cfg, overlap=overlap, inflight=inflight, tracker_thread=threaded)
+    p = Injected(K, h, w, cfg=cfg, overlap=overlap, inflight=inflight, tracker_thread=(threaded is True), pipelined=(threaded == "pipelined"))
+    lag = p.lag
     if overlap:                          # two-stream mode: step(t) returns the pose of frame t-inflight, flush() the rest
-        for _ in range(inflight):
+        for _ in range(lag):
             assert p.step(None) is None
     tail = []
     for t in range(n):
         if not overlap:
             pose = p.step(None)
-        elif t + inflight < n:
+        elif t + lag < n:
             pose = p.step(None)
         else:
             if not tail:
