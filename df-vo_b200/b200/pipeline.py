@@ -67,9 +67,9 @@ class FramePipeline:
         concurrently (their small-grid phases fill each other's idle SMs) and tracking lags by two frames: ``step``
         returns the pose of frame t-2, ``flush()`` the remaining ones (a list).  Same poses again.
         pipelined=True (overlap mode only): the tracker of a frame is split into its enqueue half and its read half
-        (track_launch / track_finish): ``step(t)`` first reads the result of the tracker enqueued by the previous step, then enqueues
-        the networks of frame t, then enqueues the tracker of frame t-inflight and returns WITHOUT waiting for it -- the tracker's
-        kernels (~1 ms of dependent small launches) run while the caller fetches the next frame.  ``step`` then returns the pose of
+        (track_launch / track_finish): ``step(t)`` enqueues the networks of frame t, then reads the result of the tracker enqueued by
+        the previous step, then enqueues the tracker of frame t-inflight and returns WITHOUT waiting for it -- the tracker's kernels
+        (~1 ms of dependent small launches) run while the caller fetches the next frame and the next step enqueues its networks.  ``step`` then returns the pose of
         frame t-inflight-1 (``self.lag`` steps behind) and ``flush()`` the remaining ones.  Same arithmetic, generator order and poses.
         tracker_thread=True (overlap mode only): the tracker runs on its own host thread (one frame at a time, in frame order, so
         the RNG stream and the poses are unchanged).  ``step(img)`` enqueues the networks of ``img``, hands the frame to the tracker
@@ -96,7 +96,9 @@ class FramePipeline:
         self.overlap = bool(overlap)
         self.inflight = int(inflight) if self.overlap else 1
         assert self.inflight in (1, 2, 3)
-        self.nslots = self.inflight + 2 if self.overlap else 2
+        # buffer slots: a frame's buffers serve its own tracker and, as reference, the next frame's; the pipelined mode finishes a
+        # tracker AFTER the next frame's networks were enqueued, which needs one slot more
+        self.nslots = (self.inflight + 2 + (1 if (pipelined and not tracker_thread) else 0)) if self.overlap else 2
         self.fused_tail = os.environ.get("DFVO_FUSED_TAIL", "1") != "0"     # device-side tail of the E branch (track_fused)
         self.pipelined = bool(pipelined) and self.overlap and not tracker_thread
         self._tok = None             # pipelined mode: (frame state, token of track_launch, host ms so far) of the tracker in flight
@@ -420,8 +422,6 @@ class FramePipeline:
             self.ref = cur
             return pose
         pose = None
-        if self.pipelined and self._tok is not None:            # the tracker enqueued by the previous step
-            pose = self._finish_inflight()
         with self.rt.on_stream(self.s_nets[fid % len(self.engs)]):
             self._depth_done = None
             cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
@@ -432,6 +432,8 @@ class FramePipeline:
         if self.tracker_thread:
             return self._hand_over(cur)
         if self.pipelined:
+            if self._tok is not None:                            # the tracker enqueued by the previous step ran while the
+                pose = self._finish_inflight()                  # networks above were being enqueued
             self.pending.append(cur)
             if len(self.pending) > self.inflight:
                 self._launch_oldest()
