@@ -18,7 +18,10 @@ outputs on the device inside the timed region through the pipeline's official `i
 every step.  The 8 distinct frames cycle the SURVEY 8d outlier fractions {0, 0.3, 0.6} (E-RANSAC stops after ~1 / ~28 / ~410
 iterations) and contain one zero-translation frame (GRIC prefers the homography -> PnP fallback).
 
-The object timed is `b200.pipeline.FramePipeline` itself (`step(frame) -> pose`), two network engines in flight by default.
+The object timed is `b200.pipeline.FramePipeline` itself (`step(frame) -> pose`): three network engines in flight and the tracker
+split into its enqueue / read halves by default (`DFVO_INFLIGHT`, `DFVO_PIPELINED`, `DFVO_TRACKER_THREAD` select the other modes,
+all with identical poses); `e2e.latency_ms` is the time from handing a frame to `step` until its pose comes back, and
+`e2e.low_latency` / `e2e.in_order` report the two-engine same-step and the single-stream in-order pipelines next to it.
 
 Output: ONE JSON line (rank 0).  `value` = frames/s with frames already in HBM; `e2e` = the same metric through the public API
 (pinned host uint8 frames -> pose on the host) with H2D/D2H inside the timed region; `e2e_libs` = through the reference-API

@@ -653,14 +653,17 @@ int homography_ransac(const double* p1, const double* p2, int N, int max_iters, 
   const float thr2 = (float)(threshold * threshold);
   DFVO_LAUNCH(k_h_prepare, dim3(cdiv(N, 128)), dim3(128), 0, s, p1, p2, N, src, dst);
   DFVO_LAUNCH(k_h_init, dim3(1), dim3(32), 0, s, st, max_iters);
-  // rounds: a scene with a dominant plane stops inside the first; a general scene (no homography fits most points) runs all max_iters
-  const int bounds[3] = {0, 256, max_iters};
+  // rounds: a scene with a dominant plane (or no outliers) stops inside the first (measured 96 .. 124 iterations at 0 % outliers), a
+  // general scene at 30 % outliers inside the second (338 .. 669), anything worse runs all max_iters.  The sequential walk of a round
+  // costs ~0.16 us per subset, so the middle round saves ~0.2 ms of the homography chain exactly where that chain is the
+  // tracker's critical path (30 % outliers: essential-matrix chain 0.45 ms, homography chain 0.81 -> 0.6 ms)
+  const int bounds[4] = {0, 256, 768, max_iters};
   int prev_i1 = 0;
 #ifndef DFVO_HOSTSIM
   static bool attr_set = false;
   if (!attr_set) { DFVO_CUDA(cudaFuncSetAttribute(k_h_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
 #endif
-  for (int rd = 0; rd < 2; ++rd) {
+  for (int rd = 0; rd < 3; ++rd) {
     const int i0 = bounds[rd] < max_iters ? bounds[rd] : max_iters, i1 = bounds[rd + 1] < max_iters ? bounds[rd + 1] : max_iters;
     if (i1 <= i0) continue;
     DFVO_LAUNCH(k_h_round_begin, dim3(1), dim3(32), 0, s, st, ok, counts, N, prev_i1, i0, i1, prob, nd);

@@ -742,37 +742,44 @@ __global__ void k_track_gate(double* __restrict__ res, const int32_t* __restrict
 
 #define SC_THREADS 1024
 #define SC_MAX 4096
+// per keypoint (many blocks): normalise, triangulate, CNN depth at int(kp_cur), sort key (pixel index, then LAST keypoint first)
+__global__ void __launch_bounds__(128)
+k_scale_points(const double* __restrict__ kp_ref, const double* __restrict__ kp_cur, int n, double fx, double fy, double cx, double cy,
+               const double* __restrict__ T21, const float* __restrict__ depth, int H, int W, const double* __restrict__ res,
+               double* __restrict__ zbuf, double* __restrict__ dbuf, unsigned long long* __restrict__ keys) {
+  if (res[TR_GATE] == 0.0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Pm[3][4];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 4; ++b) Pm[a][b] = T21[4 * a + b];
+  // normalised coordinates as the host computes them: (kp - [cx, cy]) / [fx, fy]
+  const double u0 = (kp_ref[2 * i] - cx) / fx, v0 = (kp_ref[2 * i + 1] - cy) / fy;
+  const double u1 = (kp_cur[2 * i] - cx) / fx, v1 = (kp_cur[2 * i + 1] - cy) / fy;
+  double X[4];
+  triangulate_dlt(Pm, u0, v0, u1, v1, X);
+  const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
+  zbuf[i] = Pm[2][0] * x + Pm[2][1] * y + Pm[2][2] * z + Pm[2][3];
+  const int px = (int)kp_cur[2 * i], py = (int)kp_cur[2 * i + 1];                    // truncation toward zero (ops_3d.py:35-37)
+  unsigned long long k = ~0ull;
+  if (px >= 0 && px < W && py >= 0 && py < H) {
+    const unsigned lin = (unsigned)py * (unsigned)W + (unsigned)px;
+    dbuf[i] = (double)depth[lin];
+    k = ((unsigned long long)lin << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);   // equal pixels: the LAST keypoint sorts first
+  }
+  keys[i] = k;
+}
+
+// one block: sort the keys, keep the first entry of every pixel, compact the usable ratios in pixel order
 __global__ void __launch_bounds__(SC_THREADS)
-k_scale_chain(const double* __restrict__ kp_ref, const double* __restrict__ kp_cur, int n, double fx, double fy, double cx, double cy,
-              const double* __restrict__ T21, const float* __restrict__ depth, int H, int W, double* __restrict__ res,
-              double* __restrict__ zbuf, double* __restrict__ dbuf, double* __restrict__ ratio) {
+k_scale_chain(const unsigned long long* __restrict__ keys, int n, double* __restrict__ res, const double* __restrict__ zbuf,
+              const double* __restrict__ dbuf, double* __restrict__ ratio) {
   __shared__ unsigned long long key[SC_MAX];
   __shared__ int wsum[SC_THREADS / 32];
   __shared__ int total_s;
   if (res[TR_GATE] == 0.0) return;
   const int t = threadIdx.x;
   int P = 1; while (P < n) P <<= 1;
-  double Pm[3][4];
-  for (int a = 0; a < 3; ++a) for (int b = 0; b < 4; ++b) Pm[a][b] = T21[4 * a + b];
-  for (int i = t; i < P; i += SC_THREADS) {
-    unsigned long long k = ~0ull;
-    if (i < n) {
-      // normalised coordinates as the host computes them: (kp - [cx, cy]) / [fx, fy]
-      const double u0 = (kp_ref[2 * i] - cx) / fx, v0 = (kp_ref[2 * i + 1] - cy) / fy;
-      const double u1 = (kp_cur[2 * i] - cx) / fx, v1 = (kp_cur[2 * i + 1] - cy) / fy;
-      double X[4];
-      triangulate_dlt(Pm, u0, v0, u1, v1, X);
-      const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
-      zbuf[i] = Pm[2][0] * x + Pm[2][1] * y + Pm[2][2] * z + Pm[2][3];
-      const int px = (int)kp_cur[2 * i], py = (int)kp_cur[2 * i + 1];                    // truncation toward zero (ops_3d.py:35-37)
-      if (px >= 0 && px < W && py >= 0 && py < H) {
-        const unsigned lin = (unsigned)py * (unsigned)W + (unsigned)px;
-        dbuf[i] = (double)depth[lin];
-        k = ((unsigned long long)lin << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);   // equal pixels: the LAST keypoint sorts first
-      }
-    }
-    key[i] = k;
-  }
+  for (int i = t; i < P; i += SC_THREADS) key[i] = i < n ? keys[i] : ~0ull;
   __syncthreads();
   // bitonic sort, ascending
   for (int size = 2; size <= P; size <<= 1)
@@ -815,7 +822,7 @@ k_scale_chain(const double* __restrict__ kp_ref, const double* __restrict__ kp_c
   if (t == 0) res[TR_NVALID] = (double)total_s;
 }
 
-size_t essential_tail_workspace_bytes(int N) { return (size_t)N * 8 * 3 + (size_t)N * 4 + 9 * 8 + 12 * 8 + 1024; }
+size_t essential_tail_workspace_bytes(int N) { return (size_t)N * 8 * 4 + (size_t)N * 4 + 9 * 8 + 12 * 8 + 1024; }
 
 int essential_tail(const double* E, const int32_t* info, const double* gric, int R, const double* kp_cur, const double* kp_ref, int N,
                    double fx, double fy, double cx, double cy, const double* h_gric, const float* depth, int H, int W, int min_samples,
@@ -830,6 +837,7 @@ int essential_tail(const double* E, const int32_t* info, const double* gric, int
   double* dbuf = (double*)take((size_t)N * 8);
   double* ratio = (double*)take((size_t)N * 8);
   int32_t* perm = (int32_t*)take((size_t)N * 4);
+  unsigned long long* keys = (unsigned long long*)take((size_t)N * 8);
   double* E_best = (double*)take(9 * 8);
   double* T21 = (double*)take(12 * 8);
   DFVO_LAUNCH(k_track_pick, dim3(1), dim3(32), 0, s, info, gric, E, R, res, E_best);
@@ -837,7 +845,9 @@ int essential_tail(const double* E, const int32_t* info, const double* gric, int
   DFVO_LAUNCH(k_recover_pose_vote, dim3(cdiv(4 * N, 256)), dim3(256), 0, s, (const double*)E_best, kp_cur, kp_ref, N, fx, cx, cy, 50.0, pose_mask, pose_info);
   DFVO_LAUNCH(k_recover_pose_pick, dim3(cdiv(N, 256)), dim3(256), 0, s, (const double*)E_best, N, res + TR_RT, pose_mask, pose_info);
   DFVO_LAUNCH(k_track_gate, dim3(1), dim3(32), 0, s, res, (const int32_t*)pose_info, h_gric, R, N, T21);
-  DFVO_LAUNCH(k_scale_chain, dim3(1), dim3(SC_THREADS), 0, s, kp_ref, kp_cur, N, fx, fy, cx, cy, (const double*)T21, depth, H, W, res, zbuf, dbuf, ratio);
+  DFVO_LAUNCH(k_scale_points, dim3(cdiv(N, 128)), dim3(128), 0, s, kp_ref, kp_cur, N, fx, fy, cx, cy, (const double*)T21, depth, H, W,
+              (const double*)res, zbuf, dbuf, keys);
+  DFVO_LAUNCH(k_scale_chain, dim3(1), dim3(SC_THREADS), 0, s, (const unsigned long long*)keys, N, res, (const double*)zbuf, (const double*)dbuf, ratio);
   DFVO_LAUNCH(k_scale_ransac, dim3(1), dim3(SR_THREADS), 0, s, (const double*)ratio, N, min_samples, max_trials, stop_prob, thr, res, perm,
               (const double*)(res + TR_NVALID), (const double*)(res + TR_GATE));
   DFVO_CHECK_LAUNCH();

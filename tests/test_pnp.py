@@ -34,7 +34,7 @@ def test_scale_ransac_on_device_vs_sklearn(hostsim_lib):
 
 
 def test_fused_tracker_tail_vs_stepwise(hostsim_lib):
-    pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib))
+    pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib), only=("out00", "still"))
 
 
 def test_pnp_tracker_vs_reference_golden(hostsim_lib):
