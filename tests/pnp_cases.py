@@ -252,3 +252,33 @@ def check_fused_tail_vs_stepwise(engine, only=None):
             seen_scale += 1
     assert seen_scale >= (1 if only else 2) and seen_reject >= 1
     return seen_scale, seen_reject
+
+
+def check_coop_five_point_vs_sequential(engine):
+    """csrc/fivept.cuh::solve_coop (10 lanes per minimal sample) against the one-thread-per-sample solver inside the full RANSAC
+    (DFVO_HYP_COOP is read per call): same inlier masks, iteration counts and GRIC, E to 1e-10 -- on the CPU emulation build, where
+    the cooperative kernel is not the default because every shuffle is a fiber switch."""
+    import os
+    K = synthdata.kitti_intrinsics()
+    kp_ref, kp_cur, _ = synthdata.correspondences(seed=32, n=600, outlier_frac=0.3)
+    n = kp_ref.shape[0]
+    rt = engine.rt
+    b_ref, b_cur = rt.from_host(kp_ref), rt.from_host(kp_cur)
+    np.random.seed(3)
+    perms = [np.random.permutation(n) for _ in range(2)]
+    res = {}
+    prev = os.environ.get("DFVO_HYP_COOP")
+    try:
+        for coop in ("0", "1"):
+            os.environ["DFVO_HYP_COOP"] = coop
+            w = engine.essential_launch(b_cur, b_ref, n, perms, K, threshold=0.2)
+            res[coop] = (w["E"].numpy().copy(), w["mask"].numpy().copy(), w["info"].numpy().copy(), w["gric"].numpy().copy())
+    finally:
+        if prev is None:
+            os.environ.pop("DFVO_HYP_COOP", None)
+        else:
+            os.environ["DFVO_HYP_COOP"] = prev
+    a, b = res["0"], res["1"]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.abs(a[0] - b[0]).max() < 1e-10 and np.abs(a[3] - b[3]).max() <= 1e-9 * np.abs(a[3]).max()
+    return int(a[2][0, 1])

@@ -33,6 +33,11 @@ def test_scale_ransac_on_device_vs_sklearn(hostsim_lib):
     print("scale RANSAC vs sklearn: worst relative difference %.2e" % worst)
 
 
+def test_cooperative_five_point_vs_sequential(hostsim_lib):
+    iters = pnp_cases.check_coop_five_point_vs_sequential(_engine(hostsim_lib))
+    print("RANSAC iterations:", iters)
+
+
 def test_fused_tracker_tail_vs_stepwise(hostsim_lib):
     pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib), only=("out00", "still"))
 
