@@ -857,7 +857,11 @@ def run_b200(args):
         roofline=dict(kernel="k_conv_halo / k_conv_tc (tcgen05 implicit-GEMM conv, %d launches/frame)" % (tc_n.value // prof_steps), bound="tensor",
                       achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf if peak_tf else None, traffic=traffic,
                       traffic_source=traffic_src, peak_source=peak_src, algorithmic_gflop_per_frame=tc_fl.value / prof_steps / 1e9,
-                      kernel_ms_per_frame=tc_ms.value / prof_steps, share_of_step=(tc_ms.value / prof_steps) / (ms / args.steps)),
+                      kernel_ms_per_frame=tc_ms.value / prof_steps,
+                      # share of the step of the pipeline the events were taken in (in order, one stream); the overlapped pipelines run
+                      # the convolutions of up to three frames side by side, so their step is shorter than one frame's conv time
+                      share_of_in_order_step=((tc_ms.value / prof_steps) / inorder["latency_ms"]) if inorder else None,
+                      conv_ms_over_overlapped_step=(tc_ms.value / prof_steps) / (ms / args.steps)),
         cpu_baseline=base,
         gpu_library_baseline=gpu_lib,
         extra_configs=extra_cfg,

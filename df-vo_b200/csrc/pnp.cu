@@ -316,7 +316,7 @@ DFVO_HD bool solve(int n, const double pw[][3], const double uv[][2], double fu,
 //   * the three beta approximations + Gauss-Newton + absolute orientation run on lanes 0, 1, 2 in parallel; the winner (first
 //     strictly smaller reprojection error, as in the sequential loop) is broadcast.
 // Control flow around the shuffles is warp-uniform, so the CPU emulation build runs it unchanged with one warp per block.
-struct CoopSm { double u[12][16], v[12][16], w[12][16]; };
+struct CoopSm { double u[12][32], v[12][32], w[12][32]; };      // one private column slot per lane (lanes 16..31 mirror 0..15)
 #define EP_FULL 0xffffffffu
 DFVO_D double grp_sum(double x) {                // lanes 0..15 (lanes 16..31 mirror them)
   x += __shfl_xor_sync(EP_FULL, x, 8); x += __shfl_xor_sync(EP_FULL, x, 4);
@@ -325,20 +325,21 @@ DFVO_D double grp_sum(double x) {                // lanes 0..15 (lanes 16..31 mi
 }
 
 // arow: row gl of the symmetric A (= this lane's column of At); vout[k]: this lane's element of null vector k (Ut[11 - k][gl])
-DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, double vout[4]) {
+DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int lane, double vout[4]) {
+  const int gl = lane & 15;
   const double eps = 2.220446049250313e-16 * 10, eps2 = eps * eps;
   for (int i = 0; i < 12; ++i) {
     const double t = gl < 12 ? arow[i] : 0.0;
-    sm.u[i][gl] = t;
-    sm.v[i][gl] = (i == gl) ? 1.0 : 0.0;
-    sm.w[i][gl] = grp_sum(t * t);
+    sm.u[i][lane] = t;
+    sm.v[i][lane] = (i == gl) ? 1.0 : 0.0;
+    sm.w[i][lane] = grp_sum(t * t);
   }
   for (int iter = 0; iter < 30; ++iter) {
     bool changed = false;
     for (int i = 0; i < 11; ++i)
       for (int j = i + 1; j < 12; ++j) {
-        const double ui = sm.u[i][gl], uj = sm.u[j][gl];
-        const double a = sm.w[i][gl], b = sm.w[j][gl];
+        const double ui = sm.u[i][lane], uj = sm.u[j][lane];
+        const double a = sm.w[i][lane], b = sm.w[j][lane];
         double p = grp_sum(ui * uj);
         if (p * p <= eps2 * (a * b)) continue;                    // |p| <= eps sqrt(a b)
         p *= 2;
@@ -350,22 +351,22 @@ DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, double vout[4]
         const double rq = rsqrt(q), big = q * rq, small_ = 0.5 * p * rg * rq;
         const double c = beta < 0 ? small_ : big, s = beta < 0 ? big : small_;
         const double t0 = c * ui + s * uj, t1 = -s * ui + c * uj;
-        sm.u[i][gl] = t0; sm.u[j][gl] = t1;
+        sm.u[i][lane] = t0; sm.u[j][lane] = t1;
         double a2 = t0 * t0, b2 = t1 * t1;                       // two independent butterflies in flight
         a2 += __shfl_xor_sync(EP_FULL, a2, 8); b2 += __shfl_xor_sync(EP_FULL, b2, 8);
         a2 += __shfl_xor_sync(EP_FULL, a2, 4); b2 += __shfl_xor_sync(EP_FULL, b2, 4);
         a2 += __shfl_xor_sync(EP_FULL, a2, 2); b2 += __shfl_xor_sync(EP_FULL, b2, 2);
         a2 += __shfl_xor_sync(EP_FULL, a2, 1); b2 += __shfl_xor_sync(EP_FULL, b2, 1);
-        sm.w[i][gl] = a2; sm.w[j][gl] = b2;
+        sm.w[i][lane] = a2; sm.w[j][lane] = b2;
         changed = true;
-        const double vi = sm.v[i][gl], vj = sm.v[j][gl];
-        sm.v[i][gl] = c * vi + s * vj; sm.v[j][gl] = -s * vi + c * vj;
+        const double vi = sm.v[i][lane], vj = sm.v[j][lane];
+        sm.v[i][lane] = c * vi + s * vj; sm.v[j][lane] = -s * vi + c * vj;
       }
     if (!changed) break;                                          // warp-uniform
   }
   double W[12];
   int perm[12];
-  for (int i = 0; i < 12; ++i) { const double t = sm.u[i][gl]; W[i] = sqrt(grp_sum(t * t)); perm[i] = i; }
+  for (int i = 0; i < 12; ++i) { const double t = sm.u[i][lane]; W[i] = sqrt(grp_sum(t * t)); perm[i] = i; }
   for (int i = 0; i < 11; ++i) {                                 // the selection sort of ocv_svd, on a row permutation
     int j = i;
     for (int k = i + 1; k < 12; ++k) if (W[j] < W[k]) j = k;
@@ -373,7 +374,7 @@ DFVO_D void svd12_coop(const double arow[12], CoopSm& sm, int gl, double vout[4]
   }
   for (int k = 0; k < 4; ++k) {
     const double sc = W[11 - k] > 2.2250738585072014e-308 ? 1.0 / W[11 - k] : 0.0;
-    vout[k] = sm.u[perm[11 - k]][gl] * sc;
+    vout[k] = sm.u[perm[11 - k]][lane] * sc;
   }
 }
 
@@ -387,7 +388,7 @@ DFVO_D bool solve_coop(const double pw[][3], const double uv[][2], double fu, do
     for (int p = 0; p < 5; ++p) for (int j = 0; j < 4; ++j) c.al[p][j] = 0.25;
   double row[12], vout[4];
   mtm_row(c, gl < 12 ? gl : 0, row);
-  svd12_coop(row, sm, gl, vout);
+  svd12_coop(row, sm, lane, vout);
   for (int k = 0; k < 4; ++k)
     for (int i = 0; i < 12; ++i) c.v[k][i] = __shfl_sync(EP_FULL, vout[k], i);
   double L[6][10], rho[6];

@@ -35,6 +35,7 @@ def main():
         assert np.isfinite(fwd.numpy()).all() and np.isfinite(d).all()
         print("nets ok (chains %d)" % chain, flush=True)
     rt.lib.dfvo_set_conv_chain(0)
+    eng = tracking.Engine(376, 1241, rt)              # the synthetic correspondences / depths are KITTI-sized
     for seed, outl, still in [(31, 0.0, False), (33, 0.6, False), (34, 0.1, True)]:
         kp_ref, kp_cur, info = synthdata.correspondences(n=600, seed=seed, outlier_frac=outl, zero_motion=still)
         np.random.seed(4869)
@@ -45,7 +46,17 @@ def main():
         dd = depth[ki[ok, 1], ki[ok, 0]]
         keep = dd > 0
         T, ninl = tracking.compute_pose_3d2d(eng, kp_ref[ok][keep], kp_cur[ok][keep], dd[keep], synthdata.kitti_intrinsics())
-        print("trackers ok (outliers %.1f still %d): E inliers %d, PnP inliers %d" % (outl, still, int(r["inliers"].sum()), ninl), flush=True)
+        # the fused device-side tail (recoverPose, vote, depth ratios incl. the block sort, scale RANSAC with the MT19937 stream)
+        n = kp_ref.shape[0]
+        np.random.seed(4869)
+        perms = [np.random.permutation(n) for _ in range(5)]
+        b_ref, b_cur = rt.from_host(kp_ref), rt.from_host(kp_cur)
+        b_depth = rt.from_host(np.ascontiguousarray(depth, np.float32))
+        h = eng.homography_launch(b_cur, b_ref, n)
+        w = eng.essential_launch(b_cur, b_ref, n, perms, synthdata.kitti_intrinsics(), threshold=0.2)
+        o = eng.essential_tail(w, h, b_cur, b_ref, n, synthdata.kitti_intrinsics(), b_depth, np.random)
+        print("trackers ok (outliers %.1f still %d): E inliers %d, PnP inliers %d, fused tail: valid %s scale %.4f status %d" %
+              (outl, still, int(r["inliers"].sum()), ninl, o["valid"], o["scale"], o["scale_status"]), flush=True)
     print("sanitize_run done")
 
 
