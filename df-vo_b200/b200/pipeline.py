@@ -424,7 +424,8 @@ class FramePipeline:
         pose = None
         with self.rt.on_stream(self.s_nets[fid % len(self.engs)]):
             self._depth_done = None
-            cur = self.infer(img, fid)                      # uses self.ref (previous image) for the flow pair
+            with self.rt.nvtx("dfvo.infer"):
+                cur = self.infer(img, fid)                  # uses self.ref (previous image) for the flow pair
             if self._depth_done is not None:                # join the depth side stream
                 self.rt.wait_event(self._depth_done)
             cur.ready = self.rt.record_event()
@@ -444,14 +445,14 @@ class FramePipeline:
 
     def _launch_oldest(self):
         nxt = self.pending.pop(0)
-        with self.rt.on_stream(self.s_trk):
+        with self.rt.on_stream(self.s_trk), self.rt.nvtx("dfvo.track_launch"):
             self.rt.wait_event(nxt.ready)
             self._tok = self._advance_launch(nxt, self.trk_ref)
         self.trk_ref = nxt
 
     def _finish_inflight(self):
         launched, self._tok = self._tok, None
-        with self.rt.on_stream(self.s_trk):
+        with self.rt.on_stream(self.s_trk), self.rt.nvtx("dfvo.track_finish"):
             return self._advance_finish(launched)
 
     # ---- tracker thread -------------------------------------------------------------------------------------------------
@@ -514,7 +515,7 @@ class FramePipeline:
 
     def _track_oldest(self):
         nxt = self.pending.pop(0)
-        with self.rt.on_stream(self.s_trk):
+        with self.rt.on_stream(self.s_trk), self.rt.nvtx("dfvo.track"):
             self.rt.wait_event(nxt.ready)
             pose = self._advance(nxt, self.trk_ref)
         self.trk_ref = nxt

@@ -7,6 +7,7 @@ to exist without a CUDA device.  The CPU test-suite injects the host-emulation r
 exercised without a GPU -- that object lives in the test tree, not here.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -95,6 +96,16 @@ class CudaRuntime:
         return Buf(t, arr.shape, arr.dtype, self)
 
     PINNED_STAGE_MAX = 1 << 20
+
+    def nvtx(self, name):
+        """NVTX range around a pipeline stage when DFVO_NVTX=1 (for `ncu --nvtx` / Nsight timelines); a null context otherwise."""
+        import contextlib
+        if not getattr(self, "_nvtx_on", None):
+            if getattr(self, "_nvtx_on", None) is None:
+                self._nvtx_on = os.environ.get("DFVO_NVTX", "0") == "1"
+            if not self._nvtx_on:
+                return contextlib.nullcontext()
+        return self.torch.cuda.nvtx.range(name)
 
     def upload(self, buf, arr):
         torch = self.torch

@@ -45,6 +45,10 @@ class HostsimRuntime:
     def sync(self):
         pass
 
+    def nvtx(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
     # streams / events: the emulation is synchronous, so these are no-ops with the CudaRuntime signatures
     def new_stream(self, high_priority=False):
         return None
