@@ -1,6 +1,7 @@
 // Memory-bound kernels of the LiteFlowNet path: image prep / resizes, depthwise deconv, backward
 // warp, 49-channel correlation, Regularization prep + tail, final flow upsample and the
 // forward-backward consistency map.  Reference lines are cited per kernel; layouts are NHWC.
+#include <stdlib.h>
 #include "ops.h"
 
 namespace dfvo {
@@ -631,12 +632,123 @@ k_flow_head(Ten<const bf16> in, const float* __restrict__ w, float b0, float b1,
   o[1] = a1 + b1 + r1;
 }
 
+
+#ifndef DFVO_HOSTSIM
+// Register-blocked variant for the device: a thread owns EIGHT output rows of one column, so an input pixel chunk is read from
+// shared memory once per kx and feeds up to 7 x 8 (ky, output row) pairs, and a weight vector once per tap for eight outputs; the
+// two output channels share one packed fma.rn.f32x2 (the pair (w[c][0], w[c][1]) is one 64-bit shared-memory word).  The first
+// kernel above issues 20 LDS.128 per 64 FFMA (shared-memory bound: ncu, 77 us for the 7x7 head at 2x176x608); this one
+// ~0.2 LDS per packed FMA.  Patch layout: [channel chunk q][row][pixel] x 16 B, so the lanes of a warp (consecutive pixels) read
+// consecutive 16-byte words: conflict-free.  Block = 4 warps = 32 columns x 32 rows of outputs.
+#define FH8_TW 32
+#define FH8_RPT 8
+#define FH8_WY 4
+__device__ __forceinline__ void fh_ffma2(unsigned long long& acc, float f, unsigned long long w) {
+  unsigned long long ff;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ff) : "f"(f));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ff), "l"(w));
+}
+template <int K>
+__global__ void __launch_bounds__(32 * FH8_WY, 2)
+k_flow_head8(Ten<const bf16> in, const float* __restrict__ w, float b0, float b1, Ten<const float> res, int has_res, Ten<float> out) {
+  constexpr int TH = FH8_RPT * FH8_WY, PW = FH8_TW + K - 1, PH = TH + K - 1, R = K / 2, NI = FH8_RPT + K - 1;
+  DFVO_DYN_SMEM(uint4, smem4);
+  uint4* patch = smem4;                                                    // [4][PH][PW]
+  float* ws = reinterpret_cast<float*>(smem4 + 4 * PH * PW);               // [K*K][32][2]
+  const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+  const int x0 = blockIdx.x * FH8_TW, y0 = blockIdx.y * TH, n = blockIdx.z;
+  for (int i = tid; i < K * K * 64; i += 32 * FH8_WY) ws[i] = w[i];
+  for (int i = tid; i < PH * PW * 4; i += 32 * FH8_WY) {
+    const int q = i & 3, pp = i >> 2;
+    const int py = pp / PW, px = pp - py * PW;
+    const int sx = x0 + px - R, sy = y0 + py - R;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (sx >= 0 && sx < in.W && sy >= 0 && sy < in.H) v = *reinterpret_cast<const uint4*>(in.at(n, sy, sx) + q * 8);
+    patch[(q * PH + py) * PW + px] = v;
+  }
+  __syncthreads();
+  unsigned long long acc[FH8_RPT];
+#pragma unroll
+  for (int r = 0; r < FH8_RPT; ++r) acc[r] = 0ull;
+#pragma unroll 1
+  for (int kx = 0; kx < K; ++kx) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const uint4* col = patch + (q * PH + wy * FH8_RPT) * PW + lane + kx;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {                               // four channels at a time: 4 x NI unpacked floats live
+        float f[NI][4];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const uint4 v = col[i * PW];
+          const uint32_t u0 = half ? v.z : v.x, u1 = half ? v.w : v.y;
+          f[i][0] = __uint_as_float(u0 << 16); f[i][1] = __uint_as_float(u0 & 0xffff0000u);
+          f[i][2] = __uint_as_float(u1 << 16); f[i][3] = __uint_as_float(u1 & 0xffff0000u);
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          // channels q*8 + half*4 + {0..3}: (c,0) (c,1) pairs = 4 x 64-bit words = 2 x 128-bit loads (broadcast)
+          const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(ws + (ky * K + kx) * 64 + (q * 8 + half * 4) * 2);
+          const ulonglong2 w01 = wp[0], w23 = wp[1];
+#pragma unroll
+          for (int r = 0; r < FH8_RPT; ++r) {
+            fh_ffma2(acc[r], f[r + ky][0], w01.x);
+            fh_ffma2(acc[r], f[r + ky][1], w01.y);
+            fh_ffma2(acc[r], f[r + ky][2], w23.x);
+            fh_ffma2(acc[r], f[r + ky][3], w23.y);
+          }
+        }
+      }
+    }
+  }
+  const int ox = x0 + lane;
+  if (ox >= out.W) return;
+#pragma unroll
+  for (int r = 0; r < FH8_RPT; ++r) {
+    const int oy = y0 + wy * FH8_RPT + r;
+    if (oy >= out.H) break;
+    float a0, a1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc[r]));
+    float r0 = 0.f, r1 = 0.f;
+    if (has_res) { const float* rr = res.at(n, oy, ox); r0 = rr[0]; r1 = rr[1]; }
+    float* o = out.at(n, oy, ox);
+    o[0] = a0 + b0 + r0;
+    o[1] = a1 + b1 + r1;
+  }
+}
+#endif
+
 int flow_head(Ten<const bf16> in, const float* w, float bias0, float bias1, int k, Ten<const float> residual, Ten<float> out,
               cudaStream_t s) {
   DFVO_REQUIRE(in.C == 32 && (k == 3 || k == 5 || k == 7) && in.H == out.H && in.W == out.W && in.sW % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(in.p) & 15) == 0, DFVO_ESHAPE, "flow_head shapes");
   const float hb[2] = {bias0, bias1};
   const int has_res = residual.p != nullptr;
+#ifndef DFVO_HOSTSIM
+  {
+    // big maps: the register-blocked kernel (DFVO_FLOW_HEAD8=0 keeps the first one; small maps stay on it -- fewer, fuller blocks).
+    // The choice depends on the size of ONE image, not on the batch: a pair gives the same bits alone and inside a batch.
+    static int use8 = -1;
+    if (use8 < 0) { const char* e = getenv("DFVO_FLOW_HEAD8"); use8 = !(e && atoi(e) == 0); }
+    if (use8 && (long long)out.H * out.W >= 20000) {
+      static bool attr8 = false;
+      if (!attr8) {
+        cudaFuncSetAttribute(k_flow_head8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_flow_head8<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_flow_head8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        attr8 = true;
+      }
+      const int TH = FH8_RPT * FH8_WY;
+      dim3 grid8(cdiv(out.W, FH8_TW), cdiv(out.H, TH), out.N), block8(32 * FH8_WY);
+      const size_t smem8 = (size_t)4 * (TH + k - 1) * (FH8_TW + k - 1) * 16 + (size_t)k * k * 64 * 4;
+      if (k == 7) { auto kn = k_flow_head8<7>; DFVO_LAUNCH(kn, grid8, block8, smem8, s, in, w, hb[0], hb[1], residual, has_res, out); }
+      else if (k == 5) { auto kn = k_flow_head8<5>; DFVO_LAUNCH(kn, grid8, block8, smem8, s, in, w, hb[0], hb[1], residual, has_res, out); }
+      else { auto kn = k_flow_head8<3>; DFVO_LAUNCH(kn, grid8, block8, smem8, s, in, w, hb[0], hb[1], residual, has_res, out); }
+      DFVO_CHECK_LAUNCH();
+      return DFVO_OK;
+    }
+  }
+#endif
   dim3 grid(cdiv(out.W, FH_TW), cdiv(out.H, FH_TH), out.N), block(FH_TW * FH_TH);
   const size_t smem = ((size_t)(FH_TH + k - 1) * (FH_TW + k - 1) * 20 + (size_t)k * k * 64) * 4;
 #ifndef DFVO_HOSTSIM
