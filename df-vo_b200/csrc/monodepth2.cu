@@ -114,7 +114,9 @@ struct MonoImpl : public Monodepth2Base {
 
   int build(const WeightStore& ws, int feed_h, int feed_w, float mind, float maxd, float base) {
     h = feed_h; w = feed_w; min_depth = mind; max_depth = maxd; baseline = base;
-    DFVO_REQUIRE(h % 32 == 0 && w % 32 == 0 && h >= 32 && w >= 32, DFVO_ESHAPE, "monodepth2 feed size must be a multiple of 32");
+    // >= 64: the decoder reflection-pads the 1/32-resolution map by one pixel, which needs at least two rows and columns
+    // (torch.nn.ReflectionPad2d refuses a 1-pixel map the same way)
+    DFVO_REQUIRE(h % 32 == 0 && w % 32 == 0 && h >= 64 && w >= 64, DFVO_ESHAPE, "monodepth2 feed size must be a multiple of 32 and at least 64x64 (got %dx%d)", h, w);
     TRYM(bn_conv(ws, "encoder.conv1", "encoder.bn1", 3, 2, 3, false, &conv1));
     {
       const char* e = getenv("DFVO_MONO_STEM_TC");

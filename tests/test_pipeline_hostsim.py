@@ -88,7 +88,7 @@ def test_pipeline_real_infer_plumbing(hostsim_lib):
     rt_mod.set_runtime(rt)
     h, w = 64, 96
     K = synthdata.kitti_intrinsics(h, w)
-    enc, dec = synthdata.monodepth2_weights(4869, 32, 64)
+    enc, dec = synthdata.monodepth2_weights(4869, 64, 96)      # feed >= 64: the decoder reflection-pads the 1/32 map
     p = pipeline.FramePipeline(K, h, w, precision=native.PREC_FP32, runtime=rt)
     p.load_weights(synthdata.liteflownet_weights(), enc, dec)
     frames = [synthdata.value_noise_image(h, w, 11), synthdata.value_noise_image(h, w, 12)]
