@@ -117,22 +117,31 @@ class CudaRuntime:
         if nbytes == 0 or nbytes > self.PINNED_STAGE_MAX or not buf.t.is_contiguous():
             buf.t.copy_(torch.from_numpy(a))
             return
-        # Small host arrays (shuffles, generator state, poses) go through a pinned staging buffer per destination and an
-        # asynchronous copy: a copy from pageable memory blocks the host until everything queued before it on the stream has run
-        # (measured: 0.3 ms per tracker launch).  The staging buffer is reused only after its previous copy has executed.
-        if not hasattr(self, "_stage"):
-            self._stage = {}
-        key = buf.t.data_ptr()
-        ent = self._stage.get(key)
-        if ent is None or ent[0].numel() < nbytes:
-            cap = 4096
-            while cap < nbytes:
-                cap *= 2
-            ent = self._stage[key] = [torch.empty((cap,), dtype=torch.uint8, pin_memory=True), None]
-        stage, ev = ent
-        if ev is not None:
-            ev.synchronize()
-        host = stage[:nbytes]
+        # Small host arrays (shuffles, generator state, poses) go through a pinned staging buffer and an asynchronous copy: a copy
+        # from pageable memory blocks the host until everything queued before it on the stream has run (measured: 0.3 ms per
+        # tracker launch).  Staging buffers come from a small pool per size class and are reused only after the copy out of them
+        # has executed (an event per buffer); the pool is bounded, so neither pinned allocations (~1 ms each) nor memory grow
+        # with the number of destinations.
+        if not hasattr(self, "_stage_pool"):
+            self._stage_pool = {}
+        cap = 4096
+        while cap < nbytes:
+            cap *= 2
+        pool = self._stage_pool.setdefault(cap, [])
+        ent = None
+        for cand in pool:
+            if cand[1] is None or cand[1].query():
+                ent = cand
+                break
+        if ent is None:
+            if len(pool) < 8:
+                ent = [torch.empty((cap,), dtype=torch.uint8, pin_memory=True), None]
+                pool.append(ent)
+            else:
+                ent = pool.pop(0)                       # the oldest: wait for its copy
+                ent[1].synchronize()
+                pool.append(ent)
+        host = ent[0][:nbytes]
         host.numpy().view(a.dtype).reshape(a.shape)[...] = a
         buf.t.view(torch.uint8).reshape(-1)[:nbytes].copy_(host, non_blocking=True)
         e = torch.cuda.Event()
