@@ -492,15 +492,10 @@ k_pnp_hypotheses_coop(const double* __restrict__ objp, const double* __restrict_
   }
 }
 
-// DFVO_PNP_COOP=0/1 (default: cooperative on the device, one thread per sample in the CPU emulation build where every shuffle
-// is a fiber switch); read per call so tests can compare the two paths
+// DFVO_PNP_COOP=0 selects the one-thread-per-sample kernel; read per call so tests can compare the two paths
 static bool pnp_coop_enabled() {
   const char* e = getenv("DFVO_PNP_COOP");
-#ifdef DFVO_HOSTSIM
-  return e && atoi(e) == 1;
-#else
   return !(e && atoi(e) == 0);
-#endif
 }
 
 static int pnp_hypotheses(const double* objp, const double* imgp, const int32_t* subsets, int N, int R, int iters, double fx, double fy,

@@ -338,15 +338,9 @@ int essential_ransac(const double* p1, const double* p2, int N, const int32_t* p
   for (int rd = 0; rd < 3; ++rd) {
     const int i0 = bounds[rd], i1 = bounds[rd + 1];
     if (i1 <= i0) continue;
-    // DFVO_HYP_COOP, read per call: the device build defaults to the warp-cooperative solver; the CPU emulation build (where every
-    // shuffle is a fiber switch: ~50x the cost of the one-thread-per-sample kernel) defaults to the sequential one and runs the
-    // cooperative kernel where a test asks for it (tests/test_hostsim.py)
+    // DFVO_HYP_COOP=0 selects the one-thread-per-sample solver (read per call so a test can compare the two paths)
     const char* e_coop = getenv("DFVO_HYP_COOP");
-#ifdef DFVO_HOSTSIM
-    const int coop = (e_coop && atoi(e_coop) == 1) ? 1 : 0;
-#else
     const int coop = !(e_coop && atoi(e_coop) == 0);
-#endif
     if (coop)
       DFVO_LAUNCH(k_hypotheses_coop, dim3(cdiv(i1 - i0, HYP_WARPS * 3), R), dim3(HYP_WARPS * 32), 0, s, x1n, x2n, subsets, N, i0, i1, st, Ecand,
                   ncand, max_iters);

@@ -263,7 +263,7 @@ int dfvo_pnp_ransac(const double* obj, const double* img, int N, const int32_t* 
 /* Stage entry for parity tests: the minimal solver inside solvePnPRansac -- cv2.solvePnP(obj5, img5, K, None,
  * flags=SOLVEPNP_EPNP) -- on M independent 5-point samples.  obj [M*5][3], img [M*5][2] float64 on the device ->
  * rt [M][12] = R (row-major), t; ok [M].  coop: 1 = lane-cooperative kernel (one warp per sample), 0 = one thread per sample,
- * -1 = what dfvo_pnp_ransac uses (env DFVO_PNP_COOP; cooperative on the device). */
+ * -1 = what dfvo_pnp_ransac uses (cooperative unless env DFVO_PNP_COOP=0). */
 int dfvo_epnp_minimal(const double* obj, const double* img, int M, double fx, double fy, double cx, double cy, int coop,
                       double* rt, int32_t* ok, void* stream);
 

@@ -256,8 +256,7 @@ def check_fused_tail_vs_stepwise(engine, only=None):
 
 def check_coop_five_point_vs_sequential(engine):
     """csrc/fivept.cuh::solve_coop (10 lanes per minimal sample) against the one-thread-per-sample solver inside the full RANSAC
-    (DFVO_HYP_COOP is read per call): same inlier masks, iteration counts and GRIC, E to 1e-10 -- on the CPU emulation build, where
-    the cooperative kernel is not the default because every shuffle is a fiber switch."""
+    (DFVO_HYP_COOP is read per call): same inlier masks, iteration counts and GRIC, E to 1e-10."""
     import os
     K = synthdata.kitti_intrinsics()
     kp_ref, kp_cur, _ = synthdata.correspondences(seed=32, n=600, outlier_frac=0.3)

@@ -29,7 +29,7 @@ def test_epnp_cooperative_vs_sequential_vs_cv2(hostsim_lib):
 
 
 def test_scale_ransac_on_device_vs_sklearn(hostsim_lib):
-    worst = pnp_cases.check_scale_ransac_vs_sklearn(_engine(hostsim_lib), cases=24)
+    worst = pnp_cases.check_scale_ransac_vs_sklearn(_engine(hostsim_lib), cases=60)
     print("scale RANSAC vs sklearn: worst relative difference %.2e" % worst)
 
 
@@ -39,7 +39,7 @@ def test_cooperative_five_point_vs_sequential(hostsim_lib):
 
 
 def test_fused_tracker_tail_vs_stepwise(hostsim_lib):
-    pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib), only=("out00", "still"))
+    pnp_cases.check_fused_tail_vs_stepwise(_engine(hostsim_lib))
 
 
 def test_pnp_tracker_vs_reference_golden(hostsim_lib):
