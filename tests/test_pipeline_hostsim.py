@@ -105,3 +105,43 @@ def test_pipeline_real_infer_plumbing(hostsim_lib):
     assert np.array_equal(d_host, d_dev)
     raw = p.ref.raw_depth.numpy()
     assert raw.shape == (h, w) and np.all(np.isfinite(raw)) and raw.max() > 0
+
+
+def test_pipelined_three_engines_real_infer_equals_in_order(hostsim_lib):
+    """The bench's default mode -- three network engines in flight, tracker split into enqueue / read halves -- with the real
+    (un-injected) infer path on small frames gives the poses of the in-order pipeline, frame by frame, and hands them out
+    `lag` = 4 steps late; flush() returns the rest."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    from runtime import HostsimRuntime
+    import synthdata
+    from b200 import native, pipeline, runtime as rt_mod
+    rt = HostsimRuntime(hostsim_lib)
+    rt_mod.set_runtime(rt)
+    h, w = 64, 96
+    K = synthdata.kitti_intrinsics(h, w)
+    enc, dec = synthdata.monodepth2_weights(4869, 64, 96)
+    flow_w = synthdata.liteflownet_weights()
+    frames = [synthdata.value_noise_image(h, w, 40 + i) for i in range(7)]
+
+    def run(**kw):
+        np.random.seed(5)
+        p = pipeline.FramePipeline(K, h, w, precision=native.PREC_FP32, runtime=rt, **kw)
+        p.load_weights(flow_w, enc, dec)
+        out = []
+        for f in frames:
+            r = p.step(f)
+            if r is not None:
+                out.append(r.copy())
+        tail = p.flush() if kw.get("overlap") else None
+        for q in (tail if isinstance(tail, list) else [tail]):
+            if q is not None:
+                out.append(q.copy())
+        return p, out, [p.poses[i] for i in sorted(p.poses)]
+
+    pa, oa, alla = run()
+    pb, ob, allb = run(overlap=True, inflight=3, pipelined=True)
+    assert pb.lag == 4 and pb.nslots == 6
+    assert len(oa) == len(frames) and len(ob) == len(frames) and len(allb) == len(frames)
+    for i in range(len(frames)):
+        assert np.array_equal(alla[i], allb[i]), "pose of frame %d differs between the in-order and the pipelined three-engine mode" % i
+        assert np.array_equal(oa[i], ob[i])
