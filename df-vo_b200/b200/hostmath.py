@@ -115,7 +115,9 @@ def _fit_through_origin(x, y):
 
 
 def ransac_scale(x, min_samples=3, max_trials=100, stop_probability=0.99, residual_threshold=0.1, rng=np.random):
-    """Fit ``1 ~= s * x`` like ``RANSACRegressor(...).fit(x[:,None], ones)`` (E_tracker.py:626-636) and
+    """Host statement of the scale fit that ``tracking.Engine.ransac_scale`` runs on the device (csrc/ransac.cu::k_scale_ransac);
+    nothing on the product path calls it any more -- the tests use it as the readable twin of the kernel.
+    Fit ``1 ~= s * x`` like ``RANSACRegressor(...).fit(x[:,None], ones)`` (E_tracker.py:626-636) and
     return ``estimator_.coef_[0,0]``.  Same trial loop, same acceptance rule (more inliers, or equal
     inliers and not-worse R^2 score), same dynamic max_trials, same final refit on the best inlier set."""
     x = np.asarray(x, np.float64).reshape(-1)
