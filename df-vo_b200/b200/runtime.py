@@ -123,30 +123,35 @@ class CudaRuntime:
         # has executed (an event per buffer); the pool is bounded, so neither pinned allocations (~1 ms each) nor memory grow
         # with the number of destinations.
         if not hasattr(self, "_stage_pool"):
-            self._stage_pool = {}
+            import threading
+            self._stage_pool, self._stage_lock, self._stage_made = {}, threading.Lock(), {}
         cap = 4096
         while cap < nbytes:
             cap *= 2
-        pool = self._stage_pool.setdefault(cap, [])
+        # take a free staging buffer OUT of the pool while it is in use (the tracker-thread mode uploads from two host threads)
         ent = None
-        for cand in pool:
-            if cand[1] is None or cand[1].query():
-                ent = cand
-                break
+        with self._stage_lock:
+            pool = self._stage_pool.setdefault(cap, [])
+            for i, cand in enumerate(pool):
+                if cand[1] is None or cand[1].query():
+                    ent = pool.pop(i)
+                    break
+            if ent is None and self._stage_made.get(cap, 0) >= 8 and pool:
+                ent = pool.pop(0)                        # all busy: take the oldest and wait for its copy below
+            if ent is None:
+                self._stage_made[cap] = self._stage_made.get(cap, 0) + 1
         if ent is None:
-            if len(pool) < 8:
-                ent = [torch.empty((cap,), dtype=torch.uint8, pin_memory=True), None]
-                pool.append(ent)
-            else:
-                ent = pool.pop(0)                       # the oldest: wait for its copy
-                ent[1].synchronize()
-                pool.append(ent)
+            ent = [torch.empty((cap,), dtype=torch.uint8, pin_memory=True), None]
+        elif ent[1] is not None:
+            ent[1].synchronize()
         host = ent[0][:nbytes]
         host.numpy().view(a.dtype).reshape(a.shape)[...] = a
         buf.t.view(torch.uint8).reshape(-1)[:nbytes].copy_(host, non_blocking=True)
         e = torch.cuda.Event()
         e.record(torch.cuda.current_stream(self.device))
         ent[1] = e
+        with self._stage_lock:
+            self._stage_pool[cap].append(ent)
 
     def to_host(self, buf):
         return buf.t.cpu().numpy()
